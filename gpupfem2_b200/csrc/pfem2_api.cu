@@ -1,0 +1,739 @@
+// pfem2_api.cu -- host side of libpfem2_b200.so: the handle, memory management and the C ABI
+// declared in include/pfem2_b200.h.  Replaces the host methods of the reference's ParticleHandler2D
+// (src/particles/particle_handler_2d.cu:238-423); see DESIGN.md for the pipeline.
+#include "../../include/pfem2_b200.h"
+
+#include "pfem2_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace pfem2 {
+long long g_kernel_launches = 0;
+}
+
+using namespace pfem2;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+} // namespace
+
+struct pfem2_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    pfem2_options opt{};
+
+    // mesh (borrowed) + private repack
+    pfem2_mesh_view mesh{};
+    CellGeom *geom = nullptr;
+    int *node_off = nullptr;      // n_nodes + 1
+    unsigned *node_inc = nullptr; // 3 * n_cells, (3c + i) ascending per node
+    int level = 1, ppc = 1;
+    double sub_step = 1.0;
+    double *centers = nullptr; // 3 * ppc
+    int key_bits = 1;
+
+    // particles: double-buffered SoA
+    int capacity = 0;
+    ParticleSoA soa[2]{};
+    int cur = 0;
+    bool seeded = false;
+
+    // per-step scratch
+    Counters *ctr = nullptr;
+    Counters *host_ctr = nullptr; // pinned mirror
+    cudaEvent_t readback = nullptr;
+    bool readback_pending = false;
+    int host_count = 0; // last count known on the host
+    int host_added = 0;
+    unsigned *keys[2]{}, *vals[2]{};
+    int *cell_count = nullptr;               // n_cells + 1
+    unsigned long long *cell_mask = nullptr; // n_cells + 1
+    unsigned long long *packed = nullptr;    // n_cells + 2 (scan in place)
+    unsigned long long *scan_scratch64 = nullptr;
+    int *cell_start = nullptr; // n_cells + 1
+    int *rs_hist = nullptr;
+    int *rs_scan_scratch = nullptr;
+    double *partial = nullptr; // 9 * n_cells
+
+    // lazily allocated
+    void *aos = nullptr;
+    size_t aos_bytes = 0;
+    double *nodal[4] = {nullptr, nullptr, nullptr, nullptr}; // F.x F.y W.x W.y for pfem2_step_host
+
+    std::vector<void *> owned;
+};
+
+namespace {
+
+#define CU(call)                                                                                                    \
+    do {                                                                                                            \
+        cudaError_t e_ = (call);                                                                                    \
+        if (e_ != cudaSuccess) {                                                                                    \
+            char buf_[512];                                                                                         \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            if (h) h->error = buf_; else g_create_error = buf_;                                                    \
+            return PFEM2_ECUDA;                                                                                     \
+        }                                                                                                           \
+    } while (0)
+
+int fail(pfem2_handle *h, int code, const char *msg)
+{
+    if (h) h->error = msg; else g_create_error = msg;
+    return code;
+}
+
+template <class T> int dev_alloc(pfem2_handle *h, T **p, size_t n)
+{
+    *p = nullptr;
+    CU(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return PFEM2_OK;
+}
+
+int grid_for(long long n, int threads = kThreads, int max_blocks = 148 * 16)
+{
+    long long b = (n + threads - 1) / threads;
+    return (int)std::max<long long>(1, std::min<long long>(b, max_blocks));
+}
+
+int alloc_soa(pfem2_handle *h, ParticleSoA &s, int cap)
+{
+    int rc;
+    if ((rc = dev_alloc(h, &s.x, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.y, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.l0, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.l1, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.l2, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.vx, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.vy, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.cell, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.id, cap))) return rc;
+    return PFEM2_OK;
+}
+
+void free_soa(ParticleSoA &s)
+{
+    cudaFree(s.x); cudaFree(s.y); cudaFree(s.l0); cudaFree(s.l1); cudaFree(s.l2);
+    cudaFree(s.vx); cudaFree(s.vy); cudaFree(s.cell); cudaFree(s.id);
+    s = ParticleSoA{};
+}
+
+void free_particle_scratch(pfem2_handle *h)
+{
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(h->keys[k]); cudaFree(h->vals[k]);
+        h->keys[k] = h->vals[k] = nullptr;
+    }
+    cudaFree(h->rs_hist); cudaFree(h->rs_scan_scratch);
+    h->rs_hist = h->rs_scan_scratch = nullptr;
+}
+
+int alloc_particle_storage(pfem2_handle *h, int cap)
+{
+    int rc;
+    for (int k = 0; k < 2; ++k)
+        if ((rc = alloc_soa(h, h->soa[k], cap))) return rc;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = dev_alloc(h, &h->keys[k], cap))) return rc;
+        if ((rc = dev_alloc(h, &h->vals[k], cap))) return rc;
+    }
+    // the incidence sort at create() reuses keys/vals, so they hold at least 3 * n_cells entries (ensured by caller)
+    if ((rc = dev_alloc(h, &h->rs_hist, rs_hist_elems(cap)))) return rc;
+    if ((rc = dev_alloc(h, &h->rs_scan_scratch, scan_scratch_elems<int>(kRsRadix * rs_num_tiles(cap))))) return rc;
+    h->capacity = cap;
+    return PFEM2_OK;
+}
+
+// grow particle storage to new_cap, preserving the current buffer's live prefix
+int grow(pfem2_handle *h, int new_cap)
+{
+    ParticleSoA old = h->soa[h->cur];
+    ParticleSoA other = h->soa[h->cur ^ 1];
+    const int n = h->host_count;
+    free_soa(other);
+    free_particle_scratch(h);
+    h->soa[h->cur ^ 1] = ParticleSoA{};
+    ParticleSoA fresh{};
+    int rc;
+    if ((rc = alloc_soa(h, fresh, new_cap))) return rc;
+    auto cp = [&](auto *dst, const auto *src) {
+        return cudaMemcpyAsync(dst, src, (size_t)n * sizeof(*dst), cudaMemcpyDeviceToDevice, h->stream);
+    };
+    CU(cp(fresh.x, old.x)); CU(cp(fresh.y, old.y)); CU(cp(fresh.l0, old.l0)); CU(cp(fresh.l1, old.l1));
+    CU(cp(fresh.l2, old.l2)); CU(cp(fresh.vx, old.vx)); CU(cp(fresh.vy, old.vy)); CU(cp(fresh.cell, old.cell));
+    CU(cp(fresh.id, old.id));
+    CU(cudaStreamSynchronize(h->stream));
+    free_soa(old);
+    h->soa[h->cur] = fresh;
+    if ((rc = alloc_soa(h, h->soa[h->cur ^ 1], new_cap))) return rc;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = dev_alloc(h, &h->keys[k], new_cap))) return rc;
+        if ((rc = dev_alloc(h, &h->vals[k], new_cap))) return rc;
+    }
+    if ((rc = dev_alloc(h, &h->rs_hist, rs_hist_elems(new_cap)))) return rc;
+    if ((rc = dev_alloc(h, &h->rs_scan_scratch, scan_scratch_elems<int>(kRsRadix * rs_num_tiles(new_cap))))) return rc;
+    h->capacity = new_cap;
+    if (h->aos) { cudaFree(h->aos); h->aos = nullptr; h->aos_bytes = 0; }
+    return PFEM2_OK;
+}
+
+// wait for the counter read-back of the last advect (if any) and refresh the host-side view
+int sync_counters(pfem2_handle *h)
+{
+    if (h->readback_pending) {
+        CU(cudaEventSynchronize(h->readback));
+        h->readback_pending = false;
+        h->host_count = h->host_ctr->count;
+        h->host_added = h->host_ctr->added;
+        if (h->host_ctr->overflow) return fail(h, PFEM2_ECAPACITY, "particle capacity exceeded during advect; state is invalid");
+    }
+    return PFEM2_OK;
+}
+
+int queue_readback(pfem2_handle *h)
+{
+    CU(cudaMemcpyAsync(h->host_ctr, h->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->readback, h->stream));
+    h->readback_pending = true;
+    return PFEM2_OK;
+}
+
+NodalVel nodal(const double *x, const double *y, double *const *table)
+{
+    NodalVel v;
+    v.x = x;
+    v.y = y;
+    v.table = table;
+    return v;
+}
+
+// sort the current buffer by cell into the other buffer, dropping lost particles and (optionally) re-seeding
+// empty sub-cells; expects keys[0]/vals[0], cell_count and cell_mask filled for the current buffer.
+int sort_and_reseed(pfem2_handle *h, bool reseed, NodalVel vel)
+{
+    cudaStream_t st = h->stream;
+    const int C = h->mesh.n_cells;
+    const int flip = radix_sort_pairs(h->keys[0], h->vals[0], h->keys[1], h->vals[1], &h->ctr->count, h->capacity, h->key_bits,
+                                      h->rs_hist, h->rs_scan_scratch, st);
+    PFEM2_LAUNCH(k_plan_cells, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->ppc, reseed ? 1 : 0, h->cell_count,
+                 h->cell_mask, h->packed);
+    exclusive_scan<unsigned long long>(h->packed, h->packed, C, h->scan_scratch64, st);
+    PFEM2_LAUNCH(k_plan_finish, 1, 1, 0, st, C, h->packed, h->ctr);
+    ParticleSoA src = h->soa[h->cur], dst = h->soa[h->cur ^ 1];
+    PFEM2_LAUNCH(k_gather_sorted, grid_for(h->capacity), kThreads, 0, st, src, dst, h->keys[flip], h->vals[flip], h->packed, h->ctr);
+    PFEM2_LAUNCH(k_reseed, grid_for(C + 1, kThreads, 1 << 30), kThreads, 0, st, C, h->ppc, (const double2 *)h->mesh.d_vertices,
+                 h->geom, h->centers, vel, h->cell_mask, h->packed, dst, h->cell_start, h->ctr);
+    h->cur ^= 1;
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
+{
+    if (!h) return PFEM2_EINVAL;
+    if (!h->seeded) return fail(h, PFEM2_ESTATE, "advect before seed");
+    if (substeps < 1) return fail(h, PFEM2_EINVAL, "particleSubsteps must be >= 1");
+    CU(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = sync_counters(h))) return rc;
+    // capacity policy: keep room for the growth seen so far (re-seeding only ever adds)
+    {
+        const long long margin = std::max<long long>({(long long)h->host_count / 4, 4ll * h->host_added, 4096ll});
+        if ((long long)h->host_count + margin > h->capacity) {
+            const long long want = std::max<long long>((long long)(1.5 * h->host_count), (long long)h->host_count + 2 * margin);
+            if (want > 2147483647ll - 1024) return fail(h, PFEM2_ECAPACITY, "particle count exceeds 32-bit indexing");
+            if ((rc = grow(h, (int)want))) return rc;
+        }
+    }
+    cudaStream_t st = h->stream;
+    const int C = h->mesh.n_cells;
+    const double hsub = dt / substeps; // particle_handler_2d.cu:330, host double
+    CU(cudaMemsetAsync(h->cell_count, 0, sizeof(int) * (C + 1), st));
+    CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * (C + 1), st));
+    PFEM2_LAUNCH(k_begin_advect, 1, 1, 0, st, h->ctr, h->capacity);
+    ParticleSoA p = h->soa[h->cur];
+    const int grid = grid_for(h->capacity);
+    if (h->opt.subcell_mode == 0)
+        PFEM2_LAUNCH(k_advect_locate<0>, grid, kThreads, 0, st, p, h->geom, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub,
+                     substeps, C, h->ppc, h->level, h->sub_step, h->ctr, h->keys[0], h->vals[0], h->cell_count, h->cell_mask);
+    else
+        PFEM2_LAUNCH(k_advect_locate<1>, grid, kThreads, 0, st, p, h->geom, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub,
+                     substeps, C, h->ppc, h->level, h->sub_step, h->ctr, h->keys[0], h->vals[0], h->cell_count, h->cell_mask);
+    if ((rc = sort_and_reseed(h, true, vel))) return rc;
+    if ((rc = queue_readback(h))) return rc;
+    if (h->opt.verbose) {
+        if ((rc = sync_counters(h))) return rc;
+        printf("Particle handler contains %d particles\n", h->host_count); // particle_handler_2d.cu:341
+    }
+    return PFEM2_OK;
+}
+
+int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
+{
+    if (!h) return PFEM2_EINVAL;
+    if (!h->seeded) return fail(h, PFEM2_ESTATE, "project before seed");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int C = h->mesh.n_cells, N = h->mesh.n_nodes;
+    ParticleSoA p = h->soa[h->cur];
+    // lanes per cell: enough to cover the typical segment in one or two strides
+    const int ppc = h->ppc;
+    if (ppc <= 6)
+        PFEM2_LAUNCH(k_project_cells<4>, grid_for((long long)C * 4), kThreads, 0, st, C, p, h->cell_start, h->partial);
+    else if (ppc <= 12)
+        PFEM2_LAUNCH(k_project_cells<8>, grid_for((long long)C * 8), kThreads, 0, st, C, p, h->cell_start, h->partial);
+    else if (ppc <= 24)
+        PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)C * 16), kThreads, 0, st, C, p, h->cell_start, h->partial);
+    else
+        PFEM2_LAUNCH(k_project_cells<32>, grid_for((long long)C * 32), kThreads, 0, st, C, p, h->cell_start, h->partial);
+    PFEM2_LAUNCH(k_project_nodes, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, N, h->node_off, (const int *)h->node_inc, h->partial,
+                 vx, vy, table);
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int do_correct(pfem2_handle *h, NodalVel v, NodalVel vold, bool has_old)
+{
+    if (!h) return PFEM2_EINVAL;
+    if (!h->seeded) return fail(h, PFEM2_ESTATE, "correct before seed");
+    CU(cudaSetDevice(h->device));
+    ParticleSoA p = h->soa[h->cur];
+    const int grid = grid_for(h->capacity);
+    if (has_old)
+        PFEM2_LAUNCH(k_correct<true>, grid, kThreads, 0, h->stream, p, h->geom, v, vold, h->ctr);
+    else
+        PFEM2_LAUNCH(k_correct<false>, grid, kThreads, 0, h->stream, p, h->geom, v, vold, h->ctr);
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+// node -> incidence CSR on the device with the library's own radix sort; uses keys/vals as scratch
+int build_node_incidence(pfem2_handle *h)
+{
+    cudaStream_t st = h->stream;
+    const int C = h->mesh.n_cells, N = h->mesh.n_nodes;
+    const int m = 3 * C;
+    int *count = nullptr, *n_dev = nullptr, *scratch = nullptr;
+    int rc;
+    if ((rc = dev_alloc(h, &count, (size_t)N + 1))) return rc;
+    if ((rc = dev_alloc(h, &n_dev, 1))) return rc;
+    if ((rc = dev_alloc(h, &scratch, scan_scratch_elems<int>(N)))) return rc;
+    CU(cudaMemsetAsync(count, 0, sizeof(int) * ((size_t)N + 1), st));
+    CU(cudaMemcpyAsync(n_dev, &m, sizeof(int), cudaMemcpyHostToDevice, st));
+    PFEM2_LAUNCH(k_incidence_keys, grid_for(m, kThreads, 1 << 30), kThreads, 0, st, C, h->mesh.d_cells, h->keys[0], h->vals[0], count);
+    int bits = 1;
+    while ((1ll << bits) < N) ++bits;
+    const int flip = radix_sort_pairs(h->keys[0], h->vals[0], h->keys[1], h->vals[1], n_dev, h->capacity, bits, h->rs_hist,
+                                      h->rs_scan_scratch, st);
+    CU(cudaMemcpyAsync(h->node_inc, h->vals[flip], sizeof(unsigned) * (size_t)m, cudaMemcpyDeviceToDevice, st));
+    exclusive_scan<int>(count, h->node_off, N, scratch, st);
+    CU(cudaStreamSynchronize(st));
+    cudaFree(count); cudaFree(n_dev); cudaFree(scratch);
+    return PFEM2_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+void pfem2_default_options(pfem2_options *o)
+{
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->struct_size = (int)sizeof *o;
+    o->subcell_mode = 0;
+    o->max_division_level = 4;
+    o->capacity_factor = 1.5;
+    o->stream = nullptr;
+    o->device = -1;
+    o->verbose = 0;
+}
+
+const char *pfem2_last_error(const pfem2_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+const char *pfem2_version(void) { return "pfem2_b200 0.1 (sm_100a)"; }
+
+long long pfem2_kernel_launches(void) { return g_kernel_launches; }
+
+int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_division_level, const pfem2_options *opt_in)
+{
+    pfem2_handle *h = nullptr;
+    if (!out || !mesh) return fail(nullptr, PFEM2_EINVAL, "null argument");
+    *out = nullptr;
+    if (mesh->n_cells <= 0 || mesh->n_nodes <= 0 || !mesh->d_vertices || !mesh->d_cells || !mesh->d_inv_jacobi ||
+        !mesh->d_nbr_offsets || !mesh->d_nbr_indices)
+        return fail(nullptr, PFEM2_EINVAL, "incomplete mesh view");
+    pfem2_options opt;
+    pfem2_default_options(&opt);
+    if (opt_in) memcpy(&opt, opt_in, std::min<size_t>(sizeof opt, (size_t)std::max(opt_in->struct_size, 0)));
+    if (opt.max_division_level <= 0) opt.max_division_level = 4;
+    if (opt.max_division_level > kMaxLevel) return fail(nullptr, PFEM2_EINVAL, "max_division_level > 8");
+    if (opt.capacity_factor < 1.05) opt.capacity_factor = 1.5;
+
+    int dev = opt.device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    CU(cudaSetDevice(dev));
+    h = new pfem2_handle;
+    h->device = dev;
+    h->opt = opt;
+    h->stream = (cudaStream_t)opt.stream;
+    h->mesh = *mesh;
+    // :241-243
+    const int n = std::max(std::min(cell_division_level, opt.max_division_level), 1);
+    h->level = n;
+    h->ppc = n * n;
+    h->sub_step = 1.0 / n;
+    const int C = mesh->n_cells, N = mesh->n_nodes;
+    if ((long long)C * h->ppc * opt.capacity_factor > 2147483000.0) {
+        delete h;
+        return fail(nullptr, PFEM2_EINVAL, "cells * particlesPerCell * capacity_factor exceeds 32-bit indexing");
+    }
+    h->key_bits = 1;
+    while ((1ll << h->key_bits) <= C) ++h->key_bits; // keys 0..C (C = lost)
+
+    // sub-cell centres (:248-274), host arithmetic without contraction
+    std::vector<double> cen(3 * (size_t)h->ppc);
+    {
+        int num = -1;
+        const volatile double dx = 1.0 / n;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < 2 * i + 1; ++j) {
+                const volatile double xmin = (j / 2) * dx;
+                const volatile double xmax = xmin + dx;
+                const volatile double ymin = (n - 1 - i) * dx;
+                const volatile double ymax = ymin + dx;
+                volatile double v0[3], v1[3], v2[3];
+                v0[0] = xmin; v0[1] = ymax; { volatile double t = 1.0 - xmin; v0[2] = t - ymax; }
+                v1[0] = (j % 2 == 0) ? xmin : xmax;
+                v1[1] = (j % 2 == 0) ? ymin : ymax;
+                { volatile double t = 1.0 - v1[0]; v1[2] = t - v1[1]; }
+                v2[0] = xmax; v2[1] = ymin; { volatile double t = 1.0 - xmax; v2[2] = t - ymin; }
+                ++num;
+                for (int k = 0; k < 3; ++k) {
+                    volatile double s = v0[k] + v1[k];
+                    s = s + v2[k];
+                    cen[3 * (size_t)num + k] = s * 0.3333333333333333; // CONSTANTS::ONE_THIRD
+                }
+            }
+    }
+
+    int rc;
+#define TRY(x) do { if ((rc = (x))) { std::string e = h->error; pfem2_destroy(h); g_create_error = e; return rc; } } while (0)
+    TRY(dev_alloc(h, &h->geom, (size_t)C));
+    TRY(dev_alloc(h, &h->node_off, (size_t)N + 1));
+    TRY(dev_alloc(h, &h->node_inc, 3 * (size_t)C));
+    TRY(dev_alloc(h, &h->centers, cen.size()));
+    TRY(dev_alloc(h, &h->ctr, 1));
+    TRY(dev_alloc(h, &h->cell_count, (size_t)C + 1));
+    TRY(dev_alloc(h, &h->cell_mask, (size_t)C + 1));
+    TRY(dev_alloc(h, &h->packed, (size_t)C + 2));
+    TRY(dev_alloc(h, &h->scan_scratch64, scan_scratch_elems<unsigned long long>(C)));
+    TRY(dev_alloc(h, &h->cell_start, (size_t)C + 1));
+    TRY(dev_alloc(h, &h->partial, 9 * (size_t)C));
+    {
+        cudaError_t e = cudaMallocHost((void **)&h->host_ctr, sizeof(Counters));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->readback, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            h->error = std::string("pinned/event allocation failed: ") + cudaGetErrorString(e);
+            TRY(PFEM2_ECUDA);
+        }
+        memset(h->host_ctr, 0, sizeof(Counters));
+    }
+    const long long want = std::max<long long>((long long)std::ceil((double)C * h->ppc * opt.capacity_factor), 3ll * C);
+    TRY(alloc_particle_storage(h, (int)want));
+    {
+        cudaError_t e = cudaMemcpyAsync(h->centers, cen.data(), cen.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { h->error = cudaGetErrorString(e); TRY(PFEM2_ECUDA); }
+    }
+    PFEM2_LAUNCH(k_build_geom, grid_for(C, kThreads, 1 << 30), kThreads, 0, h->stream, C, (const double2 *)mesh->d_vertices, mesh->d_cells,
+                 mesh->d_inv_jacobi, h->geom);
+    PFEM2_LAUNCH(k_set_counters, 1, 1, 0, h->stream, h->ctr, 0, h->capacity);
+    TRY(build_node_incidence(h));
+#undef TRY
+    *out = h;
+    return PFEM2_OK;
+}
+
+int pfem2_destroy(pfem2_handle *h)
+{
+    if (!h) return PFEM2_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_soa(h->soa[0]);
+    free_soa(h->soa[1]);
+    free_particle_scratch(h);
+    cudaFree(h->geom); cudaFree(h->node_off); cudaFree(h->node_inc); cudaFree(h->centers); cudaFree(h->ctr);
+    cudaFree(h->cell_count); cudaFree(h->cell_mask); cudaFree(h->packed); cudaFree(h->scan_scratch64);
+    cudaFree(h->cell_start); cudaFree(h->partial); cudaFree(h->aos);
+    for (double *p : h->nodal) cudaFree(p);
+    if (h->host_ctr) cudaFreeHost(h->host_ctr);
+    if (h->readback) cudaEventDestroy(h->readback);
+    delete h;
+    return PFEM2_OK;
+}
+
+int pfem2_seed(pfem2_handle *h)
+{
+    if (!h) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    const int C = h->mesh.n_cells;
+    h->cur = 0;
+    PFEM2_LAUNCH(k_set_counters, 1, 1, 0, h->stream, h->ctr, 0, h->capacity);
+    PFEM2_LAUNCH(k_seed, grid_for((long long)C * h->ppc), kThreads, 0, h->stream, C, h->ppc, (const double2 *)h->mesh.d_vertices, h->geom,
+                 h->centers, h->soa[0], h->cell_start, h->ctr);
+    CU(cudaGetLastError());
+    h->seeded = true;
+    h->host_count = C * h->ppc;
+    h->host_added = 0;
+    h->readback_pending = false;
+    if (h->opt.verbose) {
+        CU(cudaStreamSynchronize(h->stream)); // the reference synchronises here too (:315)
+        printf("Created %d particles\n", h->host_count); // :319
+    }
+    return PFEM2_OK;
+}
+
+int pfem2_init_velocity(pfem2_handle *h, const double *vx, const double *vy)
+{
+    return do_correct(h, nodal(vx, vy, nullptr), nodal(nullptr, nullptr, nullptr), false);
+}
+int pfem2_init_velocity_ptrs(pfem2_handle *h, double *const *t)
+{
+    return do_correct(h, nodal(nullptr, nullptr, t), nodal(nullptr, nullptr, nullptr), false);
+}
+int pfem2_advect(pfem2_handle *h, const double *vx, const double *vy, double dt, int substeps)
+{
+    return do_advect(h, nodal(vx, vy, nullptr), dt, substeps);
+}
+int pfem2_advect_ptrs(pfem2_handle *h, double *const *t, double dt, int substeps)
+{
+    return do_advect(h, nodal(nullptr, nullptr, t), dt, substeps);
+}
+int pfem2_project(pfem2_handle *h, double *vx, double *vy) { return do_project(h, vx, vy, nullptr); }
+int pfem2_project_ptrs(pfem2_handle *h, double *const *t) { return do_project(h, nullptr, nullptr, t); }
+int pfem2_correct(pfem2_handle *h, const double *vx, const double *vy, const double *ox, const double *oy)
+{
+    return do_correct(h, nodal(vx, vy, nullptr), nodal(ox, oy, nullptr), true);
+}
+int pfem2_correct_ptrs(pfem2_handle *h, double *const *t, double *const *told)
+{
+    return do_correct(h, nodal(nullptr, nullptr, t), nodal(nullptr, nullptr, told), true);
+}
+
+int pfem2_particle_count(pfem2_handle *h, int *out)
+{
+    if (!h || !out) return PFEM2_EINVAL;
+    int rc;
+    if ((rc = sync_counters(h))) return rc;
+    *out = h->host_count;
+    return PFEM2_OK;
+}
+
+int pfem2_get_stats(pfem2_handle *h, pfem2_stats *out)
+{
+    if (!h || !out) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    const int rc = sync_counters(h);
+    Counters c;
+    CU(cudaMemcpyAsync(&c, h->ctr, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    out->count = c.count; out->lost = c.lost; out->added = c.added; out->movers = c.movers;
+    out->capacity = h->capacity; out->overflow = c.overflow;
+    return rc;
+}
+
+int pfem2_export_aos(pfem2_handle *h, const void **d_particles96, int *count)
+{
+    if (!h || !d_particles96) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = sync_counters(h))) return rc;
+    const size_t need = (size_t)std::max(h->capacity, 1) * 96;
+    if (h->aos_bytes < need) {
+        if (h->aos) cudaFree(h->aos);
+        h->aos = nullptr;
+        CU(cudaMalloc(&h->aos, need));
+        h->aos_bytes = need;
+    }
+    PFEM2_LAUNCH(k_export_aos, grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->ctr, (uint4 *)h->aos);
+    CU(cudaGetLastError());
+    *d_particles96 = h->aos;
+    if (count) *count = h->host_count;
+    return PFEM2_OK;
+}
+
+int pfem2_step_host(pfem2_handle *h, const double *fx, const double *fy, double *wx, double *wy, double dt, int substeps,
+                    int *count_out)
+{
+    if (!h || !fx || !fy || !wx || !wy) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    const size_t nb = sizeof(double) * (size_t)h->mesh.n_nodes;
+    for (double *&p : h->nodal)
+        if (!p) CU(cudaMalloc((void **)&p, nb));
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(h->nodal[0], fx, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->nodal[1], fy, nb, cudaMemcpyHostToDevice, st));
+    int rc;
+    if ((rc = pfem2_advect(h, h->nodal[0], h->nodal[1], dt, substeps))) return rc;
+    if ((rc = pfem2_project(h, h->nodal[2], h->nodal[3]))) return rc;
+    if ((rc = pfem2_correct(h, h->nodal[0], h->nodal[1], h->nodal[2], h->nodal[3]))) return rc;
+    CU(cudaMemcpyAsync(wx, h->nodal[2], nb, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(wy, h->nodal[3], nb, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if ((rc = sync_counters(h))) return rc;
+    if (count_out) *count_out = h->host_count;
+    return PFEM2_OK;
+}
+
+int pfem2_download(pfem2_handle *h, double *x, double *y, double *l0, double *l1, double *l2, double *vx, double *vy,
+                   unsigned *cell, unsigned *id)
+{
+    if (!h) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = sync_counters(h))) return rc;
+    const size_t n = (size_t)h->host_count;
+    const ParticleSoA &p = h->soa[h->cur];
+    auto cp = [&](auto *dst, const auto *src) {
+        return dst ? cudaMemcpyAsync(dst, src, n * sizeof(*dst), cudaMemcpyDeviceToHost, h->stream) : cudaSuccess;
+    };
+    CU(cp(x, p.x)); CU(cp(y, p.y)); CU(cp(l0, p.l0)); CU(cp(l1, p.l1)); CU(cp(l2, p.l2));
+    CU(cp(vx, p.vx)); CU(cp(vy, p.vy)); CU(cp(cell, p.cell)); CU(cp(id, p.id));
+    CU(cudaStreamSynchronize(h->stream));
+    return PFEM2_OK;
+}
+
+int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const double *l0, const double *l1, const double *l2,
+                 const double *vx, const double *vy, const unsigned *cell, const unsigned *id)
+{
+    if (!h || n < 0 || !x || !y || !l0 || !l1 || !l2 || !vx || !vy || !cell) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = sync_counters(h))) return rc;
+    if (n > h->capacity) {
+        h->host_count = 0;
+        if ((rc = grow(h, (int)std::min<long long>(2147483000ll, (long long)(1.25 * n) + 4096)))) return rc;
+    }
+    cudaStream_t st = h->stream;
+    const int C = h->mesh.n_cells;
+    ParticleSoA &p = h->soa[h->cur];
+    auto cp = [&](auto *dst, const auto *src) {
+        return cudaMemcpyAsync(dst, src, (size_t)n * sizeof(*dst), cudaMemcpyHostToDevice, st);
+    };
+    CU(cp(p.x, x)); CU(cp(p.y, y)); CU(cp(p.l0, l0)); CU(cp(p.l1, l1)); CU(cp(p.l2, l2));
+    CU(cp(p.vx, vx)); CU(cp(p.vy, vy)); CU(cp(p.cell, cell));
+    if (id) CU(cp(p.id, id)); else CU(cudaMemsetAsync(p.id, 0, sizeof(unsigned) * (size_t)n, st));
+    PFEM2_LAUNCH(k_set_counters, 1, 1, 0, st, h->ctr, n, h->capacity);
+    CU(cudaMemsetAsync(h->cell_count, 0, sizeof(int) * (C + 1), st));
+    CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * (C + 1), st));
+    PFEM2_LAUNCH(k_keys_from_cells, grid_for(h->capacity), kThreads, 0, st, p, C, h->ctr, h->keys[0], h->vals[0], h->cell_count);
+    if ((rc = sort_and_reseed(h, false, nodal(nullptr, nullptr, nullptr)))) return rc;
+    h->seeded = true;
+    if ((rc = queue_readback(h))) return rc;
+    return sync_counters(h);
+}
+
+int pfem2_device_arrays(pfem2_handle *h, const double **x, const double **y, const double **l0, const double **l1, const double **l2,
+                        const double **vx, const double **vy, const unsigned **cell, const unsigned **id)
+{
+    if (!h) return PFEM2_EINVAL;
+    const ParticleSoA &p = h->soa[h->cur];
+    if (x) *x = p.x; if (y) *y = p.y; if (l0) *l0 = p.l0; if (l1) *l1 = p.l1; if (l2) *l2 = p.l2;
+    if (vx) *vx = p.vx; if (vy) *vy = p.vy; if (cell) *cell = p.cell; if (id) *id = p.id;
+    return PFEM2_OK;
+}
+
+int pfem2_cell_starts(pfem2_handle *h, const int **d_cell_start)
+{
+    if (!h || !d_cell_start) return PFEM2_EINVAL;
+    *d_cell_start = h->cell_start;
+    return PFEM2_OK;
+}
+
+int pfem2_mesh_inv_jacobi(int n_cells, const double *d_vertices, const unsigned *d_cells, double *d_inv_jacobi, void *stream)
+{
+    pfem2_handle *h = nullptr;
+    if (n_cells <= 0 || !d_vertices || !d_cells || !d_inv_jacobi) return fail(nullptr, PFEM2_EINVAL, "bad argument");
+    PFEM2_LAUNCH(k_inv_jacobi, grid_for(n_cells, kThreads, 1 << 30), kThreads, 0, (cudaStream_t)stream, n_cells, (const double2 *)d_vertices,
+                 d_cells, d_inv_jacobi);
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int pfem2_sort_pairs(int n, int key_bits, unsigned *keys, unsigned *vals, unsigned *keys_tmp, unsigned *vals_tmp, int *result_in_tmp,
+                     void *stream)
+{
+    pfem2_handle *h = nullptr;
+    if (n < 0 || key_bits < 1 || key_bits > 32 || !keys || !vals || !keys_tmp || !vals_tmp || !result_in_tmp)
+        return fail(nullptr, PFEM2_EINVAL, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int *n_dev = nullptr, *hist = nullptr, *scratch = nullptr;
+    CU(cudaMalloc((void **)&n_dev, sizeof(int)));
+    CU(cudaMalloc((void **)&hist, sizeof(int) * rs_hist_elems(std::max(n, 1))));
+    CU(cudaMalloc((void **)&scratch, sizeof(int) * scan_scratch_elems<int>(kRsRadix * rs_num_tiles(std::max(n, 1)))));
+    CU(cudaMemcpyAsync(n_dev, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+    *result_in_tmp = radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n_dev, n, key_bits, hist, scratch, st);
+    CU(cudaStreamSynchronize(st));
+    cudaFree(n_dev); cudaFree(hist); cudaFree(scratch);
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int pfem2_mesh_one_ring(int n_nodes, int n_cells, const unsigned *d_cells, int *d_offsets, int *d_indices, int *nnz, void *stream)
+{
+    pfem2_handle *h = nullptr;
+    if (n_nodes <= 0 || n_cells <= 0 || !d_cells || !d_offsets || !nnz) return fail(nullptr, PFEM2_EINVAL, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m = 3 * n_cells;
+    unsigned *k0, *k1, *v0, *v1;
+    int *count, *node_off, *n_dev, *hist, *scratch, *scratch2, *err;
+    CU(cudaMalloc((void **)&k0, sizeof(unsigned) * (size_t)m)); CU(cudaMalloc((void **)&k1, sizeof(unsigned) * (size_t)m));
+    CU(cudaMalloc((void **)&v0, sizeof(unsigned) * (size_t)m)); CU(cudaMalloc((void **)&v1, sizeof(unsigned) * (size_t)m));
+    CU(cudaMalloc((void **)&count, sizeof(int) * ((size_t)n_nodes + 1)));
+    CU(cudaMalloc((void **)&node_off, sizeof(int) * ((size_t)n_nodes + 1)));
+    CU(cudaMalloc((void **)&n_dev, sizeof(int))); CU(cudaMalloc((void **)&err, sizeof(int)));
+    CU(cudaMalloc((void **)&hist, sizeof(int) * rs_hist_elems(m)));
+    CU(cudaMalloc((void **)&scratch, sizeof(int) * scan_scratch_elems<int>(kRsRadix * rs_num_tiles(m))));
+    CU(cudaMalloc((void **)&scratch2, sizeof(int) * scan_scratch_elems<int>(std::max(n_nodes, n_cells))));
+    CU(cudaMemsetAsync(count, 0, sizeof(int) * ((size_t)n_nodes + 1), st));
+    CU(cudaMemsetAsync(err, 0, sizeof(int), st));
+    CU(cudaMemcpyAsync(n_dev, &m, sizeof(int), cudaMemcpyHostToDevice, st));
+    PFEM2_LAUNCH(k_incidence_keys, grid_for(m, kThreads, 1 << 30), kThreads, 0, st, n_cells, d_cells, k0, v0, count);
+    int bits = 1;
+    while ((1ll << bits) < n_nodes) ++bits;
+    const int flip = radix_sort_pairs(k0, v0, k1, v1, n_dev, m, bits, hist, scratch, st);
+    const unsigned *inc = flip ? v1 : v0;
+    exclusive_scan<int>(count, node_off, n_nodes, scratch2, st);
+    if (!d_indices) {
+        int *counts = (int *)k0 == (int *)inc ? (int *)k1 : (int *)k0; // any free buffer of >= n_cells ints
+        counts = flip ? (int *)k0 : (int *)k1;
+        PFEM2_LAUNCH(k_one_ring, grid_for(n_cells, 128, 1 << 30), 128, 0, st, n_cells, d_cells, node_off, inc, counts, nullptr, nullptr, err);
+        exclusive_scan<int>(counts, d_offsets, n_cells, scratch2, st);
+    } else {
+        PFEM2_LAUNCH(k_one_ring, grid_for(n_cells, 128, 1 << 30), 128, 0, st, n_cells, d_cells, node_off, inc, nullptr, d_offsets, d_indices, err);
+    }
+    int herr = 0;
+    CU(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(nnz, d_offsets + n_cells, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(count); cudaFree(node_off); cudaFree(n_dev);
+    cudaFree(err); cudaFree(hist); cudaFree(scratch); cudaFree(scratch2);
+    CU(cudaGetLastError());
+    if (herr) return fail(nullptr, PFEM2_EINVAL, "a cell has more than 96 one-ring neighbours");
+    return PFEM2_OK;
+}
+
+} // extern "C"

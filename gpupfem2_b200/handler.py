@@ -1,0 +1,210 @@
+"""Host-side mirror of the reference's ``ParticleHandler2D`` over the C ABI (include/pfem2_b200.h).
+
+Same methods, argument meaning and call order as reference src/particles/particle_handler_2d.cuh:9-54
+(``seedParticles``, ``initParticleVelocity``, ``advectParticles``, ``projectVelocityOntoGrid``,
+``correctParticleVelocity``, ``getParticles``, ``getParticleCount``), spelled in snake_case.  Nodal
+velocities are pairs of CUDA float64 torch tensors (the reference's ``deviceVector<double*>`` of two
+component arrays).  torch is plumbing only: device memory and streams; all compute is in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .mesh import HostMesh
+
+
+class Pfem2Error(RuntimeError):
+    pass
+
+
+class DeviceMesh:
+    """The reference Mesh2D's device arrays (src/mesh_2d.cuh:18-44) as torch CUDA tensors."""
+
+    def __init__(self, mesh: HostMesh, device="cuda:0", build_missing=True):
+        self.device = torch.device(device)
+        self.n_nodes, self.n_cells = mesh.n_nodes, mesh.n_cells
+        self.vertices = torch.as_tensor(np.ascontiguousarray(mesh.vertices, dtype=np.float64)).to(self.device)
+        self.cells = torch.as_tensor(np.ascontiguousarray(mesh.cells, dtype=np.uint32).view(np.int32)).to(self.device)
+        L = _lib.load()
+        if mesh.inv_jacobi is not None:
+            self.inv_jacobi = torch.as_tensor(np.ascontiguousarray(mesh.inv_jacobi, dtype=np.float64)).to(self.device)
+        elif build_missing:
+            self.inv_jacobi = torch.empty((self.n_cells, 4), dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):
+                rc = L.pfem2_mesh_inv_jacobi(self.n_cells, self.vertices.data_ptr(), self.cells.data_ptr(),
+                                             self.inv_jacobi.data_ptr(), None)
+            if rc:
+                raise Pfem2Error(L.pfem2_last_error(None).decode())
+        if mesh.nbr_offsets is not None:
+            self.nbr_offsets = torch.as_tensor(np.ascontiguousarray(mesh.nbr_offsets, dtype=np.int32)).to(self.device)
+            self.nbr_indices = torch.as_tensor(np.ascontiguousarray(mesh.nbr_indices, dtype=np.int32)).to(self.device)
+        elif build_missing:
+            self.nbr_offsets, self.nbr_indices = device_one_ring(self.n_nodes, self.cells)
+        torch.cuda.synchronize(self.device)
+
+    def view(self) -> _lib.MeshView:
+        return _lib.MeshView(self.n_nodes, self.n_cells, self.vertices.data_ptr(), self.cells.data_ptr(),
+                             self.inv_jacobi.data_ptr(), self.nbr_offsets.data_ptr(), self.nbr_indices.data_ptr())
+
+
+def device_one_ring(n_nodes: int, cells: torch.Tensor):
+    """Vertex-sharing one-ring CSR built on the device (replaces Mesh2D::fillCellNeighborIndices, mesh_2d.cu:107-139)."""
+    L = _lib.load()
+    n_cells = cells.shape[0]
+    off = torch.empty(n_cells + 1, dtype=torch.int32, device=cells.device)
+    nnz = C.c_int(0)
+    with torch.cuda.device(cells.device):
+        rc = L.pfem2_mesh_one_ring(n_nodes, n_cells, cells.data_ptr(), off.data_ptr(), None, C.byref(nnz), None)
+        if rc:
+            raise Pfem2Error(L.pfem2_last_error(None).decode())
+        idx = torch.empty(max(nnz.value, 1), dtype=torch.int32, device=cells.device)
+        rc = L.pfem2_mesh_one_ring(n_nodes, n_cells, cells.data_ptr(), off.data_ptr(), idx.data_ptr(), C.byref(nnz), None)
+        if rc:
+            raise Pfem2Error(L.pfem2_last_error(None).decode())
+    return off, idx[: nnz.value]
+
+
+class ParticleHandler2D:
+    FIELDS = ("x", "y", "l0", "l1", "l2", "vx", "vy", "cell", "id")
+
+    def __init__(self, mesh: DeviceMesh, cell_division_level: int, *, subcell_mode=0, max_division_level=4,
+                 capacity_factor=1.5, verbose=False):
+        self._L = _lib.load()
+        self.mesh = mesh  # borrowed for the handler's lifetime, like the reference's `const Mesh2D *`
+        opt = _lib.Options()
+        self._L.pfem2_default_options(C.byref(opt))
+        opt.subcell_mode = subcell_mode
+        opt.max_division_level = max_division_level
+        opt.capacity_factor = capacity_factor
+        opt.device = mesh.device.index if mesh.device.index is not None else 0
+        opt.verbose = 1 if verbose else 0
+        self._h = C.c_void_p()
+        view = mesh.view()
+        rc = self._L.pfem2_create(C.byref(self._h), C.byref(view), cell_division_level, C.byref(opt))
+        if rc:
+            raise Pfem2Error(f"pfem2_create: {self._L.pfem2_last_error(None).decode()}")
+        lvl = max(min(cell_division_level, max_division_level), 1)
+        self.particles_per_cell = lvl * lvl
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.pfem2_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc:
+            raise Pfem2Error(f"{what}: {self._L.pfem2_last_error(self._h).decode()} (code {rc})")
+
+    # --- reference interface -------------------------------------------------------------------
+    def seed_particles(self):
+        self._check(self._L.pfem2_seed(self._h), "seedParticles")
+
+    def init_particle_velocity(self, vel):
+        self._check(self._L.pfem2_init_velocity(self._h, vel[0].data_ptr(), vel[1].data_ptr()), "initParticleVelocity")
+
+    def advect_particles(self, vel, time_step: float, particle_substeps: int):
+        self._check(self._L.pfem2_advect(self._h, vel[0].data_ptr(), vel[1].data_ptr(), time_step, particle_substeps),
+                    "advectParticles")
+
+    def project_velocity_onto_grid(self, vel):
+        """Overwrites vel[0], vel[1] with the projected nodal velocity (like the reference)."""
+        self._check(self._L.pfem2_project(self._h, vel[0].data_ptr(), vel[1].data_ptr()), "projectVelocityOntoGrid")
+
+    def correct_particle_velocity(self, vel, vel_old):
+        self._check(self._L.pfem2_correct(self._h, vel[0].data_ptr(), vel[1].data_ptr(), vel_old[0].data_ptr(),
+                                          vel_old[1].data_ptr()), "correctParticleVelocity")
+
+    def get_particle_count(self) -> int:
+        n = C.c_int(0)
+        self._check(self._L.pfem2_particle_count(self._h, C.byref(n)), "getParticleCount")
+        return n.value
+
+    def get_particles(self) -> torch.Tensor:
+        """The reference's 96-byte AoS Particle2D records as a (count, 12) float64 view (device memory owned by
+        the handler, valid until the next mutating call)."""
+        p, n = C.c_void_p(), C.c_int(0)
+        self._check(self._L.pfem2_export_aos(self._h, C.byref(p), C.byref(n)), "getParticles")
+        out = torch.empty((n.value, 12), dtype=torch.float64, device=self.mesh.device)
+        if n.value:
+            _memcpy_d2d(out.data_ptr(), p.value, n.value * 96)
+        return out
+
+    # --- pointer-table flavour (deviceVector<double*>::data) --------------------------------------
+    def advect_particles_ptrs(self, table: torch.Tensor, time_step, particle_substeps):
+        self._check(self._L.pfem2_advect_ptrs(self._h, table.data_ptr(), time_step, particle_substeps), "advectParticles")
+
+    def project_velocity_onto_grid_ptrs(self, table: torch.Tensor):
+        self._check(self._L.pfem2_project_ptrs(self._h, table.data_ptr()), "projectVelocityOntoGrid")
+
+    def correct_particle_velocity_ptrs(self, table: torch.Tensor, table_old: torch.Tensor):
+        self._check(self._L.pfem2_correct_ptrs(self._h, table.data_ptr(), table_old.data_ptr()), "correctParticleVelocity")
+
+    def init_particle_velocity_ptrs(self, table: torch.Tensor):
+        self._check(self._L.pfem2_init_velocity_ptrs(self._h, table.data_ptr()), "initParticleVelocity")
+
+    # --- extras --------------------------------------------------------------------------------
+    def step(self, frozen, work, dt, substeps):
+        """Isolated particle step (oracle/ref_harness.cu protocol): advect(F) ; project(W) ; correct(F, W)."""
+        self.advect_particles(frozen, dt, substeps)
+        self.project_velocity_onto_grid(work)
+        self.correct_particle_velocity(frozen, work)
+
+    def step_host(self, fx: np.ndarray, fy: np.ndarray, wx: np.ndarray, wy: np.ndarray, dt, substeps) -> int:
+        """Same step with HOST nodal buffers (pinned torch tensors or numpy): the end-to-end C-ABI call."""
+        n = C.c_int(0)
+        self._check(self._L.pfem2_step_host(self._h, _hp(fx), _hp(fy), _hp(wx), _hp(wy), dt, substeps, C.byref(n)), "step_host")
+        return n.value
+
+    def stats(self) -> dict:
+        s = _lib.Stats()
+        self._check(self._L.pfem2_get_stats(self._h, C.byref(s)), "get_stats")
+        return {k: getattr(s, k) for k, _ in _lib.Stats._fields_}
+
+    def download(self) -> dict:
+        n = self.get_particle_count()
+        out = {k: np.empty(n, dtype=np.float64) for k in self.FIELDS[:7]}
+        out["cell"] = np.empty(n, dtype=np.uint32)
+        out["id"] = np.empty(n, dtype=np.uint32)
+        self._check(self._L.pfem2_download(self._h, *[out[k].ctypes.data for k in self.FIELDS]), "download")
+        return out
+
+    def upload(self, state: dict):
+        n = int(state["x"].shape[0])
+        a = [np.ascontiguousarray(state[k], dtype=np.float64) for k in self.FIELDS[:7]]
+        a.append(np.ascontiguousarray(state["cell"], dtype=np.uint32))
+        a.append(np.ascontiguousarray(state.get("id", np.zeros(n, dtype=np.uint32)), dtype=np.uint32))
+        self._check(self._L.pfem2_upload(self._h, n, *[v.ctypes.data for v in a]), "upload")
+
+    def cell_starts(self) -> torch.Tensor:
+        p = C.c_void_p()
+        self._check(self._L.pfem2_cell_starts(self._h, C.byref(p)), "cell_starts")
+        out = torch.empty(self.mesh.n_cells + 1, dtype=torch.int32, device=self.mesh.device)
+        _memcpy_d2d(out.data_ptr(), p.value, 4 * (self.mesh.n_cells + 1))
+        return out
+
+
+def _hp(a):
+    if isinstance(a, torch.Tensor):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def _memcpy_d2d(dst, src, nbytes):
+    rt = torch.cuda.cudart()
+    err = rt.cudaMemcpy(dst, src, nbytes, 3)  # cudaMemcpyDeviceToDevice
+    if int(err) != 0:
+        raise Pfem2Error(f"cudaMemcpy failed: {err}")
+
+
+def kernel_launches() -> int:
+    return int(_lib.load().pfem2_kernel_launches())

@@ -1,0 +1,145 @@
+/*
+ * pfem2_b200.h -- C ABI of the B200-native PFEM-2 particle step (libpfem2_b200.so).
+ *
+ * This is the drop-in boundary for gpuPfem2's `ParticleHandler2D`
+ * (reference src/particles/particle_handler_2d.cuh:9-54).  The reference has no FFI: its "operator
+ * API" is that C++ class, called by cases/Cylinder2D/main.cu:652-653,766,798,802,864 and
+ * cases/PoiseuilleFlow2D/main.cu:513-514,622,657,661,723, and read by DataExport
+ * (src/data_export.cu:97-104).  Each entry point below names the member it replaces; the header-
+ * compatible C++ shim that forwards to them is gpupfem2_b200/shim/particles/particle_handler_2d.cuh
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only, no C++/torch types, no exceptions, never exit().
+ *  - every function returns 0 on success or a PFEM2_E* code; pfem2_last_error() gives the text.
+ *  - all `d_` pointers are DEVICE pointers on the handle's device; `h_` pointers are host pointers.
+ *  - mesh arrays are borrowed for the handle's lifetime and never written.
+ *  - all work is issued on the handle's stream (default: the legacy null stream, like the
+ *    reference, so ordering with the caller's FEM kernels is preserved).
+ *  - nodal velocity arguments come in two flavours: `*_ptrs` takes the reference's
+ *    `deviceVector<double*>::data` (a DEVICE array of two device pointers, x then y component,
+ *    cases/Cylinder2D/main.cu:597-604); the plain form takes the two component pointers directly.
+ */
+#ifndef PFEM2_B200_H
+#define PFEM2_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFEM2_OK 0
+#define PFEM2_EINVAL 1    /* bad argument */
+#define PFEM2_ECUDA 2     /* CUDA runtime error (text in pfem2_last_error) */
+#define PFEM2_ECAPACITY 3 /* particle storage overflowed its capacity */
+#define PFEM2_ESTATE 4    /* call order violated (e.g. advect before seed) */
+
+typedef struct pfem2_handle pfem2_handle;
+
+/* Read-only view of the reference's Mesh2D device arrays (src/mesh_2d.cuh:18-44). */
+typedef struct pfem2_mesh_view {
+    int n_nodes;               /* getVertices().size */
+    int n_cells;               /* getCells().size */
+    const double *d_vertices;  /* Point2 = double2 per node      (getVertices().data) */
+    const unsigned *d_cells;   /* uint3 per cell, file order     (getCells().data) */
+    const double *d_inv_jacobi;/* Matrix2x2 = 4 doubles per cell (getInvJacobi().data) */
+    const int *d_nbr_offsets;  /* n_cells + 1                    (getCellNeighborsOffsets().data) */
+    const int *d_nbr_indices;  /* ascending one-ring per cell    (getCellNeighborIndices().data) */
+} pfem2_mesh_view;
+
+typedef struct pfem2_options {
+    int struct_size;        /* = sizeof(pfem2_options), for forward compatibility */
+    int subcell_mode;       /* 0: reference-exact flat sub-cell index with spill (default); 1: clamped */
+    int max_division_level; /* 0 -> 4 = CONSTANTS::MAX_CELL_DIVISION_LEVEL (constants.h:15); <= 8 */
+    double capacity_factor; /* 0 -> 1.5: particle capacity = factor * cells * ppc (reference: 1.1 + realloc) */
+    void *stream;           /* cudaStream_t; NULL = legacy default stream */
+    int device;             /* CUDA device ordinal; -1 = current device */
+    int verbose;            /* 1: print the reference's two stdout lines from the library itself */
+} pfem2_options;
+
+/* counters of the last pfem2_advect call (device-resident, read back on demand) */
+typedef struct pfem2_stats {
+    int count;         /* live particles */
+    int lost;          /* particles deleted by the last advect (all substeps) */
+    int added;         /* particles re-seeded by the last advect */
+    int movers;        /* particle-substeps that left their cell in the last advect */
+    int capacity;      /* particle slots allocated */
+    int overflow;      /* non-zero if a step needed more slots than capacity (state is then invalid) */
+} pfem2_stats;
+
+void pfem2_default_options(pfem2_options *opt);
+const char *pfem2_last_error(const pfem2_handle *h); /* h may be NULL: last create() error */
+const char *pfem2_version(void);
+
+/* ParticleHandler2D::ParticleHandler2D(const Mesh2D*, int)   particle_handler_2d.cu:238-294 */
+int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_division_level, const pfem2_options *opt);
+/* ParticleHandler2D::~ParticleHandler2D()                     particle_handler_2d.cu:296-302 */
+int pfem2_destroy(pfem2_handle *h);
+
+/* seedParticles()                                             particle_handler_2d.cu:304-320 */
+int pfem2_seed(pfem2_handle *h);
+/* initParticleVelocity(velocitySolution)                      particle_handler_2d.cu:322-326 */
+int pfem2_init_velocity(pfem2_handle *h, const double *d_vx, const double *d_vy);
+int pfem2_init_velocity_ptrs(pfem2_handle *h, double *const *d_vel2);
+/* advectParticles(velocitySolution, timeStep, particleSubsteps)   particle_handler_2d.cu:328-342
+ * (S x [advect + own-cell test + one-ring search + delete], then distribution check + re-seed;
+ *  afterwards the particle arrays are physically sorted by owning cell) */
+int pfem2_advect(pfem2_handle *h, const double *d_vx, const double *d_vy, double dt, int substeps);
+int pfem2_advect_ptrs(pfem2_handle *h, double *const *d_vel2, double dt, int substeps);
+/* projectVelocityOntoGrid(velocity): WRITES the two nodal arrays   particle_handler_2d.cu:350-361 */
+int pfem2_project(pfem2_handle *h, double *d_vx, double *d_vy);
+int pfem2_project_ptrs(pfem2_handle *h, double *const *d_vel2);
+/* correctParticleVelocity(velocitySolution, velocitySolutionOld)   particle_handler_2d.cu:344-348 */
+int pfem2_correct(pfem2_handle *h, const double *d_vx, const double *d_vy, const double *d_vx_old, const double *d_vy_old);
+int pfem2_correct_ptrs(pfem2_handle *h, double *const *d_vel2, double *const *d_vel_old2);
+
+/* getParticleCount()  particle_handler_2d.cuh:28-30  (synchronises the handle's stream) */
+int pfem2_particle_count(pfem2_handle *h, int *out);
+int pfem2_get_stats(pfem2_handle *h, pfem2_stats *out);
+/* getParticles()      particle_handler_2d.cuh:24-26: device pointer to the reference's 96-byte AoS
+ * Particle2D records (particle_2d.cuh:51-57: ID@0 position@16 localPosition@32 velocity@64 cellID@80),
+ * materialised lazily from the SoA storage; valid until the next mutating call. */
+int pfem2_export_aos(pfem2_handle *h, const void **d_particles96, int *count);
+
+/* One whole particle step with HOST nodal buffers (pinned or pageable), the end-to-end form of
+ *   advect(F) ; project(W) ; correct(F, W)
+ * h_f* : frozen/solved nodal velocity in (n_nodes each), h_w* : projected nodal velocity out.
+ * Copies F host->device, runs the three calls, copies W device->host and returns the live count. */
+int pfem2_step_host(pfem2_handle *h, const double *h_fx, const double *h_fy, double *h_wx, double *h_wy,
+                    double dt, int substeps, int *count_out);
+
+/* particle state download / upload (parity tests, checkpoint/restart).  Host SoA arrays of
+ * pfem2_particle_count() elements; any pointer may be NULL.  Upload re-sorts by cell. */
+int pfem2_download(pfem2_handle *h, double *h_x, double *h_y, double *h_l0, double *h_l1, double *h_l2,
+                   double *h_vx, double *h_vy, unsigned *h_cell, unsigned *h_id);
+int pfem2_upload(pfem2_handle *h, int n, const double *h_x, const double *h_y, const double *h_l0, const double *h_l1,
+                 const double *h_l2, const double *h_vx, const double *h_vy, const unsigned *h_cell, const unsigned *h_id);
+/* device pointers to the live SoA arrays (x y l0 l1 l2 vx vy as double*, cell id as unsigned*), for
+ * zero-copy consumers; valid until the next mutating call */
+int pfem2_device_arrays(pfem2_handle *h, const double **d_x, const double **d_y, const double **d_l0, const double **d_l1,
+                        const double **d_l2, const double **d_vx, const double **d_vy, const unsigned **d_cell,
+                        const unsigned **d_id);
+/* per-cell segment table of the sorted storage: particles of cell c are [start[c], start[c+1]) */
+int pfem2_cell_starts(pfem2_handle *h, const int **d_cell_start);
+
+/* ---- mesh preparation helpers (the step right before the path; reference src/mesh_2d.cu) ---- */
+/* kCalculateInvJacobi, mesh_2d.cu:21-34, same operation order -> same bits */
+int pfem2_mesh_inv_jacobi(int n_cells, const double *d_vertices, const unsigned *d_cells, double *d_inv_jacobi, void *stream);
+/* vertex-sharing one-ring CSR, ascending (Mesh2D::fillCellNeighborIndices, mesh_2d.cu:107-139), built on
+ * the device in O(C).  Call once with d_indices == NULL to get offsets (and *nnz), then again with
+ * d_indices of *nnz ints. */
+int pfem2_mesh_one_ring(int n_nodes, int n_cells, const unsigned *d_cells, int *d_offsets, int *d_indices, int *nnz,
+                        void *stream);
+
+/* ---- stand-alone device radix sort of (cell key, particle index) pairs (exposed for tests) ---- */
+int pfem2_sort_pairs(int n, int key_bits, unsigned *d_keys, unsigned *d_vals, unsigned *d_keys_tmp, unsigned *d_vals_tmp,
+                     int *result_in_tmp, void *stream);
+
+/* launch accounting: kernels launched by this library since process start (bench.py gpu_launches) */
+long long pfem2_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFEM2_B200_H */

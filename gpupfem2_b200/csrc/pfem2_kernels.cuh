@@ -348,12 +348,11 @@ k_project_cells(int n_cells, ParticleSoA p, const int *__restrict__ cell_start, 
 #pragma unroll
             for (int k = 0; k < 9; ++k) acc[k] = __dadd_rn(acc[k], __shfl_xor_sync(0xffffffffu, acc[k], d, G));
         }
-        if (valid && lane < 9) {
-            double v = acc[0];
+        if (valid) {
+            // after the butterfly every lane of the group holds all nine sums; spread the stores over the lanes
 #pragma unroll
-            for (int k = 1; k < 9; ++k)
-                if (lane == k) v = acc[k];
-            partial[9 * (size_t)c + lane] = v;
+            for (int k = 0; k < 9; ++k)
+                if (lane == (k % G)) partial[9 * (size_t)c + k] = acc[k];
         }
     }
 }

@@ -134,10 +134,9 @@ class ParticleHandler2D:
         the handler, valid until the next mutating call)."""
         p, n = C.c_void_p(), C.c_int(0)
         self._check(self._L.pfem2_export_aos(self._h, C.byref(p), C.byref(n)), "getParticles")
-        out = torch.empty((n.value, 12), dtype=torch.float64, device=self.mesh.device)
-        if n.value:
-            _memcpy_d2d(out.data_ptr(), p.value, n.value * 96)
-        return out
+        if not n.value:
+            return torch.empty((0, 12), dtype=torch.float64, device=self.mesh.device)
+        return _wrap_device(p.value, (n.value, 12), "<f8", self.mesh.device)
 
     # --- pointer-table flavour (deviceVector<double*>::data) --------------------------------------
     def advect_particles_ptrs(self, table: torch.Tensor, time_step, particle_substeps):
@@ -188,9 +187,7 @@ class ParticleHandler2D:
     def cell_starts(self) -> torch.Tensor:
         p = C.c_void_p()
         self._check(self._L.pfem2_cell_starts(self._h, C.byref(p)), "cell_starts")
-        out = torch.empty(self.mesh.n_cells + 1, dtype=torch.int32, device=self.mesh.device)
-        _memcpy_d2d(out.data_ptr(), p.value, 4 * (self.mesh.n_cells + 1))
-        return out
+        return _wrap_device(p.value, (self.mesh.n_cells + 1,), "<i4", self.mesh.device)
 
 
 def _hp(a):
@@ -199,11 +196,15 @@ def _hp(a):
     return a.ctypes.data
 
 
-def _memcpy_d2d(dst, src, nbytes):
-    rt = torch.cuda.cudart()
-    err = rt.cudaMemcpy(dst, src, nbytes, 3)  # cudaMemcpyDeviceToDevice
-    if int(err) != 0:
-        raise Pfem2Error(f"cudaMemcpy failed: {err}")
+class _DevView:
+    """Borrowed device memory exposed through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _wrap_device(ptr, shape, typestr, device):
+    return torch.as_tensor(_DevView(ptr, shape, typestr), device=device)
 
 
 def kernel_launches() -> int:

@@ -1,0 +1,57 @@
+"""The C-ABI library loads and exports every symbol include/pfem2_b200.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from gpupfem2_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pfem2_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pfem2_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_loader_agree():
+    assert sorted(_lib.SYMBOLS) == declared_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.fail(f"{_lib.LIB_PATH} missing: run __graft_entry__.build()")
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(L, s)]
+    assert not missing, f"library does not export {missing}"
+
+
+def test_default_options_and_version():
+    L = _lib.load()
+    o = _lib.Options()
+    L.pfem2_default_options(ctypes.byref(o))
+    assert o.struct_size == ctypes.sizeof(_lib.Options)
+    assert o.subcell_mode == 0 and o.max_division_level == 4 and o.device == -1
+    assert b"sm_100a" in L.pfem2_version()
+
+
+def test_create_rejects_bad_arguments_without_touching_the_gpu():
+    L = _lib.load()
+    h = ctypes.c_void_p()
+    assert L.pfem2_create(ctypes.byref(h), None, 2, None) == _lib.PFEM2_EINVAL
+    view = _lib.MeshView(0, 0, None, None, None, None, None)
+    assert L.pfem2_create(ctypes.byref(h), ctypes.byref(view), 2, None) == _lib.PFEM2_EINVAL
+    assert b"mesh" in L.pfem2_last_error(None)
+    assert L.pfem2_destroy(None) == _lib.PFEM2_OK
+
+
+def test_no_cpu_fallback_in_product_path():
+    """The product package must not import or reference the oracle (it is test infrastructure)."""
+    pkg = os.path.join(ROOT, "gpupfem2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "pfem2_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f

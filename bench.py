@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/sec of the PFEM-2 particle step on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = what the reference's cases do per time step to the particles:
+    advectParticles(F, dt, S) [S x (advect + locate) + distribution check / re-seed]
+    projectVelocityOntoGrid(W) ; correctParticleVelocity(F, W)
+with a frozen synthetic nodal field F (the FEM stage is out of scope).  A particle-step is one live
+particle carried through one such step; value = sum_k P(k) / device time.
+
+Workloads (config.workload):
+    channel16m  synthetic channel, 4000x2000 quads = 16M triangles, level 4 (16/cell, 256M particles):
+                BASELINE.json configs[3], the configuration the metric is quoted on (default; fits one B200).
+                --level 6 gives 36/cell (576M particles); the reference itself caps the level at 4.
+    channel1m   synthetic channel, 1000x500 quads = 1M triangles x 16/cell   (configs[2])
+    poiseuille  the shipped ChannelMesh (8756 triangles, level 2)              (configs[0], isolated mode)
+    cylinder    the shipped CylinderMesh3 (34185 triangles, level 2)           (configs[1], isolated mode)
+
+The JSON line carries `roofline` (dominant kernel, CUDA-event timed on the launching stream, against
+MEASURED_PEAKS.json), `cpu_baseline` (the C++/OpenMP oracle on the host cores, bounded sample) and `e2e`
+(the same metric through the C-ABI call pfem2_step_host with pinned HOST nodal buffers).
+
+--impl reference runs the UNMODIFIED reference: its CUDA ParticleHandler2D (oracle/_ref, built from
+/root/reference) on one B200 -- the reference has no CPU implementation of this path -- or, when that
+build is absent, the oracle port on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES = {  # algorithmic bytes per particle per launch (64 B fp64 SoA state)
+    "advect_locate": 88,  # R(x,y,L,cell)=44 + W(x,y,L,cell)=44, independent of S
+    "project_cells": 44,  # R(L,cell,v)
+    "correct": 60,        # R(L,cell,v)=44 + W(v)=16
+}
+ALG_BYTES_STEP = 192
+
+WORKLOADS = {
+    # name: (nx, ny, lx, ly, default level)
+    "channel16m": (4000, 2000, 20.0, 10.0, 4),
+    "channel1m": (1000, 500, 10.0, 5.0, 4),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                out["sm_max_mhz"] = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if "Active" in v and "Not" not in v:
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def channel_params(args):
+    nx, ny, lx, ly, lvl = WORKLOADS[args.workload]
+    level = args.level or lvl
+    h = lx / nx
+    umax = 1.0
+    dt = args.cfl * h * args.substeps / umax  # CFL per substep at the channel centre
+    return nx, ny, lx, ly, level, umax, dt
+
+
+def workload_description(args):
+    if args.workload in WORKLOADS:
+        nx, ny, lx, ly, level, umax, dt = channel_params(args)
+        return (f"{args.workload}: structured channel {nx}x{ny} quads = {2 * nx * ny} triangles, level {level} "
+                f"({level * level}/cell, {2 * nx * ny * level * level} particles seeded), Poiseuille field, "
+                f"S={args.substeps}, CFL/substep={args.cfl}")
+    return f"{args.workload}: shipped mesh (tests/golden fixture), level {args.level or 2}, S={args.substeps}, isolated mode"
+
+
+# ------------------------------------------------------------------------------------------------
+def build_problem(args, rank, world, device):
+    """-> (DeviceMesh, level, F (fx, fy) device tensors, dt)."""
+    import numpy as np
+    import torch
+
+    from gpupfem2_b200 import handler
+
+    if args.workload in WORKLOADS:
+        nx, ny, lx, ly, level, umax, dt = channel_params(args)
+        dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device)
+        y = dm.vertices[:, 1].contiguous()
+        fx = (4.0 * umax * y * (ly - y) / (ly * ly)).contiguous()
+        fy = torch.zeros_like(fx)
+        return dm, level, (fx, fy), dt
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from gpupfem2_b200.mesh import HostMesh
+
+    name = {"poiseuille": "channel", "cylinder": "cylinder3"}[args.workload]
+    d = np.load(os.path.join(ROOT, "tests", "golden", f"mesh_{name}.npz"))
+    hm = HostMesh(d["vertices"], d["cells"])
+    dm = handler.DeviceMesh(hm, device=device)
+    yv = hm.vertices[:, 1]
+    if args.workload == "poiseuille":  # cases/PoiseuilleFlow2D: dt = 0.01, analytic parabola 0.5 y (1 - y)
+        fx, dt = 0.5 * yv * (1.0 - yv), 0.01
+    else:  # cases/Cylinder2D: dt = 0.001, inflow profile 4 U y (H - y) / H^2 with U = 1.5, H = 0.41
+        fx, dt = 4.0 * 1.5 * yv * (0.41 - yv) / (0.41 * 0.41), 0.001
+    fx = torch.as_tensor(np.ascontiguousarray(fx)).to(device)
+    return dm, args.level or 2, (fx, torch.zeros_like(fx)), dt
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from gpupfem2_b200 import multi_gpu
+
+        return multi_gpu.bench_main(args, rank, world, local)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the particle step has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    from gpupfem2_b200 import handler
+
+    t_setup = time.time()
+    dm, level, F, dt = build_problem(args, rank, world, device)
+    W = (torch.zeros_like(F[0]), torch.zeros_like(F[0]))
+    h = handler.ParticleHandler2D(dm, level, max_division_level=8, capacity_factor=args.capacity_factor)
+    h.seed_particles()
+    h.init_particle_velocity(F)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+    small = h.get_particle_count() * 64 < 256e6  # state could sit in the 126 MB L2 -> flush between timed iterations
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=device) if small else None
+
+    for _ in range(args.warmup):
+        h.step(F, W, dt, args.substeps)
+    h.get_particle_count()
+    torch.cuda.synchronize()
+
+    h.set_profiling(True)
+    h.phase_times(reset=True)
+    launches0 = handler.kernel_launches()
+    sampler = ClockSampler(local)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    counts = []
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        if flush is not None:
+            flush.fill_(float(k))
+        ev[k][0].record()
+        h.step(F, W, dt, args.substeps)
+        ev[k][1].record()
+        counts.append(h.get_particle_count())  # waits only for the advect's counter read-back
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = handler.kernel_launches() - launches0
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(ms)
+    phases = h.phase_times(reset=True)
+    h.set_profiling(False)
+    psteps = float(sum(counts))
+    value = psteps / (total_ms * 1e-3)
+
+    # roofline of the dominant kernel (by device time) among the three algorithmic passes
+    peak, peak_src = peaks()
+    pmean = psteps / args.steps
+    per_phase = {}
+    for name, (pms, calls) in phases.items():
+        per_phase[name] = {"ms_per_step": pms / args.steps, "share": pms / total_ms if total_ms else 0.0}
+        if name in ALG_BYTES and pms > 0:
+            per_phase[name]["alg_GBps"] = ALG_BYTES[name] * pmean / (pms / args.steps * 1e-3) / 1e9
+    dom = max(ALG_BYTES, key=lambda n: phases[n][0])
+    dom_ms = phases[dom][0] / args.steps
+    achieved = ALG_BYTES[dom] * pmean / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "alg_bytes_per_particle": ALG_BYTES[dom],
+                "step": {"achieved": ALG_BYTES_STEP * value / 1e9, "frac": ALG_BYTES_STEP * value / 1e9 / peak,
+                         "alg_bytes_per_particle_step": ALG_BYTES_STEP},
+                "phases": per_phase}
+
+    # e2e: the same step through the C-ABI call with pinned HOST nodal buffers (H2D + D2H inside the timed region)
+    hF = [t.cpu().pin_memory() for t in F]
+    hW = [torch.empty_like(t).pin_memory() for t in hF]
+    e2e_counts = []
+    h.step_host(hF[0], hF[1], hW[0], hW[1], dt, args.substeps)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_counts.append(h.step_host(hF[0], hF[1], hW[0], hW[1], dt, args.substeps))
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    nodal_bytes = 2 * dm.n_nodes * 8
+    e2e = {"value": float(sum(e2e_counts)) / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": nodal_bytes,
+           "d2h_bytes_per_step": nodal_bytes + 32, "ms_per_step": t_e2e / args.steps * 1e3,
+           "api": "pfem2_step_host (C ABI), pinned host nodal buffers in, projected nodal field + count out"}
+
+    state_gb = pmean * 64 / 1e9
+    out = {
+        "metric": "particle-steps/sec (advect+locate+sort+project+correct)", "value": value, "unit": "particle-steps/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_description(args), "particles_mean": pmean, "cells": dm.n_cells, "nodes": dm.n_nodes,
+                   "substeps": args.substeps, "dt": dt,
+                   "l2": (f"flushed between timed iterations (512 MiB write; state {state_gb:.3f} GB could fit the 126 MB L2)"
+                          if small else f"inputs larger than L2 ({state_gb:.1f} GB of particle state per pass)"),
+                   "timing": "CUDA events on the launching (legacy default) stream, one pair per step",
+                   "setup_s": t_setup},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args)
+    h.close()
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_run(nx, ny, lx, ly, level, substeps, cfl, steps, warmup):
+    """Time the C++/OpenMP oracle (test infrastructure, used here only as the reported CPU baseline)."""
+    from gpupfem2_b200.mesh import poiseuille_field, structured_channel
+    from oracle import oracle as orc
+    import numpy as np
+
+    m = orc.complete_mesh(structured_channel(nx, ny, lx, ly, colmajor=True))
+    fx, fy = poiseuille_field(m, 1.0, ly)
+    dt = cfl * (lx / nx) * substeps
+    o = orc.OracleHandler(m, level, max_level=8)
+    o.seed_particles()
+    o.init_particle_velocity(fx, fy)
+    wx, wy = np.zeros_like(fx), np.zeros_like(fx)
+    for _ in range(warmup):
+        o.step(fx, fy, wx, wy, dt, substeps)
+    t0 = time.perf_counter()
+    ps = 0
+    for _ in range(steps):
+        ps += o.step(fx, fy, wx, wy, dt, substeps)
+    t = time.perf_counter() - t0
+    return ps / t, t / steps * 1e3, orc.lib().orc_max_threads(), m.n_cells, ps / steps
+
+
+def cpu_baseline(args):
+    nx, ny, lx, ly = 1000, 500, 10.0, 5.0  # bounded sample: the 1M-triangle channel, same field / CFL / level
+    level = args.level or 4
+    if args.workload in ("poiseuille", "cylinder"):
+        nx, ny, lx, ly, level = 200, 100, 10.0, 5.0, 2
+    try:
+        v, ms, cores, cells, p = oracle_run(nx, ny, lx, ly, level, args.substeps, args.cfl, 3, 1)
+    except Exception as e:  # the oracle is optional infrastructure for this leg
+        return {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+    return {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+            "sample": f"C++/OpenMP oracle, {cells} triangles x {level * level}/cell ({int(p)} particles), 3 steps after 1 warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    base = {"metric": "particle-steps/sec (advect+locate+sort+project+correct)", "unit": "particle-steps/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_description(args)}}
+    if args.workload in WORKLOADS and os.path.exists(exe):
+        nx, ny, lx, ly, level, umax, dt = channel_params(args)
+        level = min(level, 4)  # CONSTANTS::MAX_CELL_DIVISION_LEVEL
+        cmd = [exe, "time", str(nx), str(ny), repr(lx), repr(ly), str(level), str(args.substeps), repr(dt), repr(umax),
+               str(args.steps), str(args.warmup), "1"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=3000)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode == 0 and line:
+            j = json.loads(line[-1])
+            v = j["particle_steps_per_s"]
+            base.update({"value": v, "ms_per_step": j["ms_per_step"],
+                         "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": 1, "kind": "reference",
+                                          "sample": ("the reference's own CUDA ParticleHandler2D (it has no CPU implementation of this "
+                                                     "path), unmodified sources rebuilt for sm_100a, full workload on ONE B200, "
+                                                     f"{j['particles']} particles")},
+                         "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            base["config"]["reference_cells"] = j["cells"]
+            print(json.dumps(base))
+            return
+        sys.stderr.write(f"ref_harness failed (rc={r.returncode}): {r.stderr[-400:]}\n")
+    # fall back to the oracle port on the host cores (bounded sample)
+    cb = cpu_baseline(args)
+    cb_line = dict(cb)
+    base.update({"value": cb["value"], "ms_per_step": cb.get("ms_per_step"), "cpu_baseline": cb_line,
+                 "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="channel16m", choices=list(WORKLOADS) + ["poiseuille", "cylinder"])
+    ap.add_argument("--level", type=int, default=0)
+    ap.add_argument("--substeps", type=int, default=3)
+    ap.add_argument("--cfl", type=float, default=0.25, help="CFL per substep at the channel centre")
+    ap.add_argument("--capacity-factor", type=float, default=1.3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -20,7 +20,8 @@ SYMBOLS = (
     "pfem2_init_velocity", "pfem2_init_velocity_ptrs", "pfem2_advect", "pfem2_advect_ptrs", "pfem2_project",
     "pfem2_project_ptrs", "pfem2_correct", "pfem2_correct_ptrs", "pfem2_particle_count", "pfem2_get_stats",
     "pfem2_export_aos", "pfem2_step_host", "pfem2_download", "pfem2_upload", "pfem2_device_arrays", "pfem2_cell_starts",
-    "pfem2_mesh_inv_jacobi", "pfem2_mesh_one_ring", "pfem2_sort_pairs", "pfem2_kernel_launches",
+    "pfem2_mesh_inv_jacobi", "pfem2_mesh_one_ring", "pfem2_sort_pairs", "pfem2_kernel_launches", "pfem2_set_profiling",
+    "pfem2_get_phase_times",
 )
 
 
@@ -38,6 +39,8 @@ class Stats(C.Structure):
     _fields_ = [("count", C.c_int), ("lost", C.c_int), ("added", C.c_int), ("movers", C.c_int), ("capacity", C.c_int),
                 ("overflow", C.c_int)]
 
+
+PHASES = ("advect_locate", "sort", "reorder", "project_cells", "project_nodes", "correct")
 
 _lib = None
 
@@ -80,5 +83,7 @@ def load():
     L.pfem2_mesh_one_ring.argtypes = [i, i, vp, vp, vp, C.POINTER(i), vp]
     L.pfem2_sort_pairs.argtypes = [i, i, vp, vp, vp, vp, C.POINTER(i), vp]
     L.pfem2_kernel_launches.restype = C.c_longlong
+    L.pfem2_set_profiling.argtypes = [vp, i]
+    L.pfem2_get_phase_times.argtypes = [vp, C.POINTER(d), C.POINTER(C.c_longlong), i]
     _lib = L
     return L

@@ -73,7 +73,13 @@ struct pfem2_handle {
     size_t aos_bytes = 0;
     double *nodal[4] = {nullptr, nullptr, nullptr, nullptr}; // F.x F.y W.x W.y for pfem2_step_host
 
-    std::vector<void *> owned;
+    // optional per-phase CUDA-event timing (pfem2_set_profiling)
+    bool profiling = false;
+    struct PhaseRec { int phase; cudaEvent_t a, b; };
+    std::vector<PhaseRec> phase_recs;
+    std::vector<cudaEvent_t> event_pool;
+    double phase_ms[PFEM2_NUM_PHASES] = {0};
+    long long phase_calls[PFEM2_NUM_PHASES] = {0};
 };
 
 namespace {
@@ -94,6 +100,38 @@ int fail(pfem2_handle *h, int code, const char *msg)
     if (h) h->error = msg; else g_create_error = msg;
     return code;
 }
+
+cudaEvent_t take_event(pfem2_handle *h)
+{
+    if (!h->event_pool.empty()) {
+        cudaEvent_t e = h->event_pool.back();
+        h->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// RAII: brackets the launches of one pipeline phase with CUDA events on the handle's stream
+struct PhaseScope {
+    pfem2_handle *h;
+    pfem2_handle::PhaseRec rec;
+    PhaseScope(pfem2_handle *h_, int phase) : h(h_)
+    {
+        if (!h->profiling) return;
+        rec.phase = phase;
+        rec.a = take_event(h);
+        rec.b = take_event(h);
+        cudaEventRecord(rec.a, h->stream);
+    }
+    ~PhaseScope()
+    {
+        if (!h->profiling) return;
+        cudaEventRecord(rec.b, h->stream);
+        h->phase_recs.push_back(rec);
+    }
+};
 
 template <class T> int dev_alloc(pfem2_handle *h, T **p, size_t n)
 {
@@ -225,8 +263,13 @@ int sort_and_reseed(pfem2_handle *h, bool reseed, NodalVel vel)
 {
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells;
-    const int flip = radix_sort_pairs(h->keys[0], h->vals[0], h->keys[1], h->vals[1], &h->ctr->count, h->capacity, h->key_bits,
-                                      h->rs_hist, h->rs_scan_scratch, st);
+    int flip;
+    {
+        PhaseScope ps(h, PFEM2_PHASE_SORT);
+        flip = radix_sort_pairs(h->keys[0], h->vals[0], h->keys[1], h->vals[1], &h->ctr->count, h->capacity, h->key_bits,
+                                h->rs_hist, h->rs_scan_scratch, st);
+    }
+    PhaseScope ps(h, PFEM2_PHASE_REORDER);
     PFEM2_LAUNCH(k_plan_cells, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->ppc, reseed ? 1 : 0, h->cell_count,
                  h->cell_mask, h->packed);
     exclusive_scan<unsigned long long>(h->packed, h->packed, C, h->scan_scratch64, st);
@@ -265,12 +308,15 @@ int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
     PFEM2_LAUNCH(k_begin_advect, 1, 1, 0, st, h->ctr, h->capacity);
     ParticleSoA p = h->soa[h->cur];
     const int grid = grid_for(h->capacity);
+    {
+    PhaseScope ps(h, PFEM2_PHASE_ADVECT);
     if (h->opt.subcell_mode == 0)
         PFEM2_LAUNCH(k_advect_locate<0>, grid, kThreads, 0, st, p, h->geom, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub,
                      substeps, C, h->ppc, h->level, h->sub_step, h->ctr, h->keys[0], h->vals[0], h->cell_count, h->cell_mask);
     else
         PFEM2_LAUNCH(k_advect_locate<1>, grid, kThreads, 0, st, p, h->geom, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub,
                      substeps, C, h->ppc, h->level, h->sub_step, h->ctr, h->keys[0], h->vals[0], h->cell_count, h->cell_mask);
+    }
     if ((rc = sort_and_reseed(h, true, vel))) return rc;
     if ((rc = queue_readback(h))) return rc;
     if (h->opt.verbose) {
@@ -290,6 +336,8 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
     ParticleSoA p = h->soa[h->cur];
     // lanes per cell: enough to cover the typical segment in one or two strides
     const int ppc = h->ppc;
+    {
+    PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
     if (ppc <= 6)
         PFEM2_LAUNCH(k_project_cells<4>, grid_for((long long)C * 4), kThreads, 0, st, C, p, h->cell_start, h->partial);
     else if (ppc <= 12)
@@ -298,6 +346,8 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
         PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)C * 16), kThreads, 0, st, C, p, h->cell_start, h->partial);
     else
         PFEM2_LAUNCH(k_project_cells<32>, grid_for((long long)C * 32), kThreads, 0, st, C, p, h->cell_start, h->partial);
+    }
+    PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
     PFEM2_LAUNCH(k_project_nodes, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, N, h->node_off, (const int *)h->node_inc, h->partial,
                  vx, vy, table);
     CU(cudaGetLastError());
@@ -311,6 +361,7 @@ int do_correct(pfem2_handle *h, NodalVel v, NodalVel vold, bool has_old)
     CU(cudaSetDevice(h->device));
     ParticleSoA p = h->soa[h->cur];
     const int grid = grid_for(h->capacity);
+    PhaseScope ps(h, PFEM2_PHASE_CORRECT);
     if (has_old)
         PFEM2_LAUNCH(k_correct<true>, grid, kThreads, 0, h->stream, p, h->geom, v, vold, h->ctr);
     else
@@ -479,6 +530,8 @@ int pfem2_destroy(pfem2_handle *h)
     cudaFree(h->cell_count); cudaFree(h->cell_mask); cudaFree(h->packed); cudaFree(h->scan_scratch64);
     cudaFree(h->cell_start); cudaFree(h->partial); cudaFree(h->aos);
     for (double *p : h->nodal) cudaFree(p);
+    for (auto &r : h->phase_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     if (h->host_ctr) cudaFreeHost(h->host_ctr);
     if (h->readback) cudaEventDestroy(h->readback);
     delete h;
@@ -660,6 +713,36 @@ int pfem2_cell_starts(pfem2_handle *h, const int **d_cell_start)
 {
     if (!h || !d_cell_start) return PFEM2_EINVAL;
     *d_cell_start = h->cell_start;
+    return PFEM2_OK;
+}
+
+int pfem2_set_profiling(pfem2_handle *h, int enabled)
+{
+    if (!h) return PFEM2_EINVAL;
+    h->profiling = enabled != 0;
+    return PFEM2_OK;
+}
+
+int pfem2_get_phase_times(pfem2_handle *h, double *ms, long long *calls, int reset)
+{
+    if (!h) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    for (auto &r : h->phase_recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            h->phase_ms[r.phase] += t;
+            h->phase_calls[r.phase] += 1;
+        }
+        h->event_pool.push_back(r.a);
+        h->event_pool.push_back(r.b);
+    }
+    h->phase_recs.clear();
+    for (int k = 0; k < PFEM2_NUM_PHASES; ++k) {
+        if (ms) ms[k] = h->phase_ms[k];
+        if (calls) calls[k] = h->phase_calls[k];
+        if (reset) { h->phase_ms[k] = 0; h->phase_calls[k] = 0; }
+    }
     return PFEM2_OK;
 }
 

@@ -46,9 +46,57 @@ class DeviceMesh:
             self.nbr_offsets, self.nbr_indices = device_one_ring(self.n_nodes, self.cells)
         torch.cuda.synchronize(self.device)
 
+    @classmethod
+    def from_tensors(cls, vertices: torch.Tensor, cells: torch.Tensor):
+        """Build from device tensors (vertices (N,2) float64, cells (C,3) int32 bit-pattern of uint32); inverse
+        Jacobians and the one-ring are computed on the device by the library."""
+        self = cls.__new__(cls)
+        self.device = vertices.device
+        self.n_nodes, self.n_cells = int(vertices.shape[0]), int(cells.shape[0])
+        self.vertices, self.cells = vertices.contiguous(), cells.contiguous()
+        L = _lib.load()
+        self.inv_jacobi = torch.empty((self.n_cells, 4), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = L.pfem2_mesh_inv_jacobi(self.n_cells, self.vertices.data_ptr(), self.cells.data_ptr(),
+                                         self.inv_jacobi.data_ptr(), None)
+        if rc:
+            raise Pfem2Error(L.pfem2_last_error(None).decode())
+        self.nbr_offsets, self.nbr_indices = device_one_ring(self.n_nodes, self.cells)
+        torch.cuda.synchronize(self.device)
+        return self
+
     def view(self) -> _lib.MeshView:
         return _lib.MeshView(self.n_nodes, self.n_cells, self.vertices.data_ptr(), self.cells.data_ptr(),
                              self.inv_jacobi.data_ptr(), self.nbr_offsets.data_ptr(), self.nbr_indices.data_ptr())
+
+
+def device_structured_channel(nx, ny, lx, ly, colmajor=True, device="cuda:0") -> "DeviceMesh":
+    """mesh.structured_channel generated directly in HBM (same numbering and the same x = i*hx, y = j*hy
+    arithmetic, so the vertex bits agree with the host generator and with oracle/ref_harness.cu)."""
+    dev = torch.device(device)
+    hx, hy = lx / nx, ly / ny
+    i = torch.arange(nx + 1, device=dev, dtype=torch.int64)
+    j = torch.arange(ny + 1, device=dev, dtype=torch.int64)
+    if colmajor:  # node = i*(ny+1)+j
+        x = (i.to(torch.float64) * hx)[:, None].expand(nx + 1, ny + 1)
+        y = (j.to(torch.float64) * hy)[None, :].expand(nx + 1, ny + 1)
+    else:  # node = j*(nx+1)+i
+        x = (i.to(torch.float64) * hx)[None, :].expand(ny + 1, nx + 1)
+        y = (j.to(torch.float64) * hy)[:, None].expand(ny + 1, nx + 1)
+    vertices = torch.stack([x.reshape(-1), y.reshape(-1)], dim=1).contiguous()
+
+    def nid(a, b):
+        return a * (ny + 1) + b if colmajor else b * (nx + 1) + a
+
+    qi = torch.arange(nx, device=dev, dtype=torch.int64)
+    qj = torch.arange(ny, device=dev, dtype=torch.int64)
+    if colmajor:  # quad = i*ny+j
+        I, J = qi[:, None].expand(nx, ny).reshape(-1), qj[None, :].expand(nx, ny).reshape(-1)
+    else:  # quad = j*nx+i
+        I, J = qi[None, :].expand(ny, nx).reshape(-1), qj[:, None].expand(ny, nx).reshape(-1)
+    a, b, c, d = nid(I, J), nid(I + 1, J), nid(I + 1, J + 1), nid(I, J + 1)
+    cells = torch.stack([a, b, c, a, c, d], dim=1).reshape(-1, 3).to(torch.int32).contiguous()
+    return DeviceMesh.from_tensors(vertices, cells)
 
 
 def device_one_ring(n_nodes: int, cells: torch.Tensor):
@@ -163,6 +211,17 @@ class ParticleHandler2D:
         n = C.c_int(0)
         self._check(self._L.pfem2_step_host(self._h, _hp(fx), _hp(fy), _hp(wx), _hp(wy), dt, substeps, C.byref(n)), "step_host")
         return n.value
+
+    def set_profiling(self, enabled: bool):
+        self._check(self._L.pfem2_set_profiling(self._h, 1 if enabled else 0), "set_profiling")
+
+    def phase_times(self, reset=True) -> dict:
+        """{phase: (milliseconds, launch groups)} accumulated since the last reset, from CUDA events."""
+        n = len(_lib.PHASES)
+        ms = (C.c_double * n)()
+        calls = (C.c_longlong * n)()
+        self._check(self._L.pfem2_get_phase_times(self._h, ms, calls, 1 if reset else 0), "phase_times")
+        return {name: (ms[k], calls[k]) for k, name in enumerate(_lib.PHASES)}
 
     def stats(self) -> dict:
         s = _lib.Stats()

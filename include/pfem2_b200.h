@@ -136,6 +136,18 @@ int pfem2_mesh_one_ring(int n_nodes, int n_cells, const unsigned *d_cells, int *
 int pfem2_sort_pairs(int n, int key_bits, unsigned *d_keys, unsigned *d_vals, unsigned *d_keys_tmp, unsigned *d_vals_tmp,
                      int *result_in_tmp, void *stream);
 
+/* ---- per-phase device timing (bench.py roofline): CUDA events on the handle's stream around each phase ---- */
+#define PFEM2_PHASE_ADVECT 0        /* k_advect_locate: S substeps of advect + own-cell test + one-ring search */
+#define PFEM2_PHASE_SORT 1          /* radix sort of (cell key, index) pairs */
+#define PFEM2_PHASE_REORDER 2       /* distribution-check plan + scan + gather into cell order + re-seed */
+#define PFEM2_PHASE_PROJECT_CELLS 3 /* per-cell segmented reduction */
+#define PFEM2_PHASE_PROJECT_NODES 4 /* per-node gather + division */
+#define PFEM2_PHASE_CORRECT 5       /* velocity correction */
+#define PFEM2_NUM_PHASES 6
+int pfem2_set_profiling(pfem2_handle *h, int enabled);
+/* accumulated milliseconds and launch-group counts per phase since the last reset (synchronises the stream) */
+int pfem2_get_phase_times(pfem2_handle *h, double *ms, long long *calls, int reset);
+
 /* launch accounting: kernels launched by this library since process start (bench.py gpu_launches) */
 long long pfem2_kernel_launches(void);
 

@@ -289,3 +289,16 @@ def test_live_reference_binary(gpu, oracle, tmp_path):
     mine = h.download()
     assert_states_equal(mine, ref, "vs live reference")
     assert rel_inf(w[0].cpu().numpy(), ref["wx"]) <= REL_TOL and rel_inf(w[1].cpu().numpy(), ref["wy"]) <= REL_TOL
+
+
+def test_device_channel_generator_matches_host(gpu, oracle):
+    from gpupfem2_b200.mesh import structured_channel
+
+    for colmajor in (True, False):
+        hm = oracle.complete_mesh(structured_channel(9, 5, 1.8, 1.0, colmajor=colmajor))
+        dm = gpu.device_structured_channel(9, 5, 1.8, 1.0, colmajor=colmajor)
+        assert np.array_equal(dm.vertices.cpu().numpy(), hm.vertices)
+        assert np.array_equal(dm.cells.cpu().numpy().view(np.uint32), hm.cells)
+        assert np.array_equal(dm.nbr_offsets.cpu().numpy(), hm.nbr_offsets)
+        assert np.array_equal(dm.nbr_indices.cpu().numpy(), hm.nbr_indices)
+        assert np.array_equal(dm.inv_jacobi.cpu().numpy(), hm.inv_jacobi)

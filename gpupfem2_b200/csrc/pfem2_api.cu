@@ -14,6 +14,7 @@
 
 namespace pfem2 {
 long long g_kernel_launches = 0;
+int g_num_sms = 148;
 }
 
 using namespace pfem2;
@@ -58,15 +59,22 @@ struct pfem2_handle {
     bool readback_pending = false;
     int host_count = 0; // last count known on the host
     int host_added = 0;
-    unsigned *keys[2]{}, *vals[2]{};
-    int *cell_count = nullptr;               // n_cells + 1
+    unsigned *keys[2]{}, *vals[2]{};         // (new cell, array index) of the movers, ping-pong for the radix sort
+    unsigned *stay_bits = nullptr;           // capacity / 32 + 2: ballot of particles that stayed in their cell
+    int *warp_movers = nullptr;              // capacity / 32 + 2: movers per warp, scanned in place
+    int *warp_scan_scratch = nullptr;
+    int *stay = nullptr, *arrive = nullptr;  // n_cells + 1 each (one allocation, zeroed together)
     unsigned long long *cell_mask = nullptr; // n_cells + 1
     unsigned long long *packed = nullptr;    // n_cells + 2 (scan in place)
     unsigned long long *scan_scratch64 = nullptr;
-    int *cell_start = nullptr; // n_cells + 1
+    int *cell_start[2] = {nullptr, nullptr}; // n_cells + 1, ping-pong (old / new segment table)
+    int cs = 0;
+    int *n_cells_dev = nullptr;              // device copy of n_cells (scan length)
     int *rs_hist = nullptr;
     int *rs_scan_scratch = nullptr;
+    int *rs_info = nullptr;
     double *partial = nullptr; // 9 * n_cells
+    int4 *edge_nbr = nullptr;  // n_cells: cells across the three edges (-1 = boundary)
 
     // lazily allocated
     void *aos = nullptr;
@@ -140,8 +148,9 @@ template <class T> int dev_alloc(pfem2_handle *h, T **p, size_t n)
     return PFEM2_OK;
 }
 
-int grid_for(long long n, int threads = kThreads, int max_blocks = 148 * 16)
+int grid_for(long long n, int threads = kThreads, int max_blocks = 0)
 {
+    if (max_blocks <= 0) max_blocks = g_num_sms * 16; // persistent grid-stride kernels: a multiple of the SM count
     long long b = (n + threads - 1) / threads;
     return (int)std::max<long long>(1, std::min<long long>(b, max_blocks));
 }
@@ -175,7 +184,24 @@ void free_particle_scratch(pfem2_handle *h)
         h->keys[k] = h->vals[k] = nullptr;
     }
     cudaFree(h->rs_hist); cudaFree(h->rs_scan_scratch);
-    h->rs_hist = h->rs_scan_scratch = nullptr;
+    cudaFree(h->stay_bits); cudaFree(h->warp_movers); cudaFree(h->warp_scan_scratch);
+    h->rs_hist = h->rs_scan_scratch = h->warp_movers = h->warp_scan_scratch = nullptr;
+    h->stay_bits = nullptr;
+}
+
+int alloc_particle_scratch(pfem2_handle *h, int cap)
+{
+    int rc;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = dev_alloc(h, &h->keys[k], cap))) return rc;
+        if ((rc = dev_alloc(h, &h->vals[k], cap))) return rc;
+    }
+    if ((rc = dev_alloc(h, &h->rs_hist, rs_hist_elems(cap)))) return rc;
+    if ((rc = dev_alloc(h, &h->rs_scan_scratch, rs_scan_scratch_elems(cap)))) return rc;
+    if ((rc = dev_alloc(h, &h->stay_bits, (size_t)cap / 32 + 2))) return rc;
+    if ((rc = dev_alloc(h, &h->warp_movers, (size_t)cap / 32 + 2))) return rc;
+    if ((rc = dev_alloc(h, &h->warp_scan_scratch, scan_scratch_elems<int>((long long)cap / 32 + 2)))) return rc;
+    return PFEM2_OK;
 }
 
 int alloc_particle_storage(pfem2_handle *h, int cap)
@@ -183,13 +209,8 @@ int alloc_particle_storage(pfem2_handle *h, int cap)
     int rc;
     for (int k = 0; k < 2; ++k)
         if ((rc = alloc_soa(h, h->soa[k], cap))) return rc;
-    for (int k = 0; k < 2; ++k) {
-        if ((rc = dev_alloc(h, &h->keys[k], cap))) return rc;
-        if ((rc = dev_alloc(h, &h->vals[k], cap))) return rc;
-    }
     // the incidence sort at create() reuses keys/vals, so they hold at least 3 * n_cells entries (ensured by caller)
-    if ((rc = dev_alloc(h, &h->rs_hist, rs_hist_elems(cap)))) return rc;
-    if ((rc = dev_alloc(h, &h->rs_scan_scratch, scan_scratch_elems<int>(kRsRadix * rs_num_tiles(cap))))) return rc;
+    if ((rc = alloc_particle_scratch(h, cap))) return rc;
     h->capacity = cap;
     return PFEM2_OK;
 }
@@ -216,12 +237,7 @@ int grow(pfem2_handle *h, int new_cap)
     free_soa(old);
     h->soa[h->cur] = fresh;
     if ((rc = alloc_soa(h, h->soa[h->cur ^ 1], new_cap))) return rc;
-    for (int k = 0; k < 2; ++k) {
-        if ((rc = dev_alloc(h, &h->keys[k], new_cap))) return rc;
-        if ((rc = dev_alloc(h, &h->vals[k], new_cap))) return rc;
-    }
-    if ((rc = dev_alloc(h, &h->rs_hist, rs_hist_elems(new_cap)))) return rc;
-    if ((rc = dev_alloc(h, &h->rs_scan_scratch, scan_scratch_elems<int>(kRsRadix * rs_num_tiles(new_cap))))) return rc;
+    if ((rc = alloc_particle_scratch(h, new_cap))) return rc;
     h->capacity = new_cap;
     if (h->aos) { cudaFree(h->aos); h->aos = nullptr; h->aos_bytes = 0; }
     return PFEM2_OK;
@@ -257,30 +273,45 @@ NodalVel nodal(const double *x, const double *y, double *const *table)
     return v;
 }
 
-// sort the current buffer by cell into the other buffer, dropping lost particles and (optionally) re-seeding
-// empty sub-cells; expects keys[0]/vals[0], cell_count and cell_mask filled for the current buffer.
-int sort_and_reseed(pfem2_handle *h, bool reseed, NodalVel vel)
+// Re-establish the cell-sorted order in the other buffer: stayers keep their relative order, the movers listed in
+// keys[0]/vals[0] (n = ctr->n_movers, array order) are radix-sorted by new cell and appended behind the stayers of
+// their cell, lost particles are dropped and (optionally) every empty sub-cell is re-seeded.
+int reorder(pfem2_handle *h, bool reseed, bool have_stayers, NodalVel vel)
 {
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells;
     int flip;
     {
         PhaseScope ps(h, PFEM2_PHASE_SORT);
-        flip = radix_sort_pairs(h->keys[0], h->vals[0], h->keys[1], h->vals[1], &h->ctr->count, h->capacity, h->key_bits,
-                                h->rs_hist, h->rs_scan_scratch, st);
+        flip = radix_sort_pairs(h->keys[0], h->vals[0], h->keys[1], h->vals[1], &h->ctr->n_movers, h->capacity, h->key_bits,
+                                h->rs_hist, h->rs_scan_scratch, h->rs_info, st);
     }
     PhaseScope ps(h, PFEM2_PHASE_REORDER);
-    PFEM2_LAUNCH(k_plan_cells, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->ppc, reseed ? 1 : 0, h->cell_count,
-                 h->cell_mask, h->packed);
-    exclusive_scan<unsigned long long>(h->packed, h->packed, C, h->scan_scratch64, st);
+    PFEM2_LAUNCH(k_plan_cells, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->ppc, reseed ? 1 : 0, h->stay, h->arrive,
+                 h->cell_mask, h->packed, h->ctr);
+    exclusive_scan_dev<unsigned long long>(h->packed, h->packed, h->n_cells_dev, 1, 0, C, h->scan_scratch64, st);
     PFEM2_LAUNCH(k_plan_finish, 1, 1, 0, st, C, h->packed, h->ctr);
     ParticleSoA src = h->soa[h->cur], dst = h->soa[h->cur ^ 1];
-    PFEM2_LAUNCH(k_gather_sorted, grid_for(h->capacity), kThreads, 0, st, src, dst, h->keys[flip], h->vals[flip], h->packed, h->ctr);
+    if (have_stayers)
+        PFEM2_LAUNCH(k_scatter_stayers, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->stay_bits,
+                     h->cell_start[h->cs], h->packed, h->ctr);
+    PFEM2_LAUNCH(k_scatter_movers, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_movers, h->keys[flip], h->vals[flip],
+                 h->stay, h->packed, h->ctr);
     PFEM2_LAUNCH(k_reseed, grid_for(C + 1, kThreads, 1 << 30), kThreads, 0, st, C, h->ppc, (const double2 *)h->mesh.d_vertices,
-                 h->geom, h->centers, vel, h->cell_mask, h->packed, dst, h->cell_start, h->ctr);
+                 h->geom, h->centers, vel, h->cell_mask, h->stay, h->arrive, h->packed, dst, h->cell_start[h->cs ^ 1], h->ctr);
     h->cur ^= 1;
+    h->cs ^= 1;
     CU(cudaGetLastError());
     return PFEM2_OK;
+}
+
+template <int MODE, bool WALK, bool MASK64>
+void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps)
+{
+    const int C = h->mesh.n_cells;
+    PFEM2_LAUNCH((k_advect_locate<MODE, WALK, MASK64>), grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->geom,
+                 h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub, substeps, C, h->ppc, h->level, h->sub_step,
+                 h->ctr, h->stay_bits, h->warp_movers, h->stay, h->arrive, h->cell_mask);
 }
 
 int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
@@ -293,9 +324,9 @@ int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
     if ((rc = sync_counters(h))) return rc;
     // capacity policy: keep room for the growth seen so far (re-seeding only ever adds)
     {
-        const long long margin = std::max<long long>({(long long)h->host_count / 4, 4ll * h->host_added, 4096ll});
+        const long long margin = std::max<long long>({(long long)h->host_count / 16, 4ll * h->host_added, 4096ll});
         if ((long long)h->host_count + margin > h->capacity) {
-            const long long want = std::max<long long>((long long)(1.5 * h->host_count), (long long)h->host_count + 2 * margin);
+            const long long want = std::max<long long>((long long)(1.25 * h->host_count), (long long)h->host_count + 2 * margin);
             if (want > 2147483647ll - 1024) return fail(h, PFEM2_ECAPACITY, "particle count exceeds 32-bit indexing");
             if ((rc = grow(h, (int)want))) return rc;
         }
@@ -303,21 +334,31 @@ int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells;
     const double hsub = dt / substeps; // particle_handler_2d.cu:330, host double
-    CU(cudaMemsetAsync(h->cell_count, 0, sizeof(int) * (C + 1), st));
-    CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * (C + 1), st));
+    CU(cudaMemsetAsync(h->stay, 0, sizeof(int) * 2 * ((size_t)C + 1), st)); // stay and arrive are one allocation
+    CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * ((size_t)C + 1), st));
     PFEM2_LAUNCH(k_begin_advect, 1, 1, 0, st, h->ctr, h->capacity);
-    ParticleSoA p = h->soa[h->cur];
-    const int grid = grid_for(h->capacity);
     {
-    PhaseScope ps(h, PFEM2_PHASE_ADVECT);
-    if (h->opt.subcell_mode == 0)
-        PFEM2_LAUNCH(k_advect_locate<0>, grid, kThreads, 0, st, p, h->geom, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub,
-                     substeps, C, h->ppc, h->level, h->sub_step, h->ctr, h->keys[0], h->vals[0], h->cell_count, h->cell_mask);
-    else
-        PFEM2_LAUNCH(k_advect_locate<1>, grid, kThreads, 0, st, p, h->geom, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub,
-                     substeps, C, h->ppc, h->level, h->sub_step, h->ctr, h->keys[0], h->vals[0], h->cell_count, h->cell_mask);
+        PhaseScope ps(h, PFEM2_PHASE_ADVECT);
+        const bool m64 = h->ppc > 32, walk = h->opt.exact_search == 0;
+        const int mode = h->opt.subcell_mode ? 1 : 0;
+#define PFEM2_ADV(M, W, B) launch_advect<M, W, B>(h, vel, hsub, substeps)
+        if (mode == 0) {
+            if (walk) { if (m64) PFEM2_ADV(0, true, true); else PFEM2_ADV(0, true, false); }
+            else      { if (m64) PFEM2_ADV(0, false, true); else PFEM2_ADV(0, false, false); }
+        } else {
+            if (walk) { if (m64) PFEM2_ADV(1, true, true); else PFEM2_ADV(1, true, false); }
+            else      { if (m64) PFEM2_ADV(1, false, true); else PFEM2_ADV(1, false, false); }
+        }
+#undef PFEM2_ADV
     }
-    if ((rc = sort_and_reseed(h, true, vel))) return rc;
+    {
+        PhaseScope ps(h, PFEM2_PHASE_SORT);
+        exclusive_scan_dev<int>(h->warp_movers, h->warp_movers, &h->ctr->n_warps, 1, 0, (long long)h->capacity / 32 + 1,
+                                h->warp_scan_scratch, st);
+        PFEM2_LAUNCH(k_emit_movers, grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], h->ctr, h->stay_bits, h->warp_movers,
+                     h->keys[0], h->vals[0]);
+    }
+    if ((rc = reorder(h, true, true, vel))) return rc;
     if ((rc = queue_readback(h))) return rc;
     if (h->opt.verbose) {
         if ((rc = sync_counters(h))) return rc;
@@ -339,13 +380,13 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
     {
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
     if (ppc <= 6)
-        PFEM2_LAUNCH(k_project_cells<4>, grid_for((long long)C * 4), kThreads, 0, st, C, p, h->cell_start, h->partial);
+        PFEM2_LAUNCH(k_project_cells<4>, grid_for((long long)C * 4), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
     else if (ppc <= 12)
-        PFEM2_LAUNCH(k_project_cells<8>, grid_for((long long)C * 8), kThreads, 0, st, C, p, h->cell_start, h->partial);
+        PFEM2_LAUNCH(k_project_cells<8>, grid_for((long long)C * 8), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
     else if (ppc <= 24)
-        PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)C * 16), kThreads, 0, st, C, p, h->cell_start, h->partial);
+        PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)C * 16), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
     else
-        PFEM2_LAUNCH(k_project_cells<32>, grid_for((long long)C * 32), kThreads, 0, st, C, p, h->cell_start, h->partial);
+        PFEM2_LAUNCH(k_project_cells<32>, grid_for((long long)C * 32), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
     }
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
     PFEM2_LAUNCH(k_project_nodes, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, N, h->node_off, (const int *)h->node_inc, h->partial,
@@ -387,9 +428,10 @@ int build_node_incidence(pfem2_handle *h)
     int bits = 1;
     while ((1ll << bits) < N) ++bits;
     const int flip = radix_sort_pairs(h->keys[0], h->vals[0], h->keys[1], h->vals[1], n_dev, h->capacity, bits, h->rs_hist,
-                                      h->rs_scan_scratch, st);
+                                      h->rs_scan_scratch, h->rs_info, st);
     CU(cudaMemcpyAsync(h->node_inc, h->vals[flip], sizeof(unsigned) * (size_t)m, cudaMemcpyDeviceToDevice, st));
-    exclusive_scan<int>(count, h->node_off, N, scratch, st);
+    CU(cudaMemcpyAsync(n_dev, &N, sizeof(int), cudaMemcpyHostToDevice, st));
+    exclusive_scan_dev<int>(count, h->node_off, n_dev, 1, 0, N, scratch, st);
     CU(cudaStreamSynchronize(st));
     cudaFree(count); cudaFree(n_dev); cudaFree(scratch);
     return PFEM2_OK;
@@ -436,6 +478,10 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
     int dev = opt.device;
     if (dev < 0) CU(cudaGetDevice(&dev));
     CU(cudaSetDevice(dev));
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_num_sms = sms;
+    }
     h = new pfem2_handle;
     h->device = dev;
     h->opt = opt;
@@ -487,11 +533,16 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
     TRY(dev_alloc(h, &h->node_inc, 3 * (size_t)C));
     TRY(dev_alloc(h, &h->centers, cen.size()));
     TRY(dev_alloc(h, &h->ctr, 1));
-    TRY(dev_alloc(h, &h->cell_count, (size_t)C + 1));
+    TRY(dev_alloc(h, &h->stay, 2 * ((size_t)C + 1)));
+    h->arrive = h->stay + ((size_t)C + 1);
+    TRY(dev_alloc(h, &h->n_cells_dev, 1));
+    TRY(dev_alloc(h, &h->rs_info, 4));
+    TRY(dev_alloc(h, &h->edge_nbr, (size_t)C));
     TRY(dev_alloc(h, &h->cell_mask, (size_t)C + 1));
     TRY(dev_alloc(h, &h->packed, (size_t)C + 2));
     TRY(dev_alloc(h, &h->scan_scratch64, scan_scratch_elems<unsigned long long>(C)));
-    TRY(dev_alloc(h, &h->cell_start, (size_t)C + 1));
+    TRY(dev_alloc(h, &h->cell_start[0], (size_t)C + 1));
+    TRY(dev_alloc(h, &h->cell_start[1], (size_t)C + 1));
     TRY(dev_alloc(h, &h->partial, 9 * (size_t)C));
     {
         cudaError_t e = cudaMallocHost((void **)&h->host_ctr, sizeof(Counters));
@@ -512,6 +563,18 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
     PFEM2_LAUNCH(k_build_geom, grid_for(C, kThreads, 1 << 30), kThreads, 0, h->stream, C, (const double2 *)mesh->d_vertices, mesh->d_cells,
                  mesh->d_inv_jacobi, h->geom);
     PFEM2_LAUNCH(k_set_counters, 1, 1, 0, h->stream, h->ctr, 0, h->capacity);
+    {
+        // locate acceleration data (edge neighbours, strict-interior margins); partial[] doubles as scratch
+        double *hmin = h->partial;
+        unsigned long long *dmax = h->packed;
+        cudaError_t e = cudaMemsetAsync(dmax, 0, sizeof(unsigned long long), h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->n_cells_dev, &C, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { h->error = cudaGetErrorString(e); TRY(PFEM2_ECUDA); }
+        PFEM2_LAUNCH(k_cell_metrics, grid_for(C, kThreads, 1 << 30), kThreads, 0, h->stream, C, (const double2 *)mesh->d_vertices, h->geom,
+                     hmin, dmax);
+        PFEM2_LAUNCH(k_build_locate_data, grid_for(C, kThreads, 1 << 30), kThreads, 0, h->stream, C, h->geom, mesh->d_nbr_offsets,
+                     mesh->d_nbr_indices, hmin, dmax, h->edge_nbr);
+    }
     TRY(build_node_incidence(h));
 #undef TRY
     *out = h;
@@ -527,8 +590,9 @@ int pfem2_destroy(pfem2_handle *h)
     free_soa(h->soa[1]);
     free_particle_scratch(h);
     cudaFree(h->geom); cudaFree(h->node_off); cudaFree(h->node_inc); cudaFree(h->centers); cudaFree(h->ctr);
-    cudaFree(h->cell_count); cudaFree(h->cell_mask); cudaFree(h->packed); cudaFree(h->scan_scratch64);
-    cudaFree(h->cell_start); cudaFree(h->partial); cudaFree(h->aos);
+    cudaFree(h->stay); cudaFree(h->cell_mask); cudaFree(h->packed); cudaFree(h->scan_scratch64);
+    cudaFree(h->cell_start[0]); cudaFree(h->cell_start[1]); cudaFree(h->partial); cudaFree(h->aos);
+    cudaFree(h->n_cells_dev); cudaFree(h->rs_info); cudaFree(h->edge_nbr);
     for (double *p : h->nodal) cudaFree(p);
     for (auto &r : h->phase_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
@@ -544,9 +608,10 @@ int pfem2_seed(pfem2_handle *h)
     CU(cudaSetDevice(h->device));
     const int C = h->mesh.n_cells;
     h->cur = 0;
+    h->cs = 0;
     PFEM2_LAUNCH(k_set_counters, 1, 1, 0, h->stream, h->ctr, 0, h->capacity);
     PFEM2_LAUNCH(k_seed, grid_for((long long)C * h->ppc), kThreads, 0, h->stream, C, h->ppc, (const double2 *)h->mesh.d_vertices, h->geom,
-                 h->centers, h->soa[0], h->cell_start, h->ctr);
+                 h->centers, h->soa[0], h->cell_start[0], h->ctr);
     CU(cudaGetLastError());
     h->seeded = true;
     h->host_count = C * h->ppc;
@@ -690,10 +755,10 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
     CU(cp(p.vx, vx)); CU(cp(p.vy, vy)); CU(cp(p.cell, cell));
     if (id) CU(cp(p.id, id)); else CU(cudaMemsetAsync(p.id, 0, sizeof(unsigned) * (size_t)n, st));
     PFEM2_LAUNCH(k_set_counters, 1, 1, 0, st, h->ctr, n, h->capacity);
-    CU(cudaMemsetAsync(h->cell_count, 0, sizeof(int) * (C + 1), st));
-    CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * (C + 1), st));
-    PFEM2_LAUNCH(k_keys_from_cells, grid_for(h->capacity), kThreads, 0, st, p, C, h->ctr, h->keys[0], h->vals[0], h->cell_count);
-    if ((rc = sort_and_reseed(h, false, nodal(nullptr, nullptr, nullptr)))) return rc;
+    CU(cudaMemsetAsync(h->stay, 0, sizeof(int) * 2 * ((size_t)C + 1), st));
+    CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * ((size_t)C + 1), st));
+    PFEM2_LAUNCH(k_all_movers, grid_for(h->capacity), kThreads, 0, st, p, C, h->ctr, h->keys[0], h->vals[0], h->arrive, &h->ctr->n_movers);
+    if ((rc = reorder(h, false, false, nodal(nullptr, nullptr, nullptr)))) return rc;
     h->seeded = true;
     if ((rc = queue_readback(h))) return rc;
     return sync_counters(h);
@@ -712,7 +777,7 @@ int pfem2_device_arrays(pfem2_handle *h, const double **x, const double **y, con
 int pfem2_cell_starts(pfem2_handle *h, const int **d_cell_start)
 {
     if (!h || !d_cell_start) return PFEM2_EINVAL;
-    *d_cell_start = h->cell_start;
+    *d_cell_start = h->cell_start[h->cs];
     return PFEM2_OK;
 }
 
@@ -764,11 +829,11 @@ int pfem2_sort_pairs(int n, int key_bits, unsigned *keys, unsigned *vals, unsign
         return fail(nullptr, PFEM2_EINVAL, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     int *n_dev = nullptr, *hist = nullptr, *scratch = nullptr;
-    CU(cudaMalloc((void **)&n_dev, sizeof(int)));
+    CU(cudaMalloc((void **)&n_dev, 8 * sizeof(int)));
     CU(cudaMalloc((void **)&hist, sizeof(int) * rs_hist_elems(std::max(n, 1))));
-    CU(cudaMalloc((void **)&scratch, sizeof(int) * scan_scratch_elems<int>(kRsRadix * rs_num_tiles(std::max(n, 1)))));
+    CU(cudaMalloc((void **)&scratch, sizeof(int) * rs_scan_scratch_elems(std::max(n, 1))));
     CU(cudaMemcpyAsync(n_dev, &n, sizeof(int), cudaMemcpyHostToDevice, st));
-    *result_in_tmp = radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n_dev, n, key_bits, hist, scratch, st);
+    *result_in_tmp = radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n_dev, n, key_bits, hist, scratch, n_dev + 4, st);
     CU(cudaStreamSynchronize(st));
     cudaFree(n_dev); cudaFree(hist); cudaFree(scratch);
     CU(cudaGetLastError());
@@ -789,7 +854,7 @@ int pfem2_mesh_one_ring(int n_nodes, int n_cells, const unsigned *d_cells, int *
     CU(cudaMalloc((void **)&node_off, sizeof(int) * ((size_t)n_nodes + 1)));
     CU(cudaMalloc((void **)&n_dev, sizeof(int))); CU(cudaMalloc((void **)&err, sizeof(int)));
     CU(cudaMalloc((void **)&hist, sizeof(int) * rs_hist_elems(m)));
-    CU(cudaMalloc((void **)&scratch, sizeof(int) * scan_scratch_elems<int>(kRsRadix * rs_num_tiles(m))));
+    CU(cudaMalloc((void **)&scratch, sizeof(int) * rs_scan_scratch_elems(m)));
     CU(cudaMalloc((void **)&scratch2, sizeof(int) * scan_scratch_elems<int>(std::max(n_nodes, n_cells))));
     CU(cudaMemsetAsync(count, 0, sizeof(int) * ((size_t)n_nodes + 1), st));
     CU(cudaMemsetAsync(err, 0, sizeof(int), st));
@@ -797,14 +862,22 @@ int pfem2_mesh_one_ring(int n_nodes, int n_cells, const unsigned *d_cells, int *
     PFEM2_LAUNCH(k_incidence_keys, grid_for(m, kThreads, 1 << 30), kThreads, 0, st, n_cells, d_cells, k0, v0, count);
     int bits = 1;
     while ((1ll << bits) < n_nodes) ++bits;
-    const int flip = radix_sort_pairs(k0, v0, k1, v1, n_dev, m, bits, hist, scratch, st);
+    int *info;
+    CU(cudaMalloc((void **)&info, 4 * sizeof(int)));
+    const int flip = radix_sort_pairs(k0, v0, k1, v1, n_dev, m, bits, hist, scratch, info, st);
     const unsigned *inc = flip ? v1 : v0;
-    exclusive_scan<int>(count, node_off, n_nodes, scratch2, st);
+    int *len_dev;
+    CU(cudaMalloc((void **)&len_dev, 2 * sizeof(int)));
+    {
+        const int lens[2] = {n_nodes, n_cells};
+        CU(cudaMemcpyAsync(len_dev, lens, sizeof lens, cudaMemcpyHostToDevice, st));
+    }
+    exclusive_scan_dev<int>(count, node_off, len_dev, 1, 0, n_nodes, scratch2, st);
     if (!d_indices) {
         int *counts = (int *)k0 == (int *)inc ? (int *)k1 : (int *)k0; // any free buffer of >= n_cells ints
         counts = flip ? (int *)k0 : (int *)k1;
         PFEM2_LAUNCH(k_one_ring, grid_for(n_cells, 128, 1 << 30), 128, 0, st, n_cells, d_cells, node_off, inc, counts, nullptr, nullptr, err);
-        exclusive_scan<int>(counts, d_offsets, n_cells, scratch2, st);
+        exclusive_scan_dev<int>(counts, d_offsets, len_dev + 1, 1, 0, n_cells, scratch2, st);
     } else {
         PFEM2_LAUNCH(k_one_ring, grid_for(n_cells, 128, 1 << 30), 128, 0, st, n_cells, d_cells, node_off, inc, nullptr, d_offsets, d_indices, err);
     }
@@ -813,7 +886,7 @@ int pfem2_mesh_one_ring(int n_nodes, int n_cells, const unsigned *d_cells, int *
     CU(cudaMemcpyAsync(nnz, d_offsets + n_cells, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(count); cudaFree(node_off); cudaFree(n_dev);
-    cudaFree(err); cudaFree(hist); cudaFree(scratch); cudaFree(scratch2);
+    cudaFree(err); cudaFree(hist); cudaFree(scratch); cudaFree(scratch2); cudaFree(len_dev); cudaFree(info);
     CU(cudaGetLastError());
     if (herr) return fail(nullptr, PFEM2_EINVAL, "a cell has more than 96 one-ring neighbours");
     return PFEM2_OK;

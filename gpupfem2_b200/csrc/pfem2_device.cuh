@@ -22,7 +22,7 @@ struct __align__(16) CellGeom {
     double j0, j1, j2, j3; // Matrix2x2::data, row-major (cuda_math.cuh:180)
     double v3x, v3y;       // vertices[cells[c].z]
     unsigned n0, n1, n2;   // cells[c].{x,y,z}
-    unsigned pad;
+    unsigned pad;          // float bits: strict-interior margin of the locate fast path (k_build_locate_data)
 };
 static_assert(sizeof(CellGeom) == 64, "CellGeom must be one 64-byte record");
 
@@ -44,7 +44,10 @@ struct Counters {
     int movers;   // particle-substeps that left their cell
     int overflow; // capacity exceeded
     int capacity;
-    int pad;
+    int n_old;    // array length before the advect in flight
+    int n_warps;  // ceil(n_old / 32)
+    int n_movers; // particles that changed cell in the advect in flight
+    int pad[2];
 };
 
 __device__ __forceinline__ CellGeom load_geom(const CellGeom *__restrict__ g, unsigned c)

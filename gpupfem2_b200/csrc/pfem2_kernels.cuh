@@ -93,20 +93,91 @@ k_seed(int n_cells, int ppc, const double2 *__restrict__ vertices, const CellGeo
 }
 
 // ---------------------------------------------------------------------------------------------
+// locate helpers
+// ---------------------------------------------------------------------------------------------
+// Exact rule of kCheckParticleInNeighbors (:133-162): ascending one-ring of cell c, first accepting cell wins.
+__device__ __forceinline__ bool ring_scan(const CellGeom *__restrict__ geom, const int *__restrict__ nbr_off,
+                                          const int *__restrict__ nbr_idx, unsigned &c, double x, double y, double &L0,
+                                          double &L1, double &L2)
+{
+    const int k1 = __ldg(nbr_off + c + 1);
+    for (int k = __ldg(nbr_off + c); k < k1; ++k) {
+        const unsigned nb = (unsigned)__ldg(nbr_idx + k);
+        const CellGeom gn = load_geom(geom, nb);
+        double a0, a1, a2;
+        to_local(gn, x, y, a0, a1, a2);
+        if (inside_unit(a0, a1, a2)) {
+            c = nb;
+            L0 = a0; L1 = a1; L2 = a2;
+            return true;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool shares_vertex(const CellGeom &a, const CellGeom &b)
+{
+    return a.n0 == b.n0 || a.n0 == b.n1 || a.n0 == b.n2 || a.n1 == b.n0 || a.n1 == b.n1 || a.n1 == b.n2 || a.n2 == b.n0 ||
+           a.n2 == b.n1 || a.n2 == b.n2;
+}
+
+// Locate a particle that left cell c (own-cell test failed with local coordinates a0..a2).
+// Fast path: walk across the edge with the most negative coordinate, up to kWalkHops cells.  A cell T in which
+// the point is STRICTLY interior by the per-cell margin (CellGeom.pad, set at create so that no other cell of a
+// non-overlapping triangulation can accept the point even with the +-2e-6 tolerance: DESIGN.md "locate") is the
+// unique acceptor, so the reference's ordered scan would return exactly T if T is in the one-ring of c, and would
+// delete the particle otherwise.  Everything else (tolerance band, domain boundary, hop limit) falls back to the
+// ordered scan itself, so the result is always the reference's rule.
+constexpr int kWalkHops = 3;
+template <bool WALK>
+__device__ __forceinline__ bool locate_mover(const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
+                                             const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx,
+                                             const CellGeom &g0, unsigned &c, double x, double y, double a0, double a1,
+                                             double a2, double &L0, double &L1, double &L2)
+{
+    if (WALK) {
+        unsigned cur = c;
+#pragma unroll 1
+        for (int hop = 0; hop < kWalkHops; ++hop) {
+            const int4 e = __ldg(edge_nbr + cur);
+            const int nxt = (a0 <= a1 && a0 <= a2) ? e.x : ((a1 <= a2) ? e.y : e.z);
+            if (nxt < 0) break; // domain boundary: let the ordered scan decide
+            const CellGeom gn = load_geom(geom, (unsigned)nxt);
+            to_local(gn, x, y, a0, a1, a2);
+            const double m = (double)__uint_as_float(gn.pad);
+            if (a0 > m && a1 > m && a2 > m) { // strictly interior: unique acceptor
+                if (!shares_vertex(g0, gn)) return false; // acceptor outside the one-ring -> deleted
+                c = (unsigned)nxt;
+                L0 = a0; L1 = a1; L2 = a2;
+                return true;
+            }
+            if (inside_unit(a0, a1, a2)) break; // accepted inside the tolerance band: ties possible -> ordered scan
+            cur = (unsigned)nxt;
+        }
+    }
+    return ring_scan(geom, nbr_off, nbr_idx, c, x, y, L0, L1, L2);
+}
+
+// ---------------------------------------------------------------------------------------------
 // advect + locate, all S substeps fused in one pass over the particles
 //   kAdvectParticles :54-70, kCheckParticleInCell :117-131, kCheckParticleInNeighbors :133-162.
 // The nodal field is frozen inside advectParticles and particles do not interact, so the S substeps
-// need no global barrier between them.  A particle with no accepting cell in
-// own ∪ one-ring is marked lost (cell = kLostCell) and dropped by the following sort.
-// Also accumulates, per surviving particle: the live count of its cell, and its sub-cell bit in the
-// cell occupancy mask with the reference's flat, unclamped index (kCountParticlesInSubcells :173-181).
+// need no global barrier between them.  Positions, local coordinates and the new cell are
+// written in place.  A particle with no accepting cell in own ∪ one-ring is marked lost.
+// Per warp of 32 consecutive particles the kernel also emits
+//   stay_bits[w]    ballot of particles that end in the cell they started in (they keep their array order),
+//   warp_movers[w]  number of particles that changed cell (sorted separately by new cell),
+// and accumulates per cell, with one atomic per distinct cell per warp (match_any aggregation):
+//   stay[c], arrive[c]  survivors that stayed in / moved into cell c,
+//   cell_mask[c]        sub-cell occupancy bits, flat unclamped index like kCountParticlesInSubcells (:173-181).
 // ---------------------------------------------------------------------------------------------
-template <int SUBCELL_MODE>
+template <int SUBCELL_MODE, bool WALK, bool MASK64>
 __global__ void __launch_bounds__(kThreads)
-k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int *__restrict__ nbr_off,
-                const int *__restrict__ nbr_idx, NodalVel vel, double h, int substeps, int n_cells, int ppc, int level,
-                double sub_step, Counters *ctr, unsigned *__restrict__ keys, unsigned *__restrict__ vals,
-                int *__restrict__ cell_count, unsigned long long *__restrict__ cell_mask)
+k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
+                const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, NodalVel vel, double h, int substeps,
+                int n_cells, int ppc, int level, double sub_step, Counters *ctr, unsigned *__restrict__ stay_bits,
+                int *__restrict__ warp_movers, int *__restrict__ stay, int *__restrict__ arrive,
+                unsigned long long *__restrict__ cell_mask)
 {
     const double *__restrict__ Vx, *__restrict__ Vy;
     {
@@ -116,68 +187,89 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int *__r
         Vy = b;
     }
     const int n = ctr->count;
+    const int lane = threadIdx.x & 31;
     int my_movers = 0, my_lost = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        unsigned c = p.cell[i];
-        double x = p.x[i], y = p.y[i];
-        double L0 = p.l0[i], L1 = p.l1[i], L2 = p.l2[i];
+    // warp-uniform loop (the aggregation below uses full-mask warp intrinsics); base is a multiple of 32
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        const bool valid = i < n;
+        unsigned c0 = 0, c = 0;
+        double x = 0, y = 0, L0 = 0, L1 = 0, L2 = 0;
         bool lost = false;
-        for (int s = 0; s < substeps; ++s) {
-            const CellGeom g = load_geom(geom, c);
-            // kAdvectParticles: velocity from the STORED local position and cell
-            const double ux = interp3(L0, L1, L2, __ldg(Vx + g.n0), __ldg(Vx + g.n1), __ldg(Vx + g.n2));
-            const double uy = interp3(L0, L1, L2, __ldg(Vy + g.n0), __ldg(Vy + g.n1), __ldg(Vy + g.n2));
-            x = __fma_rn(ux, h, x);
-            y = __fma_rn(uy, h, y);
-            // own cell first (wins even if a neighbour would also accept)
-            double a0, a1, a2;
-            to_local(g, x, y, a0, a1, a2);
-            if (inside_unit(a0, a1, a2)) {
-                L0 = a0; L1 = a1; L2 = a2;
-                continue;
-            }
-            ++my_movers;
-            // ascending one-ring, first accepting cell wins
-            bool found = false;
-            const int k1 = __ldg(nbr_off + c + 1);
-            for (int k = __ldg(nbr_off + c); k < k1; ++k) {
-                const unsigned nb = (unsigned)__ldg(nbr_idx + k);
-                const CellGeom gn = load_geom(geom, nb);
-                to_local(gn, x, y, a0, a1, a2);
+        if (valid) {
+            c0 = c = p.cell[i];
+            x = p.x[i];
+            y = p.y[i];
+            L0 = p.l0[i];
+            L1 = p.l1[i];
+            L2 = p.l2[i];
+#pragma unroll 1
+            for (int s = 0; s < substeps; ++s) {
+                const CellGeom g = load_geom(geom, c);
+                // kAdvectParticles: velocity from the STORED local position and cell
+                const double ux = interp3(L0, L1, L2, __ldg(Vx + g.n0), __ldg(Vx + g.n1), __ldg(Vx + g.n2));
+                const double uy = interp3(L0, L1, L2, __ldg(Vy + g.n0), __ldg(Vy + g.n1), __ldg(Vy + g.n2));
+                x = __fma_rn(ux, h, x);
+                y = __fma_rn(uy, h, y);
+                // own cell first (wins even if a neighbour would also accept)
+                double a0, a1, a2;
+                to_local(g, x, y, a0, a1, a2);
                 if (inside_unit(a0, a1, a2)) {
-                    c = nb;
                     L0 = a0; L1 = a1; L2 = a2;
-                    found = true;
+                    continue;
+                }
+                ++my_movers;
+                if (!locate_mover<WALK>(geom, edge_nbr, nbr_off, nbr_idx, g, c, x, y, a0, a1, a2, L0, L1, L2)) {
+                    lost = true;
                     break;
                 }
             }
-            if (!found) {
-                lost = true;
-                break;
+            p.x[i] = x;
+            p.y[i] = y;
+            if (lost) {
+                p.cell[i] = kLostCell;
+                ++my_lost;
+            } else {
+                p.l0[i] = L0;
+                p.l1[i] = L1;
+                p.l2[i] = L2;
+                if (c != c0) p.cell[i] = c;
             }
         }
-        p.x[i] = x;
-        p.y[i] = y;
-        vals[i] = (unsigned)i;
-        if (lost) {
-            p.cell[i] = kLostCell;
-            keys[i] = (unsigned)n_cells; // sorts behind every live particle
-            ++my_lost;
-        } else {
-            p.l0[i] = L0;
-            p.l1[i] = L1;
-            p.l2[i] = L2;
-            p.cell[i] = c;
-            keys[i] = c;
-            atomicAdd(cell_count + c, 1);
-            const int sub = SUBCELL_MODE == 0 ? subcell_index(L0, L1, L2, level, sub_step)
-                                              : subcell_index_clamped(L0, L1, L2, level, sub_step);
-            // reference: ++hist[cellID * ppc + sub] in unsigned arithmetic, unchecked
-            const unsigned long long flat = (unsigned long long)(unsigned)(c * (unsigned)ppc + (unsigned)sub);
-            if (flat < (unsigned long long)n_cells * ppc) {
-                const unsigned fc = (unsigned)(flat / (unsigned)ppc);
-                atomicOr(cell_mask + fc, 1ull << (unsigned)(flat - (unsigned long long)fc * ppc));
+        const bool live = valid && !lost;
+        const bool stays = live && c == c0;
+        const unsigned sb = __ballot_sync(0xffffffffu, stays);
+        const unsigned mb = __ballot_sync(0xffffffffu, live && !stays);
+        if (lane == 0) {
+            stay_bits[base >> 5] = sb;
+            warp_movers[base >> 5] = __popc(mb);
+        }
+        // per-cell survivor counts: one atomic per distinct (cell, stays) pair in the warp
+        {
+            const unsigned key = live ? (c * 2u + (stays ? 1u : 0u)) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (live && (peers & ((1u << lane) - 1)) == 0) atomicAdd((stays ? stay : arrive) + c, __popc(peers));
+        }
+        // sub-cell occupancy: bits OR-reduced per target word across the warp, one atomicOr per word
+        {
+            unsigned fc = 0xffffffffu;
+            unsigned long long bit = 0;
+            if (live) {
+                const int sub = SUBCELL_MODE == 0 ? subcell_index(L0, L1, L2, level, sub_step)
+                                                  : subcell_index_clamped(L0, L1, L2, level, sub_step);
+                // reference: ++hist[cellID * ppc + sub] in unsigned arithmetic, unchecked
+                const unsigned long long flat = (unsigned long long)(unsigned)(c * (unsigned)ppc + (unsigned)sub);
+                if (flat < (unsigned long long)n_cells * ppc) {
+                    fc = (unsigned)(flat / (unsigned)ppc);
+                    bit = 1ull << (unsigned)(flat - (unsigned long long)fc * ppc);
+                }
             }
+            const unsigned peers = __match_any_sync(0xffffffffu, fc);
+            unsigned lo = __reduce_or_sync(peers, (unsigned)bit);
+            unsigned hi = 0;
+            if (MASK64) hi = __reduce_or_sync(peers, (unsigned)(bit >> 32));
+            if (fc != 0xffffffffu && (peers & ((1u << lane) - 1)) == 0)
+                atomicOr(cell_mask + fc, (unsigned long long)lo | ((unsigned long long)hi << 32));
         }
     }
     // block-level reduction of the two statistics counters
@@ -193,46 +285,76 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int *__r
     }
 }
 
-// keys / counts of an existing (possibly unsorted) array, used by upload(): no motion, no re-seeding
+// movers -> (new cell, array index) pairs in array order, at the positions the scan of warp_movers assigns
 __global__ void __launch_bounds__(kThreads)
-k_keys_from_cells(ParticleSoA p, int n_cells, Counters *ctr, unsigned *__restrict__ keys, unsigned *__restrict__ vals,
-                  int *__restrict__ cell_count)
+k_emit_movers(ParticleSoA p, Counters *ctr, const unsigned *__restrict__ stay_bits,
+              const int *__restrict__ warp_mover_base, unsigned *__restrict__ keys, unsigned *__restrict__ vals)
+{
+    const int n = ctr->count;
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        const unsigned sb = __ldg(stay_bits + (base >> 5));
+        unsigned c = kLostCell;
+        if (i < n && !((sb >> lane) & 1u)) c = p.cell[i];
+        const bool mover = c != kLostCell;
+        const unsigned mb = __ballot_sync(0xffffffffu, mover);
+        if (mover) {
+            const int pos = __ldg(warp_mover_base + (base >> 5)) + __popc(mb & ((1u << lane) - 1));
+            keys[pos] = c;
+            vals[pos] = (unsigned)i;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->n_movers = warp_mover_base[ctr->n_warps]; // scan total
+}
+
+// upload(): an arbitrary (unsorted) array is handled as "everybody is a mover"
+__global__ void __launch_bounds__(kThreads)
+k_all_movers(ParticleSoA p, int n_cells, Counters *ctr, unsigned *__restrict__ keys, unsigned *__restrict__ vals,
+             int *__restrict__ arrive, int *__restrict__ n_movers)
 {
     const int n = ctr->count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned c = p.cell[i];
+        unsigned c = p.cell[i];
+        if (c >= (unsigned)n_cells) c = (unsigned)n_cells - 1; // caller validated; keep memory safe regardless
+        keys[i] = c;
         vals[i] = (unsigned)i;
-        if (c < (unsigned)n_cells) {
-            keys[i] = c;
-            atomicAdd(cell_count + c, 1);
-        } else {
-            keys[i] = (unsigned)n_cells;
-        }
+        atomicAdd(arrive + c, 1);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_movers = n;
 }
 
 // ---------------------------------------------------------------------------------------------
 // distribution check, planning part: kCountParticlesToBeAdded (:183-195)
-//   packed[c] = live(c) | missing(c) << 32   (one 64-bit scan yields both prefix sums)
+//   packed[c] = (stay + arrive + missing)(c) | arrive(c) << 32   (one 64-bit scan yields both prefix sums)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_plan_cells(int n_cells, int ppc, int reseed, const int *__restrict__ cell_count,
-             const unsigned long long *__restrict__ cell_mask, unsigned long long *__restrict__ packed)
+k_plan_cells(int n_cells, int ppc, int reseed, const int *__restrict__ stay, const int *__restrict__ arrive,
+             const unsigned long long *__restrict__ cell_mask, unsigned long long *__restrict__ packed, Counters *ctr)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cells) return;
-    const unsigned long long full = ppc >= 64 ? ~0ull : ((1ull << ppc) - 1ull);
-    const int missing = reseed ? ppc - __popcll(cell_mask[c] & full) : 0;
-    packed[c] = (unsigned long long)(unsigned)cell_count[c] | ((unsigned long long)(unsigned)missing << 32);
+    int missing = 0;
+    if (c < n_cells) {
+        const unsigned long long full = ppc >= 64 ? ~0ull : ((1ull << ppc) - 1ull);
+        missing = reseed ? ppc - __popcll(cell_mask[c] & full) : 0;
+        const unsigned a = (unsigned)arrive[c];
+        packed[c] = (unsigned long long)((unsigned)stay[c] + a + (unsigned)missing) | ((unsigned long long)a << 32);
+    }
+    // total number of re-seeded particles
+    const unsigned any = __ballot_sync(0xffffffffu, missing != 0);
+    if (any) {
+        int m = missing;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m += __shfl_xor_sync(0xffffffffu, m, d);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->added, m);
+    }
 }
 
 __global__ void k_plan_finish(int n_cells, const unsigned long long *__restrict__ packed_start, Counters *ctr)
 {
     const unsigned long long t = packed_start[n_cells];
-    const int live = (int)(unsigned)(t & 0xffffffffull), added = (int)(unsigned)(t >> 32);
-    ctr->live = live;
-    ctr->added = added;
-    const long long total = (long long)live + added;
+    const long long total = (long long)(unsigned)(t & 0xffffffffull);
+    ctr->live = (int)total - ctr->added;
     if (total > ctr->capacity) {
         ctr->overflow = 1;
         ctr->count = 0; // nothing valid to iterate over; the host reports PFEM2_ECAPACITY
@@ -241,29 +363,63 @@ __global__ void k_plan_finish(int n_cells, const unsigned long long *__restrict_
     }
 }
 
-// gather the survivors into cell order: sorted position j (within the live particles) -> destination
-// j + (number of re-seeded particles in all earlier cells).  src order within a cell is the stable
-// sort order, i.e. the previous array order.
+__device__ __forceinline__ void copy_particle(const ParticleSoA &src, int s, const ParticleSoA &dst, int d, unsigned cell)
+{
+    dst.x[d] = src.x[s];
+    dst.y[d] = src.y[s];
+    dst.l0[d] = src.l0[s];
+    dst.l1[d] = src.l1[s];
+    dst.l2[d] = src.l2[s];
+    dst.vx[d] = src.vx[s];
+    dst.vy[d] = src.vy[s];
+    dst.cell[d] = cell;
+    dst.id[d] = src.id[s];
+}
+
+// stayers keep their relative order: destination = new segment start + number of stayers before it in its old
+// segment (popcount over the stay bits from the old segment start).  n_old = array length before the advect.
 __global__ void __launch_bounds__(kThreads)
-k_gather_sorted(ParticleSoA src, ParticleSoA dst, const unsigned *__restrict__ keys_sorted,
-                const unsigned *__restrict__ vals_sorted, const unsigned long long *__restrict__ packed_start,
-                const Counters *ctr)
+k_scatter_stayers(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_old_ptr,
+                  const unsigned *__restrict__ stay_bits, const int *__restrict__ old_start,
+                  const unsigned long long *__restrict__ packed_start, const Counters *ctr)
 {
     if (ctr->overflow) return;
-    const int live = ctr->live;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < live; j += gridDim.x * blockDim.x) {
+    const int n = *n_old_ptr;
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned sb = __ldg(stay_bits + (base >> 5));
+        if (!((sb >> lane) & 1u)) continue;
+        const int i = base + lane;
+        const unsigned c = src.cell[i];
+        const int s0 = __ldg(old_start + c);
+        int rank;
+        if (s0 >= base) {
+            rank = __popc(sb & ((1u << lane) - 1) & ~((1u << (s0 - base)) - 1));
+        } else {
+            rank = __popc(sb & ((1u << lane) - 1));
+            int w = s0 >> 5;
+            rank += __popc(__ldg(stay_bits + w) & ~((1u << (s0 & 31)) - 1));
+            for (++w; w < (base >> 5); ++w) rank += __popc(__ldg(stay_bits + w));
+        }
+        const int d = (int)(unsigned)(packed_start[c] & 0xffffffffull) + rank;
+        copy_particle(src, i, dst, d, c);
+    }
+}
+
+// movers, sorted by new cell (stable: array order within a cell), go right behind the cell's stayers
+__global__ void __launch_bounds__(kThreads)
+k_scatter_movers(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_movers, const unsigned *__restrict__ keys_sorted,
+                 const unsigned *__restrict__ vals_sorted, const int *__restrict__ stay,
+                 const unsigned long long *__restrict__ packed_start, const Counters *ctr)
+{
+    if (ctr->overflow) return;
+    const int m = *n_movers;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
         const unsigned c = keys_sorted[j];
         const unsigned s = vals_sorted[j];
-        const int d = j + (int)(unsigned)(packed_start[c] >> 32);
-        dst.x[d] = src.x[s];
-        dst.y[d] = src.y[s];
-        dst.l0[d] = src.l0[s];
-        dst.l1[d] = src.l1[s];
-        dst.l2[d] = src.l2[s];
-        dst.vx[d] = src.vx[s];
-        dst.vy[d] = src.vy[s];
-        dst.cell[d] = c;
-        dst.id[d] = src.id[s];
+        const unsigned long long ps = packed_start[c];
+        const int d = (int)(unsigned)(ps & 0xffffffffull) + __ldg(stay + c) + (j - (int)(unsigned)(ps >> 32));
+        copy_particle(src, (int)s, dst, d, c);
     }
 }
 
@@ -273,19 +429,17 @@ k_gather_sorted(ParticleSoA src, ParticleSoA dst, const unsigned *__restrict__ k
 __global__ void __launch_bounds__(kThreads)
 k_reseed(int n_cells, int ppc, const double2 *__restrict__ vertices, const CellGeom *__restrict__ geom,
          const double *__restrict__ centers, NodalVel vel, const unsigned long long *__restrict__ cell_mask,
-         const unsigned long long *__restrict__ packed_start, ParticleSoA dst, int *__restrict__ cell_start,
-         const Counters *ctr)
+         const int *__restrict__ stay, const int *__restrict__ arrive, const unsigned long long *__restrict__ packed_start,
+         ParticleSoA dst, int *__restrict__ cell_start, const Counters *ctr)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > n_cells) return;
-    const unsigned long long ps = packed_start[c];
-    const int start = (int)(unsigned)(ps & 0xffffffffull) + (int)(unsigned)(ps >> 32);
+    const int start = (int)(unsigned)(packed_start[c] & 0xffffffffull);
     cell_start[c] = start;
     if (c == n_cells || ctr->overflow) return;
-    const unsigned long long pn = packed_start[c + 1];
-    const int missing = (int)(unsigned)(pn >> 32) - (int)(unsigned)(ps >> 32);
-    if (missing == 0) return;
-    const int live = (int)(unsigned)(pn & 0xffffffffull) - (int)(unsigned)(ps & 0xffffffffull);
+    const int live = stay[c] + arrive[c];
+    const int missing = (int)(unsigned)(packed_start[c + 1] & 0xffffffffull) - start - live;
+    if (missing <= 0) return;
     const double *Vx, *Vy;
     vel.resolve(Vx, Vy);
     const uint4 nn = __ldg(reinterpret_cast<const uint4 *>(&geom[c].n0));
@@ -491,6 +645,59 @@ k_one_ring(int n_cells, const unsigned *__restrict__ cells, const int *__restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// locate acceleration data, built once at create():
+//   edge_nbr[c] = cells across the edges opposite to local vertices 0,1,2 (-1 on the domain boundary),
+//   CellGeom.pad = strict-interior margin of cell c as a float (see locate_mover and DESIGN.md):
+//       margin_c = 12 * 2e-6 * (longest edge in the mesh) / (smallest height of c), at least 1e-5.
+// A cell T' accepts a point p (all barycentrics >= -tol) only if dist(p, T') <= 6 tol diam(T'); a point whose
+// barycentrics in T all exceed margin_T is farther than that from every other cell of a non-overlapping mesh.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_cell_metrics(int n_cells, const double2 *__restrict__ vertices, const CellGeom *__restrict__ geom, double *__restrict__ hmin,
+               unsigned long long *__restrict__ dmax_bits)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double longest = 0.0;
+    if (c < n_cells) {
+        const CellGeom g = geom[c];
+        const double2 a = vertices[g.n0], b = vertices[g.n1], z = vertices[g.n2];
+        const double e0 = hypot(b.x - z.x, b.y - z.y), e1 = hypot(a.x - z.x, a.y - z.y), e2 = hypot(a.x - b.x, a.y - b.y);
+        longest = fmax(e0, fmax(e1, e2));
+        const double area2 = fabs((a.x - z.x) * (b.y - z.y) - (a.y - z.y) * (b.x - z.x));
+        hmin[c] = area2 / longest;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) longest = fmax(longest, __shfl_xor_sync(0xffffffffu, longest, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(dmax_bits, (unsigned long long)__double_as_longlong(longest));
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_build_locate_data(int n_cells, CellGeom *__restrict__ geom, const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx,
+                    const double *__restrict__ hmin, const unsigned long long *__restrict__ dmax_bits, int4 *__restrict__ edge_nbr)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const unsigned a0 = geom[c].n0, a1 = geom[c].n1, a2 = geom[c].n2;
+    int4 e = make_int4(-1, -1, -1, 0);
+    for (int k = nbr_off[c]; k < nbr_off[c + 1]; ++k) {
+        const int nb = nbr_idx[k];
+        const unsigned b0 = geom[nb].n0, b1 = geom[nb].n1, b2 = geom[nb].n2;
+        const bool s0 = a0 == b0 || a0 == b1 || a0 == b2;
+        const bool s1 = a1 == b0 || a1 == b1 || a1 == b2;
+        const bool s2 = a2 == b0 || a2 == b1 || a2 == b2;
+        if (s1 && s2 && !s0 && e.x < 0) e.x = nb; // shares the edge opposite to vertex 0
+        if (s0 && s2 && !s1 && e.y < 0) e.y = nb;
+        if (s0 && s1 && !s2 && e.z < 0) e.z = nb;
+    }
+    edge_nbr[c] = e;
+    const double dmax = __longlong_as_double((long long)*dmax_bits);
+    double m = 12.0 * 2e-6 * dmax / hmin[c];
+    if (!(m >= 1e-5)) m = 1e-5;
+    if (!(m < 0.3)) m = 2.0; // degenerate cell: never take the fast path into it
+    geom[c].pad = __float_as_uint(__double2float_ru(m * 1.0001));
+}
+
 __global__ void k_set_counters(Counters *ctr, int count, int capacity)
 {
     ctr->count = count;
@@ -500,6 +707,9 @@ __global__ void k_set_counters(Counters *ctr, int count, int capacity)
     ctr->movers = 0;
     ctr->overflow = 0;
     ctr->capacity = capacity;
+    ctr->n_old = count;
+    ctr->n_warps = (count + 31) >> 5;
+    ctr->n_movers = 0;
 }
 
 __global__ void k_begin_advect(Counters *ctr, int capacity)
@@ -508,6 +718,8 @@ __global__ void k_begin_advect(Counters *ctr, int capacity)
     ctr->movers = 0;
     ctr->added = 0;
     ctr->capacity = capacity;
+    ctr->n_old = ctr->count;
+    ctr->n_warps = (ctr->count + 31) >> 5;
 }
 
 } // namespace pfem2

@@ -56,6 +56,8 @@ typedef struct pfem2_options {
     void *stream;           /* cudaStream_t; NULL = legacy default stream */
     int device;             /* CUDA device ordinal; -1 = current device */
     int verbose;            /* 1: print the reference's two stdout lines from the library itself */
+    int exact_search;       /* 1: always use the reference's ordered one-ring scan; 0 (default): edge-walk fast path
+                               that returns the same cell (falls back to the ordered scan in the tolerance band) */
 } pfem2_options;
 
 /* counters of the last pfem2_advect call (device-resident, read back on demand) */

@@ -63,7 +63,7 @@ struct pfem2_handle {
     unsigned *stay_bits = nullptr;           // capacity / 32 + 2: ballot of particles that stayed in their cell
     int *warp_movers = nullptr;              // capacity / 32 + 2: movers per warp, scanned in place
     int *warp_scan_scratch = nullptr;
-    int *stay = nullptr, *arrive = nullptr;  // n_cells + 1 each (one allocation, zeroed together)
+    int *stay = nullptr, *arrive = nullptr, *cursor = nullptr; // n_cells + 1 each (one allocation, zeroed together)
     unsigned long long *cell_mask = nullptr; // n_cells + 1
     unsigned long long *packed = nullptr;    // n_cells + 2 (scan in place)
     unsigned long long *scan_scratch64 = nullptr;
@@ -276,12 +276,12 @@ NodalVel nodal(const double *x, const double *y, double *const *table)
 // Re-establish the cell-sorted order in the other buffer: stayers keep their relative order, the movers listed in
 // keys[0]/vals[0] (n = ctr->n_movers, array order) are radix-sorted by new cell and appended behind the stayers of
 // their cell, lost particles are dropped and (optionally) every empty sub-cell is re-seeded.
-int reorder(pfem2_handle *h, bool reseed, bool have_stayers, NodalVel vel)
+int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalVel vel)
 {
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells;
-    int flip;
-    {
+    int flip = 0;
+    if (stable) {
         PhaseScope ps(h, PFEM2_PHASE_SORT);
         flip = radix_sort_pairs(h->keys[0], h->vals[0], h->keys[1], h->vals[1], &h->ctr->n_movers, h->capacity, h->key_bits,
                                 h->rs_hist, h->rs_scan_scratch, h->rs_info, st);
@@ -292,11 +292,15 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, NodalVel vel)
     exclusive_scan_dev<unsigned long long>(h->packed, h->packed, h->n_cells_dev, 1, 0, C, h->scan_scratch64, st);
     PFEM2_LAUNCH(k_plan_finish, 1, 1, 0, st, C, h->packed, h->ctr);
     ParticleSoA src = h->soa[h->cur], dst = h->soa[h->cur ^ 1];
-    if (have_stayers)
-        PFEM2_LAUNCH(k_scatter_stayers, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->stay_bits,
-                     h->cell_start[h->cs], h->packed, h->ctr);
-    PFEM2_LAUNCH(k_scatter_movers, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_movers, h->keys[flip], h->vals[flip],
-                 h->stay, h->packed, h->ctr);
+    if (stable) {
+        if (have_stayers)
+            PFEM2_LAUNCH(k_scatter_stayers, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->stay_bits,
+                         h->cell_start[h->cs], h->packed, h->ctr);
+        PFEM2_LAUNCH(k_scatter_movers, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_movers, h->keys[flip],
+                     h->vals[flip], h->stay, h->packed, h->ctr);
+    } else {
+        PFEM2_LAUNCH(k_scatter_all, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->packed, h->ctr);
+    }
     PFEM2_LAUNCH(k_reseed, grid_for(C + 1, kThreads, 1 << 30), kThreads, 0, st, C, h->ppc, (const double2 *)h->mesh.d_vertices,
                  h->geom, h->centers, vel, h->cell_mask, h->stay, h->arrive, h->packed, dst, h->cell_start[h->cs ^ 1], h->ctr);
     h->cur ^= 1;
@@ -334,7 +338,7 @@ int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells;
     const double hsub = dt / substeps; // particle_handler_2d.cu:330, host double
-    CU(cudaMemsetAsync(h->stay, 0, sizeof(int) * 2 * ((size_t)C + 1), st)); // stay and arrive are one allocation
+    CU(cudaMemsetAsync(h->stay, 0, sizeof(int) * 3 * ((size_t)C + 1), st)); // stay, arrive, cursor: one allocation
     CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * ((size_t)C + 1), st));
     PFEM2_LAUNCH(k_begin_advect, 1, 1, 0, st, h->ctr, h->capacity);
     {
@@ -351,14 +355,15 @@ int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
         }
 #undef PFEM2_ADV
     }
-    {
+    const bool stable = h->opt.stable_order != 0;
+    if (stable) {
         PhaseScope ps(h, PFEM2_PHASE_SORT);
         exclusive_scan_dev<int>(h->warp_movers, h->warp_movers, &h->ctr->n_warps, 1, 0, (long long)h->capacity / 32 + 1,
                                 h->warp_scan_scratch, st);
         PFEM2_LAUNCH(k_emit_movers, grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], h->ctr, h->stay_bits, h->warp_movers,
                      h->keys[0], h->vals[0]);
     }
-    if ((rc = reorder(h, true, true, vel))) return rc;
+    if ((rc = reorder(h, true, true, stable, vel))) return rc;
     if ((rc = queue_readback(h))) return rc;
     if (h->opt.verbose) {
         if ((rc = sync_counters(h))) return rc;
@@ -533,8 +538,9 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
     TRY(dev_alloc(h, &h->node_inc, 3 * (size_t)C));
     TRY(dev_alloc(h, &h->centers, cen.size()));
     TRY(dev_alloc(h, &h->ctr, 1));
-    TRY(dev_alloc(h, &h->stay, 2 * ((size_t)C + 1)));
+    TRY(dev_alloc(h, &h->stay, 3 * ((size_t)C + 1)));
     h->arrive = h->stay + ((size_t)C + 1);
+    h->cursor = h->arrive + ((size_t)C + 1);
     TRY(dev_alloc(h, &h->n_cells_dev, 1));
     TRY(dev_alloc(h, &h->rs_info, 4));
     TRY(dev_alloc(h, &h->edge_nbr, (size_t)C));
@@ -755,10 +761,10 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
     CU(cp(p.vx, vx)); CU(cp(p.vy, vy)); CU(cp(p.cell, cell));
     if (id) CU(cp(p.id, id)); else CU(cudaMemsetAsync(p.id, 0, sizeof(unsigned) * (size_t)n, st));
     PFEM2_LAUNCH(k_set_counters, 1, 1, 0, st, h->ctr, n, h->capacity);
-    CU(cudaMemsetAsync(h->stay, 0, sizeof(int) * 2 * ((size_t)C + 1), st));
+    CU(cudaMemsetAsync(h->stay, 0, sizeof(int) * 3 * ((size_t)C + 1), st));
     CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * ((size_t)C + 1), st));
     PFEM2_LAUNCH(k_all_movers, grid_for(h->capacity), kThreads, 0, st, p, C, h->ctr, h->keys[0], h->vals[0], h->arrive, &h->ctr->n_movers);
-    if ((rc = reorder(h, false, false, nodal(nullptr, nullptr, nullptr)))) return rc;
+    if ((rc = reorder(h, false, false, true, nodal(nullptr, nullptr, nullptr)))) return rc;
     h->seeded = true;
     if ((rc = queue_readback(h))) return rc;
     return sync_counters(h);

@@ -406,6 +406,33 @@ k_scatter_stayers(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_ol
     }
 }
 
+// Fast reorder (default): one counting-sort scatter of ALL survivors in array order.  Lanes of a warp that go to
+// the same cell form a group (match_any); the group leader reserves a contiguous run behind the cell's cursor with
+// one atomicAdd, so each group writes one contiguous run per array.  The order of runs inside a cell depends on the
+// order the atomics retire (owner cells and the particle SET are exact; only the slot order within a cell and hence
+// the last bits of the projection sums can differ between runs).  pfem2_options.stable_order selects the
+// deterministic stayer / sorted-mover path below instead.
+__global__ void __launch_bounds__(kThreads)
+k_scatter_all(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_old_ptr, int *__restrict__ cursor,
+              const unsigned long long *__restrict__ packed_start, const Counters *ctr)
+{
+    if (ctr->overflow) return;
+    const int n = *n_old_ptr;
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        const unsigned c = i < n ? src.cell[i] : kLostCell;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        if (c == kLostCell) continue;
+        const int leader = __ffs(peers) - 1;
+        int run = 0;
+        if (lane == leader) run = atomicAdd(cursor + c, __popc(peers));
+        run = __shfl_sync(peers, run, leader);
+        const int d = (int)(unsigned)(packed_start[c] & 0xffffffffull) + run + __popc(peers & ((1u << lane) - 1));
+        copy_particle(src, i, dst, d, c);
+    }
+}
+
 // movers, sorted by new cell (stable: array order within a cell), go right behind the cell's stayers
 __global__ void __launch_bounds__(kThreads)
 k_scatter_movers(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_movers, const unsigned *__restrict__ keys_sorted,

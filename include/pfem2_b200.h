@@ -58,6 +58,8 @@ typedef struct pfem2_options {
     int verbose;            /* 1: print the reference's two stdout lines from the library itself */
     int exact_search;       /* 1: always use the reference's ordered one-ring scan; 0 (default): edge-walk fast path
                                that returns the same cell (falls back to the ordered scan in the tolerance band) */
+    int stable_order;       /* 0 (default): counting-sort scatter, slot order inside a cell depends on atomic retirement
+                               order; 1: deterministic order (stayers keep their order, movers radix-sorted by cell) */
 } pfem2_options;
 
 /* counters of the last pfem2_advect call (device-resident, read back on demand) */

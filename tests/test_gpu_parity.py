@@ -37,8 +37,9 @@ def dev_field(c, dev="cuda:0"):
 GOLDEN_CASES = ["tiny_l1", "tiny_l2", "tiny_l3", "tiny_l4", "tiny_box", "tiny_fast", "channel_l2", "channel_fast_rev", "cyl3_box"]
 
 
+@pytest.mark.parametrize("stable", [False, True], ids=["fast_order", "stable_order"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_cuda_matches_reference_dumps(gpu, oracle, name):
+def test_cuda_matches_reference_dumps(gpu, oracle, name, stable):
     c = cases.build_case(name)
     g = load_golden(name)
     oracle.complete_mesh(c.mesh)  # one-ring from the validated O(C) builder; invJ recomputed on the device below
@@ -46,7 +47,7 @@ def test_cuda_matches_reference_dumps(gpu, oracle, name):
     dm = gpu.DeviceMesh(c.mesh)
     if "invj" in g:
         assert np.array_equal(dm.inv_jacobi.cpu().numpy(), g["invj"]), "device inverse Jacobians differ from the reference's"
-    h = gpu.ParticleHandler2D(dm, c.level)
+    h = gpu.ParticleHandler2D(dm, c.level, stable_order=stable)
     h.seed_particles()
     assert h.get_particle_count() == c.mesh.n_cells * c.level * c.level
     f, w = dev_field(c)
@@ -69,6 +70,7 @@ def run_both(gpu, oracle, mesh, fx, fy, level, substeps, dt, nsteps, check_every
     dm = gpu.DeviceMesh(mesh)
     h = gpu.ParticleHandler2D(dm, level, **opts)
     o = oracle.OracleHandler(mesh, level, max_level=opts.get("max_division_level", 4), subcell_mode=opts.get("subcell_mode", 0))
+    opts = dict(opts)
     h.seed_particles()
     o.seed_particles()
     f = (torch.as_tensor(fx).cuda(), torch.as_tensor(fy).cuda())
@@ -102,6 +104,7 @@ def test_clamped_subcell_mode_matches_oracle(gpu, oracle):
     m = cases._tiny(False)
     fx, fy = cases._mix(m, 0.5, 1.0, 0.2, 1.0)
     run_both(gpu, oracle, m, fx, fy, 3, 3, 0.2, 10, subcell_mode=1)
+    run_both(gpu, oracle, m, fx, fy, 3, 3, 0.2, 10, subcell_mode=1, stable_order=True)
 
 
 def test_high_cfl_interior_deletions_match_oracle(gpu, oracle):
@@ -173,7 +176,7 @@ def test_pointer_table_flavour_and_step_host(gpu, oracle):
     c = cases.build_case("tiny_l3")
     oracle.complete_mesh(c.mesh)
     dm = gpu.DeviceMesh(c.mesh)
-    hs = [gpu.ParticleHandler2D(dm, c.level) for _ in range(3)]
+    hs = [gpu.ParticleHandler2D(dm, c.level, stable_order=True) for _ in range(3)]
     f, w = dev_field(c)
     w2 = (torch.zeros_like(f[0]), torch.zeros_like(f[0]))
     tf = torch.tensor([f[0].data_ptr(), f[1].data_ptr()], dtype=torch.int64, device="cuda")
@@ -215,6 +218,8 @@ def test_download_upload_roundtrip_and_resort(gpu, oracle):
     t = h2.download()
     assert np.all(np.diff(t["cell"].astype(np.int64)) >= 0)
     assert_states_equal(s, t, "after upload", exact_vel=True)
+    for k in s:  # upload is a stable sort by cell of what was uploaded
+        assert np.array_equal(t[k], s[k][perm][np.argsort(s["cell"][perm], kind="stable")]), k
     w2 = (torch.zeros_like(f[0]), torch.zeros_like(f[0]))
     for _ in range(3):
         h1.step(f, w, c.dt, c.substeps)
@@ -311,8 +316,8 @@ def test_walk_fast_path_equals_ordered_scan(gpu, oracle, name):
     c = cases.build_case(name)
     oracle.complete_mesh(c.mesh)
     dm = gpu.DeviceMesh(c.mesh)
-    ha = gpu.ParticleHandler2D(dm, c.level)
-    hb = gpu.ParticleHandler2D(dm, c.level, exact_search=True)
+    ha = gpu.ParticleHandler2D(dm, c.level, stable_order=True)
+    hb = gpu.ParticleHandler2D(dm, c.level, exact_search=True, stable_order=True)
     f, w = dev_field(c)
     w2 = (torch.zeros_like(f[0]), torch.zeros_like(f[0]))
     for h in (ha, hb):

@@ -77,7 +77,7 @@ def load():
     L.pfem2_step_host.argtypes = [vp, vp, vp, vp, vp, d, i, C.POINTER(i)]
     L.pfem2_download.argtypes = [vp] + [vp] * 9
     L.pfem2_upload.argtypes = [vp, i] + [vp] * 9
-    L.pfem2_device_arrays.argtypes = [vp] + [C.POINTER(vp)] * 9
+    L.pfem2_device_arrays.argtypes = [vp] + [C.POINTER(vp)] * 4
     L.pfem2_cell_starts.argtypes = [vp, C.POINTER(vp)]
     L.pfem2_mesh_inv_jacobi.argtypes = [i, vp, vp, vp, vp]
     L.pfem2_mesh_one_ring.argtypes = [i, i, vp, vp, vp, C.POINTER(i), vp]

@@ -158,22 +158,16 @@ int grid_for(long long n, int threads = kThreads, int max_blocks = 0)
 int alloc_soa(pfem2_handle *h, ParticleSoA &s, int cap)
 {
     int rc;
-    if ((rc = dev_alloc(h, &s.x, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.y, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.l0, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.l1, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.l2, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.vx, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.vy, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.cell, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.id, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.pos, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.lab, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.tail, cap))) return rc;
+    if ((rc = dev_alloc(h, &s.vel, cap))) return rc;
     return PFEM2_OK;
 }
 
 void free_soa(ParticleSoA &s)
 {
-    cudaFree(s.x); cudaFree(s.y); cudaFree(s.l0); cudaFree(s.l1); cudaFree(s.l2);
-    cudaFree(s.vx); cudaFree(s.vy); cudaFree(s.cell); cudaFree(s.id);
+    cudaFree(s.pos); cudaFree(s.lab); cudaFree(s.tail); cudaFree(s.vel);
     s = ParticleSoA{};
 }
 
@@ -230,9 +224,7 @@ int grow(pfem2_handle *h, int new_cap)
     auto cp = [&](auto *dst, const auto *src) {
         return cudaMemcpyAsync(dst, src, (size_t)n * sizeof(*dst), cudaMemcpyDeviceToDevice, h->stream);
     };
-    CU(cp(fresh.x, old.x)); CU(cp(fresh.y, old.y)); CU(cp(fresh.l0, old.l0)); CU(cp(fresh.l1, old.l1));
-    CU(cp(fresh.l2, old.l2)); CU(cp(fresh.vx, old.vx)); CU(cp(fresh.vy, old.vy)); CU(cp(fresh.cell, old.cell));
-    CU(cp(fresh.id, old.id));
+    CU(cp(fresh.pos, old.pos)); CU(cp(fresh.lab, old.lab)); CU(cp(fresh.tail, old.tail)); CU(cp(fresh.vel, old.vel));
     CU(cudaStreamSynchronize(h->stream));
     free_soa(old);
     h->soa[h->cur] = fresh;
@@ -384,14 +376,15 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
     const int ppc = h->ppc;
     {
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
-    if (ppc <= 6)
+    // lanes per cell: about a quarter of the nominal segment length, so each lane keeps several loads in flight
+    if (ppc <= 4)
+        PFEM2_LAUNCH(k_project_cells<2>, grid_for((long long)C * 2), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
+    else if (ppc <= 16)
         PFEM2_LAUNCH(k_project_cells<4>, grid_for((long long)C * 4), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
-    else if (ppc <= 12)
+    else if (ppc <= 36)
         PFEM2_LAUNCH(k_project_cells<8>, grid_for((long long)C * 8), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
-    else if (ppc <= 24)
-        PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)C * 16), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
     else
-        PFEM2_LAUNCH(k_project_cells<32>, grid_for((long long)C * 32), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
+        PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)C * 16), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
     }
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
     PFEM2_LAUNCH(k_project_nodes, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, N, h->node_off, (const int *)h->node_inc, h->partial,
@@ -731,12 +724,26 @@ int pfem2_download(pfem2_handle *h, double *x, double *y, double *l0, double *l1
     if ((rc = sync_counters(h))) return rc;
     const size_t n = (size_t)h->host_count;
     const ParticleSoA &p = h->soa[h->cur];
-    auto cp = [&](auto *dst, const auto *src) {
-        return dst ? cudaMemcpyAsync(dst, src, n * sizeof(*dst), cudaMemcpyDeviceToHost, h->stream) : cudaSuccess;
-    };
-    CU(cp(x, p.x)); CU(cp(y, p.y)); CU(cp(l0, p.l0)); CU(cp(l1, p.l1)); CU(cp(l2, p.l2));
-    CU(cp(vx, p.vx)); CU(cp(vy, p.vy)); CU(cp(cell, p.cell)); CU(cp(id, p.id));
+    std::vector<double2> hp(n), hl(n), hv(n);
+    std::vector<ParticleTail> ht(n);
+    if (n) {
+        CU(cudaMemcpyAsync(hp.data(), p.pos, n * 16, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(hl.data(), p.lab, n * 16, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(ht.data(), p.tail, n * 16, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(hv.data(), p.vel, n * 16, cudaMemcpyDeviceToHost, h->stream));
+    }
     CU(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < n; ++i) {
+        if (x) x[i] = hp[i].x;
+        if (y) y[i] = hp[i].y;
+        if (l0) l0[i] = hl[i].x;
+        if (l1) l1[i] = hl[i].y;
+        if (l2) l2[i] = ht[i].l2;
+        if (vx) vx[i] = hv[i].x;
+        if (vy) vy[i] = hv[i].y;
+        if (cell) cell[i] = ht[i].cell;
+        if (id) id[i] = ht[i].id;
+    }
     return PFEM2_OK;
 }
 
@@ -754,12 +761,26 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells;
     ParticleSoA &p = h->soa[h->cur];
-    auto cp = [&](auto *dst, const auto *src) {
-        return cudaMemcpyAsync(dst, src, (size_t)n * sizeof(*dst), cudaMemcpyHostToDevice, st);
-    };
-    CU(cp(p.x, x)); CU(cp(p.y, y)); CU(cp(p.l0, l0)); CU(cp(p.l1, l1)); CU(cp(p.l2, l2));
-    CU(cp(p.vx, vx)); CU(cp(p.vy, vy)); CU(cp(p.cell, cell));
-    if (id) CU(cp(p.id, id)); else CU(cudaMemsetAsync(p.id, 0, sizeof(unsigned) * (size_t)n, st));
+    {
+        std::vector<double2> hp(n), hl(n), hv(n);
+        std::vector<ParticleTail> ht(n);
+        for (int i = 0; i < n; ++i) {
+            if (cell[i] >= (unsigned)C) return fail(h, PFEM2_EINVAL, "upload: cell index out of range");
+            hp[i] = make_double2(x[i], y[i]);
+            hl[i] = make_double2(l0[i], l1[i]);
+            hv[i] = make_double2(vx[i], vy[i]);
+            ht[i].l2 = l2[i];
+            ht[i].cell = cell[i];
+            ht[i].id = id ? id[i] : 0u;
+        }
+        if (n) {
+            CU(cudaMemcpyAsync(p.pos, hp.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(p.lab, hl.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(p.tail, ht.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(p.vel, hv.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+        }
+        CU(cudaStreamSynchronize(st));
+    }
     PFEM2_LAUNCH(k_set_counters, 1, 1, 0, st, h->ctr, n, h->capacity);
     CU(cudaMemsetAsync(h->stay, 0, sizeof(int) * 3 * ((size_t)C + 1), st));
     CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * ((size_t)C + 1), st));
@@ -770,13 +791,14 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
     return sync_counters(h);
 }
 
-int pfem2_device_arrays(pfem2_handle *h, const double **x, const double **y, const double **l0, const double **l1, const double **l2,
-                        const double **vx, const double **vy, const unsigned **cell, const unsigned **id)
+int pfem2_device_arrays(pfem2_handle *h, const double **d_pos, const double **d_lab, const void **d_tail, const double **d_vel)
 {
     if (!h) return PFEM2_EINVAL;
     const ParticleSoA &p = h->soa[h->cur];
-    if (x) *x = p.x; if (y) *y = p.y; if (l0) *l0 = p.l0; if (l1) *l1 = p.l1; if (l2) *l2 = p.l2;
-    if (vx) *vx = p.vx; if (vy) *vy = p.vy; if (cell) *cell = p.cell; if (id) *id = p.id;
+    if (d_pos) *d_pos = (const double *)p.pos;
+    if (d_lab) *d_lab = (const double *)p.lab;
+    if (d_tail) *d_tail = p.tail;
+    if (d_vel) *d_vel = (const double *)p.vel;
     return PFEM2_OK;
 }
 

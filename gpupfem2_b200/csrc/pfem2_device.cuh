@@ -26,14 +26,41 @@ struct __align__(16) CellGeom {
 };
 static_assert(sizeof(CellGeom) == 64, "CellGeom must be one 64-byte record");
 
-// Structure-of-arrays particle storage (64 B of state per particle).
-struct ParticleSoA {
-    double *x, *y;        // Particle2D::position
-    double *l0, *l1, *l2; // Particle2D::localPosition (barycentric)
-    double *vx, *vy;      // Particle2D::velocity
-    unsigned *cell;       // Particle2D::cellID
-    unsigned *id;         // Particle2D::ID
+// Structure-of-arrays particle storage: four arrays of 16-byte records (64 B of state per particle), so every
+// access -- streaming or scattered -- is one 128-bit load / store and a warp touches whole 32-byte sectors.
+//   pos  = Particle2D::position            (x, y)
+//   lab  = Particle2D::localPosition.x, .y (first two barycentrics)
+//   tail = localPosition.z, cellID, ID
+//   vel  = Particle2D::velocity            (vx, vy)
+struct __align__(16) ParticleTail {
+    double l2;
+    unsigned cell;
+    unsigned id;
 };
+static_assert(sizeof(ParticleTail) == 16, "ParticleTail must be a 16-byte record");
+
+struct ParticleSoA {
+    double2 *pos;
+    double2 *lab;
+    ParticleTail *tail;
+    double2 *vel;
+};
+
+__device__ __forceinline__ ParticleTail ld_tail(const ParticleTail *p)
+{
+    const int4 r = *reinterpret_cast<const int4 *>(p);
+    ParticleTail t;
+    t.l2 = __hiloint2double(r.y, r.x);
+    t.cell = (unsigned)r.z;
+    t.id = (unsigned)r.w;
+    return t;
+}
+__device__ __forceinline__ void st_tail(ParticleTail *p, double l2, unsigned cell, unsigned id)
+{
+    *reinterpret_cast<int4 *>(p) = make_int4(__double2loint(l2), __double2hiint(l2), (int)cell, (int)id);
+}
+__device__ __forceinline__ unsigned ld_cell(const ParticleTail *p) { return reinterpret_cast<const unsigned *>(p)[2]; }
+__device__ __forceinline__ void st_cell(ParticleTail *p, unsigned c) { reinterpret_cast<unsigned *>(p)[2] = c; }
 
 // device-resident counters (one per handle); mirrors pfem2_stats
 struct Counters {

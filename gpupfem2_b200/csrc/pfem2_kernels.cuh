@@ -1,7 +1,7 @@
 // pfem2_kernels.cuh -- the particle-step kernels (sm_100a).
 //
-// Data layout in HBM: particles are nine SoA arrays (64 B of state per particle),
-// kept PHYSICALLY SORTED BY OWNING CELL after every advect, so cell c owns the contiguous segment
+// Data layout in HBM: particles are four SoA arrays of 16-byte records (64 B of state per
+// particle), kept PHYSICALLY SORTED BY OWNING CELL after every advect, so cell c owns the contiguous segment
 // [cell_start[c], cell_start[c+1]).  Mesh data the path reads is repacked once into one 64-byte
 // CellGeom record per cell.  All particle counts live in device memory (Counters); kernels are
 // grid-stride and read the live count themselves, so a step issues no device->host copy.
@@ -71,15 +71,10 @@ k_seed(int n_cells, int ppc, const double2 *__restrict__ vertices, const CellGeo
         const uint4 nn = __ldg(reinterpret_cast<const uint4 *>(&geom[c].n0));
         const double2 v0 = __ldg(&vertices[nn.x]), v1 = __ldg(&vertices[nn.y]), v2 = __ldg(&vertices[nn.z]);
         const double L0 = __ldg(&centers[3 * s]), L1 = __ldg(&centers[3 * s + 1]), L2 = __ldg(&centers[3 * s + 2]);
-        p.x[i] = to_global1(L0, L1, L2, v0.x, v1.x, v2.x);
-        p.y[i] = to_global1(L0, L1, L2, v0.y, v1.y, v2.y);
-        p.l0[i] = L0;
-        p.l1[i] = L1;
-        p.l2[i] = L2;
-        p.vx[i] = 0.0;
-        p.vy[i] = 0.0;
-        p.cell[i] = (unsigned)c;
-        p.id[i] = (unsigned)i;
+        p.pos[i] = make_double2(to_global1(L0, L1, L2, v0.x, v1.x, v2.x), to_global1(L0, L1, L2, v0.y, v1.y, v2.y));
+        p.lab[i] = make_double2(L0, L1);
+        st_tail(p.tail + i, L2, (unsigned)c, (unsigned)i);
+        p.vel[i] = make_double2(0.0, 0.0);
         if (s == 0) cell_start[c] = (int)i;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -197,18 +192,23 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
         double x = 0, y = 0, L0 = 0, L1 = 0, L2 = 0;
         bool lost = false;
         if (valid) {
-            c0 = c = p.cell[i];
-            x = p.x[i];
-            y = p.y[i];
-            L0 = p.l0[i];
-            L1 = p.l1[i];
-            L2 = p.l2[i];
+            const double2 pos = p.pos[i], lab = p.lab[i];
+            const ParticleTail tl = ld_tail(p.tail + i);
+            c0 = c = tl.cell;
+            x = pos.x;
+            y = pos.y;
+            L0 = lab.x;
+            L1 = lab.y;
+            L2 = tl.l2;
+            // cell record and its six nodal velocities stay in registers while the particle stays in the cell
+            CellGeom g = load_geom(geom, c);
+            double ax0 = __ldg(Vx + g.n0), ax1 = __ldg(Vx + g.n1), ax2 = __ldg(Vx + g.n2);
+            double ay0 = __ldg(Vy + g.n0), ay1 = __ldg(Vy + g.n1), ay2 = __ldg(Vy + g.n2);
 #pragma unroll 1
             for (int s = 0; s < substeps; ++s) {
-                const CellGeom g = load_geom(geom, c);
                 // kAdvectParticles: velocity from the STORED local position and cell
-                const double ux = interp3(L0, L1, L2, __ldg(Vx + g.n0), __ldg(Vx + g.n1), __ldg(Vx + g.n2));
-                const double uy = interp3(L0, L1, L2, __ldg(Vy + g.n0), __ldg(Vy + g.n1), __ldg(Vy + g.n2));
+                const double ux = interp3(L0, L1, L2, ax0, ax1, ax2);
+                const double uy = interp3(L0, L1, L2, ay0, ay1, ay2);
                 x = __fma_rn(ux, h, x);
                 y = __fma_rn(uy, h, y);
                 // own cell first (wins even if a neighbour would also accept)
@@ -223,17 +223,19 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
                     lost = true;
                     break;
                 }
+                if (s + 1 < substeps) {
+                    g = load_geom(geom, c);
+                    ax0 = __ldg(Vx + g.n0); ax1 = __ldg(Vx + g.n1); ax2 = __ldg(Vx + g.n2);
+                    ay0 = __ldg(Vy + g.n0); ay1 = __ldg(Vy + g.n1); ay2 = __ldg(Vy + g.n2);
+                }
             }
-            p.x[i] = x;
-            p.y[i] = y;
+            p.pos[i] = make_double2(x, y);
             if (lost) {
-                p.cell[i] = kLostCell;
+                st_cell(p.tail + i, kLostCell);
                 ++my_lost;
             } else {
-                p.l0[i] = L0;
-                p.l1[i] = L1;
-                p.l2[i] = L2;
-                if (c != c0) p.cell[i] = c;
+                p.lab[i] = make_double2(L0, L1);
+                st_tail(p.tail + i, L2, c, tl.id);
             }
         }
         const bool live = valid && !lost;
@@ -296,7 +298,7 @@ k_emit_movers(ParticleSoA p, Counters *ctr, const unsigned *__restrict__ stay_bi
         const int i = base + lane;
         const unsigned sb = __ldg(stay_bits + (base >> 5));
         unsigned c = kLostCell;
-        if (i < n && !((sb >> lane) & 1u)) c = p.cell[i];
+        if (i < n && !((sb >> lane) & 1u)) c = ld_cell(p.tail + i);
         const bool mover = c != kLostCell;
         const unsigned mb = __ballot_sync(0xffffffffu, mover);
         if (mover) {
@@ -315,7 +317,7 @@ k_all_movers(ParticleSoA p, int n_cells, Counters *ctr, unsigned *__restrict__ k
 {
     const int n = ctr->count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        unsigned c = p.cell[i];
+        unsigned c = ld_cell(p.tail + i);
         if (c >= (unsigned)n_cells) c = (unsigned)n_cells - 1; // caller validated; keep memory safe regardless
         keys[i] = c;
         vals[i] = (unsigned)i;
@@ -363,17 +365,14 @@ __global__ void k_plan_finish(int n_cells, const unsigned long long *__restrict_
     }
 }
 
-__device__ __forceinline__ void copy_particle(const ParticleSoA &src, int s, const ParticleSoA &dst, int d, unsigned cell)
+__device__ __forceinline__ void copy_particle(const ParticleSoA &src, int s, const ParticleSoA &dst, int d)
 {
-    dst.x[d] = src.x[s];
-    dst.y[d] = src.y[s];
-    dst.l0[d] = src.l0[s];
-    dst.l1[d] = src.l1[s];
-    dst.l2[d] = src.l2[s];
-    dst.vx[d] = src.vx[s];
-    dst.vy[d] = src.vy[s];
-    dst.cell[d] = cell;
-    dst.id[d] = src.id[s];
+    const double2 a = src.pos[s], b = src.lab[s], v = src.vel[s];
+    const int4 t = *reinterpret_cast<const int4 *>(src.tail + s);
+    dst.pos[d] = a;
+    dst.lab[d] = b;
+    *reinterpret_cast<int4 *>(dst.tail + d) = t;
+    dst.vel[d] = v;
 }
 
 // stayers keep their relative order: destination = new segment start + number of stayers before it in its old
@@ -390,7 +389,7 @@ k_scatter_stayers(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_ol
         const unsigned sb = __ldg(stay_bits + (base >> 5));
         if (!((sb >> lane) & 1u)) continue;
         const int i = base + lane;
-        const unsigned c = src.cell[i];
+        const unsigned c = ld_cell(src.tail + i);
         const int s0 = __ldg(old_start + c);
         int rank;
         if (s0 >= base) {
@@ -402,7 +401,7 @@ k_scatter_stayers(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_ol
             for (++w; w < (base >> 5); ++w) rank += __popc(__ldg(stay_bits + w));
         }
         const int d = (int)(unsigned)(packed_start[c] & 0xffffffffull) + rank;
-        copy_particle(src, i, dst, d, c);
+        copy_particle(src, i, dst, d);
     }
 }
 
@@ -419,17 +418,39 @@ k_scatter_all(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_old_pt
     if (ctr->overflow) return;
     const int n = *n_old_ptr;
     const int lane = threadIdx.x & 31;
-    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
-        const int i = base + lane;
-        const unsigned c = i < n ? src.cell[i] : kLostCell;
-        const unsigned peers = __match_any_sync(0xffffffffu, c);
-        if (c == kLostCell) continue;
-        const int leader = __ffs(peers) - 1;
-        int run = 0;
-        if (lane == leader) run = atomicAdd(cursor + c, __popc(peers));
-        run = __shfl_sync(peers, run, leader);
-        const int d = (int)(unsigned)(packed_start[c] & 0xffffffffull) + run + __popc(peers & ((1u << lane) - 1));
-        copy_particle(src, i, dst, d, c);
+    constexpr int U = 4; // particles per thread per iteration: all loads are issued before the first dependent atomic
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp_global * (32 * U); base < n; base += warps_total * (32 * U)) {
+        double2 a[U], b[U], v[U];
+        int4 t[U];
+        unsigned c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * 32 + lane;
+            c[u] = kLostCell;
+            if (i < n) {
+                t[u] = *reinterpret_cast<const int4 *>(src.tail + i);
+                c[u] = (unsigned)t[u].z;
+                a[u] = src.pos[i];
+                b[u] = src.lab[i];
+                v[u] = src.vel[i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned peers = __match_any_sync(0xffffffffu, c[u]);
+            if (c[u] == kLostCell) continue;
+            const int leader = __ffs(peers) - 1;
+            int run = 0;
+            if (lane == leader) run = atomicAdd(cursor + c[u], __popc(peers));
+            run = __shfl_sync(peers, run, leader);
+            const int d = (int)(unsigned)(__ldg(packed_start + c[u]) & 0xffffffffull) + run + __popc(peers & ((1u << lane) - 1));
+            dst.pos[d] = a[u];
+            dst.lab[d] = b[u];
+            *reinterpret_cast<int4 *>(dst.tail + d) = t[u];
+            dst.vel[d] = v[u];
+        }
     }
 }
 
@@ -446,7 +467,7 @@ k_scatter_movers(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_mov
         const unsigned s = vals_sorted[j];
         const unsigned long long ps = packed_start[c];
         const int d = (int)(unsigned)(ps & 0xffffffffull) + __ldg(stay + c) + (j - (int)(unsigned)(ps >> 32));
-        copy_particle(src, (int)s, dst, d, c);
+        copy_particle(src, (int)s, dst, d);
     }
 }
 
@@ -478,15 +499,10 @@ k_reseed(int n_cells, int ppc, const double2 *__restrict__ vertices, const CellG
     for (int s = 0; s < ppc; ++s) {
         if ((mask >> s) & 1ull) continue;
         const double L0 = __ldg(&centers[3 * s]), L1 = __ldg(&centers[3 * s + 1]), L2 = __ldg(&centers[3 * s + 2]);
-        dst.x[d] = to_global1(L0, L1, L2, v0.x, v1.x, v2.x);
-        dst.y[d] = to_global1(L0, L1, L2, v0.y, v1.y, v2.y);
-        dst.l0[d] = L0;
-        dst.l1[d] = L1;
-        dst.l2[d] = L2;
-        dst.vx[d] = interp3(L0, L1, L2, ax0, ax1, ax2);
-        dst.vy[d] = interp3(L0, L1, L2, ay0, ay1, ay2);
-        dst.cell[d] = (unsigned)c;
-        dst.id[d] = (unsigned)d;
+        dst.pos[d] = make_double2(to_global1(L0, L1, L2, v0.x, v1.x, v2.x), to_global1(L0, L1, L2, v0.y, v1.y, v2.y));
+        dst.lab[d] = make_double2(L0, L1);
+        st_tail(dst.tail + d, L2, (unsigned)c, (unsigned)d);
+        dst.vel[d] = make_double2(interp3(L0, L1, L2, ax0, ax1, ax2), interp3(L0, L1, L2, ay0, ay1, ay2));
         ++d;
     }
 }
@@ -514,14 +530,35 @@ k_project_cells(int n_cells, ParticleSoA p, const int *__restrict__ cell_start, 
         double acc[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-        for (int i = b + lane; i < e; i += G) {
-            const double L[3] = {p.l0[i], p.l1[i], p.l2[i]};
-            const double vx = p.vx[i], vy = p.vy[i];
+        // each lane walks the segment with stride G; two particles in flight per lane
+        int i = b + lane;
+        for (; i + G < e; i += 2 * G) {
+            const double2 la = p.lab[i], lb = p.lab[i + G];
+            const double2 va = p.vel[i], vb = p.vel[i + G];
+            const double za = p.tail[i].l2, zb = p.tail[i + G].l2;
+            const double La[3] = {la.x, la.y, za}, Lb[3] = {lb.x, lb.y, zb};
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                acc[3 * k + 0] = __dadd_rn(acc[3 * k + 0], __dmul_rn(L[k], vx)); // t = L_i * v (plain mul), then add
-                acc[3 * k + 1] = __dadd_rn(acc[3 * k + 1], __dmul_rn(L[k], vy));
-                acc[3 * k + 2] = __dadd_rn(acc[3 * k + 2], L[k]);
+                acc[3 * k + 0] = __dadd_rn(acc[3 * k + 0], __dmul_rn(La[k], va.x)); // t = L_i * v (plain mul), then add
+                acc[3 * k + 1] = __dadd_rn(acc[3 * k + 1], __dmul_rn(La[k], va.y));
+                acc[3 * k + 2] = __dadd_rn(acc[3 * k + 2], La[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                acc[3 * k + 0] = __dadd_rn(acc[3 * k + 0], __dmul_rn(Lb[k], vb.x));
+                acc[3 * k + 1] = __dadd_rn(acc[3 * k + 1], __dmul_rn(Lb[k], vb.y));
+                acc[3 * k + 2] = __dadd_rn(acc[3 * k + 2], Lb[k]);
+            }
+        }
+        if (i < e) {
+            const double2 la = p.lab[i];
+            const double2 va = p.vel[i];
+            const double La[3] = {la.x, la.y, p.tail[i].l2};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                acc[3 * k + 0] = __dadd_rn(acc[3 * k + 0], __dmul_rn(La[k], va.x));
+                acc[3 * k + 1] = __dadd_rn(acc[3 * k + 1], __dmul_rn(La[k], va.y));
+                acc[3 * k + 2] = __dadd_rn(acc[3 * k + 2], La[k]);
             }
         }
 #pragma unroll
@@ -580,9 +617,12 @@ k_correct(ParticleSoA p, const CellGeom *__restrict__ geom, NodalVel vel, NodalV
     }
     const int n = ctr->count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned c = p.cell[i];
+        const double2 lab = p.lab[i];
+        const ParticleTail tl = ld_tail(p.tail + i);
+        const double2 vel = p.vel[i];
+        const unsigned c = tl.cell;
         const uint4 nn = __ldg(reinterpret_cast<const uint4 *>(&geom[c].n0));
-        const double L0 = p.l0[i], L1 = p.l1[i], L2 = p.l2[i];
+        const double L0 = lab.x, L1 = lab.y, L2 = tl.l2;
         double dx0 = __ldg(Vx + nn.x), dx1 = __ldg(Vx + nn.y), dx2 = __ldg(Vx + nn.z);
         double dy0 = __ldg(Vy + nn.x), dy1 = __ldg(Vy + nn.y), dy2 = __ldg(Vy + nn.z);
         if (HAS_OLD) {
@@ -593,8 +633,8 @@ k_correct(ParticleSoA p, const CellGeom *__restrict__ geom, NodalVel vel, NodalV
             dy1 = __dsub_rn(dy1, __ldg(Oy + nn.y));
             dy2 = __dsub_rn(dy2, __ldg(Oy + nn.z));
         }
-        p.vx[i] = __dadd_rn(p.vx[i], interp3(L0, L1, L2, dx0, dx1, dx2));
-        p.vy[i] = __dadd_rn(p.vy[i], interp3(L0, L1, L2, dy0, dy1, dy2));
+        p.vel[i] = make_double2(__dadd_rn(vel.x, interp3(L0, L1, L2, dx0, dx1, dx2)),
+                                __dadd_rn(vel.y, interp3(L0, L1, L2, dy0, dy1, dy2)));
     }
 }
 
@@ -607,13 +647,14 @@ __global__ void __launch_bounds__(kThreads) k_export_aos(ParticleSoA p, const Co
     const int n = ctr->count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint4 *rec = out + 6 * (size_t)i;
-        const double x = p.x[i], y = p.y[i], l0 = p.l0[i], l1 = p.l1[i], l2 = p.l2[i], vx = p.vx[i], vy = p.vy[i];
-        rec[0] = make_uint4(p.id[i], 0u, 0u, 0u);
-        reinterpret_cast<double2 *>(rec)[1] = make_double2(x, y);
-        reinterpret_cast<double2 *>(rec)[2] = make_double2(l0, l1);
-        reinterpret_cast<double2 *>(rec)[3] = make_double2(l2, 0.0);
-        reinterpret_cast<double2 *>(rec)[4] = make_double2(vx, vy);
-        rec[5] = make_uint4(p.cell[i], 0u, 0u, 0u);
+        const double2 pos = p.pos[i], lab = p.lab[i], vel = p.vel[i];
+        const ParticleTail tl = ld_tail(p.tail + i);
+        rec[0] = make_uint4(tl.id, 0u, 0u, 0u);
+        reinterpret_cast<double2 *>(rec)[1] = pos;
+        reinterpret_cast<double2 *>(rec)[2] = lab;
+        reinterpret_cast<double2 *>(rec)[3] = make_double2(tl.l2, 0.0);
+        reinterpret_cast<double2 *>(rec)[4] = vel;
+        rec[5] = make_uint4(tl.cell, 0u, 0u, 0u);
     }
 }
 

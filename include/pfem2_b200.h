@@ -119,11 +119,10 @@ int pfem2_download(pfem2_handle *h, double *h_x, double *h_y, double *h_l0, doub
                    double *h_vx, double *h_vy, unsigned *h_cell, unsigned *h_id);
 int pfem2_upload(pfem2_handle *h, int n, const double *h_x, const double *h_y, const double *h_l0, const double *h_l1,
                  const double *h_l2, const double *h_vx, const double *h_vy, const unsigned *h_cell, const unsigned *h_id);
-/* device pointers to the live SoA arrays (x y l0 l1 l2 vx vy as double*, cell id as unsigned*), for
- * zero-copy consumers; valid until the next mutating call */
-int pfem2_device_arrays(pfem2_handle *h, const double **d_x, const double **d_y, const double **d_l0, const double **d_l1,
-                        const double **d_l2, const double **d_vx, const double **d_vy, const unsigned **d_cell,
-                        const unsigned **d_id);
+/* device pointers to the live particle arrays, four arrays of 16-byte records (valid until the next mutating call):
+ *   pos  double2 (x, y) ; lab double2 (first two barycentrics) ; tail { double l2; unsigned cell; unsigned id; } ;
+ *   vel  double2 (vx, vy) */
+int pfem2_device_arrays(pfem2_handle *h, const double **d_pos, const double **d_lab, const void **d_tail, const double **d_vel);
 /* per-cell segment table of the sorted storage: particles of cell c are [start[c], start[c+1]) */
 int pfem2_cell_starts(pfem2_handle *h, const int **d_cell_start);
 

@@ -127,30 +127,37 @@ constexpr int kWalkHops = 3;
 template <bool WALK>
 __device__ __forceinline__ bool locate_mover(const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
                                              const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx,
-                                             const CellGeom &g0, unsigned &c, double x, double y, double a0, double a1,
+                                             CellGeom &g, int4 &e, unsigned &c, double x, double y, double a0, double a1,
                                              double a2, double &L0, double &L1, double &L2)
 {
     if (WALK) {
-        unsigned cur = c;
+        int4 ecur = e;
+        const unsigned o0 = g.n0, o1 = g.n1, o2 = g.n2; // nodes of the cell the particle started the substep in
 #pragma unroll 1
         for (int hop = 0; hop < kWalkHops; ++hop) {
-            const int4 e = __ldg(edge_nbr + cur);
-            const int nxt = (a0 <= a1 && a0 <= a2) ? e.x : ((a1 <= a2) ? e.y : e.z);
+            const int nxt = (a0 <= a1 && a0 <= a2) ? ecur.x : ((a1 <= a2) ? ecur.y : ecur.z);
             if (nxt < 0) break; // domain boundary: let the ordered scan decide
             const CellGeom gn = load_geom(geom, (unsigned)nxt);
+            ecur = __ldg(edge_nbr + nxt);
             to_local(gn, x, y, a0, a1, a2);
             const double m = (double)__uint_as_float(gn.pad);
             if (a0 > m && a1 > m && a2 > m) { // strictly interior: unique acceptor
-                if (!shares_vertex(g0, gn)) return false; // acceptor outside the one-ring -> deleted
+                const bool in_ring = gn.n0 == o0 || gn.n0 == o1 || gn.n0 == o2 || gn.n1 == o0 || gn.n1 == o1 || gn.n1 == o2 ||
+                                     gn.n2 == o0 || gn.n2 == o1 || gn.n2 == o2;
+                if (!in_ring) return false; // acceptor outside the one-ring -> deleted
                 c = (unsigned)nxt;
+                g = gn;
+                e = ecur;
                 L0 = a0; L1 = a1; L2 = a2;
                 return true;
             }
             if (inside_unit(a0, a1, a2)) break; // accepted inside the tolerance band: ties possible -> ordered scan
-            cur = (unsigned)nxt;
         }
     }
-    return ring_scan(geom, nbr_off, nbr_idx, c, x, y, L0, L1, L2);
+    if (!ring_scan(geom, nbr_off, nbr_idx, c, x, y, L0, L1, L2)) return false;
+    g = load_geom(geom, c);
+    e = __ldg(edge_nbr + c);
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -167,7 +174,7 @@ __device__ __forceinline__ bool locate_mover(const CellGeom *__restrict__ geom, 
 //   cell_mask[c]        sub-cell occupancy bits, flat unclamped index like kCountParticlesInSubcells (:173-181).
 // ---------------------------------------------------------------------------------------------
 template <int SUBCELL_MODE, bool WALK, bool MASK64>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
                 const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, NodalVel vel, double h, int substeps,
                 int n_cells, int ppc, int level, double sub_step, Counters *ctr, unsigned *__restrict__ stay_bits,
@@ -202,6 +209,7 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
             L2 = tl.l2;
             // cell record and its six nodal velocities stay in registers while the particle stays in the cell
             CellGeom g = load_geom(geom, c);
+            int4 e = __ldg(edge_nbr + c); // prefetched with the cell record so the first walk hop has no extra dependent load
             double ax0 = __ldg(Vx + g.n0), ax1 = __ldg(Vx + g.n1), ax2 = __ldg(Vx + g.n2);
             double ay0 = __ldg(Vy + g.n0), ay1 = __ldg(Vy + g.n1), ay2 = __ldg(Vy + g.n2);
 #pragma unroll 1
@@ -219,12 +227,11 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
                     continue;
                 }
                 ++my_movers;
-                if (!locate_mover<WALK>(geom, edge_nbr, nbr_off, nbr_idx, g, c, x, y, a0, a1, a2, L0, L1, L2)) {
+                if (!locate_mover<WALK>(geom, edge_nbr, nbr_off, nbr_idx, g, e, c, x, y, a0, a1, a2, L0, L1, L2)) {
                     lost = true;
                     break;
                 }
                 if (s + 1 < substeps) {
-                    g = load_geom(geom, c);
                     ax0 = __ldg(Vx + g.n0); ax1 = __ldg(Vx + g.n1); ax2 = __ldg(Vx + g.n2);
                     ay0 = __ldg(Vy + g.n0); ay1 = __ldg(Vy + g.n1); ay2 = __ldg(Vy + g.n2);
                 }
@@ -246,13 +253,8 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
             stay_bits[base >> 5] = sb;
             warp_movers[base >> 5] = __popc(mb);
         }
-        // per-cell survivor counts: one atomic per distinct (cell, stays) pair in the warp
-        {
-            const unsigned key = live ? (c * 2u + (stays ? 1u : 0u)) : 0xffffffffu;
-            const unsigned peers = __match_any_sync(0xffffffffu, key);
-            if (live && (peers & ((1u << lane) - 1)) == 0) atomicAdd((stays ? stay : arrive) + c, __popc(peers));
-        }
-        // sub-cell occupancy: bits OR-reduced per target word across the warp, one atomicOr per word
+        // per-cell survivor counts and sub-cell occupancy: lanes that end in the same cell form one group
+        // (match_any); its leader issues one atomic per counter for the whole group
         {
             unsigned fc = 0xffffffffu;
             unsigned long long bit = 0;
@@ -266,12 +268,20 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
                     bit = 1ull << (unsigned)(flat - (unsigned long long)fc * ppc);
                 }
             }
-            const unsigned peers = __match_any_sync(0xffffffffu, fc);
-            unsigned lo = __reduce_or_sync(peers, (unsigned)bit);
+            const bool own_word = live && fc == c; // false only for the tolerance-band spill into another cell's word
+            const unsigned peers = __match_any_sync(0xffffffffu, live ? c : 0xffffffffu);
+            const unsigned long long gbit = own_word ? bit : 0ull;
+            unsigned lo = __reduce_or_sync(peers, (unsigned)gbit);
             unsigned hi = 0;
-            if (MASK64) hi = __reduce_or_sync(peers, (unsigned)(bit >> 32));
-            if (fc != 0xffffffffu && (peers & ((1u << lane) - 1)) == 0)
-                atomicOr(cell_mask + fc, (unsigned long long)lo | ((unsigned long long)hi << 32));
+            if (MASK64) hi = __reduce_or_sync(peers, (unsigned)(gbit >> 32));
+            if (live && (peers & ((1u << lane) - 1)) == 0) {
+                const int ns = __popc(peers & sb), na = __popc(peers & mb);
+                if (ns) atomicAdd(stay + c, ns);
+                if (na) atomicAdd(arrive + c, na);
+                const unsigned long long word = (unsigned long long)lo | ((unsigned long long)hi << 32);
+                if (word) atomicOr(cell_mask + c, word);
+            }
+            if (live && !own_word && fc != 0xffffffffu) atomicOr(cell_mask + fc, bit);
         }
     }
     // block-level reduction of the two statistics counters

@@ -100,3 +100,14 @@ def vortex_field(mesh: HostMesh, umean: float, amp: float, wavelength: float) ->
     fx = umean + amp * np.sin(k * x) * np.cos(k * y)
     fy = -amp * np.cos(k * x) * np.sin(k * y)
     return np.ascontiguousarray(fx), np.ascontiguousarray(fy)
+
+
+def write_dat(path: str, mesh: HostMesh) -> None:
+    """Write the reference's DAT text format (vertices + type-203 triangles, 1-based ids) so that the reference's
+    own Mesh2D::loadMeshFromFile (src/mesh_2d.cu:36-96) reads the mesh back bit for bit (%.14e like the shipped files)."""
+    with open(path, "w") as f:
+        f.write(f"{mesh.n_nodes} {mesh.n_cells}\n")
+        for i, (x, y) in enumerate(mesh.vertices, start=1):
+            f.write(f"{i} {x:.14e} {y:.14e} {0.0:.14e}\n")
+        for k, (a, b, c) in enumerate(mesh.cells.astype(np.int64), start=1):
+            f.write(f"{k} 203 {a + 1} {b + 1} {c + 1} \n")

@@ -21,7 +21,8 @@ SYMBOLS = (
     "pfem2_project_ptrs", "pfem2_correct", "pfem2_correct_ptrs", "pfem2_particle_count", "pfem2_get_stats",
     "pfem2_export_aos", "pfem2_step_host", "pfem2_download", "pfem2_upload", "pfem2_device_arrays", "pfem2_cell_starts",
     "pfem2_mesh_inv_jacobi", "pfem2_mesh_one_ring", "pfem2_sort_pairs", "pfem2_kernel_launches", "pfem2_set_profiling",
-    "pfem2_get_phase_times",
+    "pfem2_get_phase_times", "pfem2_set_owned_cells", "pfem2_advect_move", "pfem2_emigrants_count", "pfem2_emigrants_pack",
+    "pfem2_immigrants_append", "pfem2_advect_finish", "pfem2_project_accumulate", "pfem2_project_finalize",
 )
 
 
@@ -83,6 +84,14 @@ def load():
     L.pfem2_mesh_one_ring.argtypes = [i, i, vp, vp, vp, C.POINTER(i), vp]
     L.pfem2_sort_pairs.argtypes = [i, i, vp, vp, vp, vp, C.POINTER(i), vp]
     L.pfem2_kernel_launches.restype = C.c_longlong
+    L.pfem2_set_owned_cells.argtypes = [vp, i, i]
+    L.pfem2_advect_move.argtypes = [vp, vp, vp, d, i]
+    L.pfem2_emigrants_count.argtypes = [vp, C.POINTER(i), i, C.POINTER(i)]
+    L.pfem2_emigrants_pack.argtypes = [vp, vp, C.c_longlong]
+    L.pfem2_immigrants_append.argtypes = [vp, vp, i]
+    L.pfem2_advect_finish.argtypes = [vp, vp, vp]
+    L.pfem2_project_accumulate.argtypes = [vp, vp]
+    L.pfem2_project_finalize.argtypes = [vp, vp, vp, vp]
     L.pfem2_set_profiling.argtypes = [vp, i]
     L.pfem2_get_phase_times.argtypes = [vp, C.POINTER(d), C.POINTER(C.c_longlong), i]
     _lib = L

@@ -43,6 +43,12 @@ struct pfem2_handle {
     unsigned *node_inc = nullptr; // 3 * n_cells, (3c + i) ascending per node
     int level = 1, ppc = 1;
     double sub_step = 1.0;
+    int own_lo = 0, own_hi = 0;              // owned cell range [own_lo, own_hi): seeding / re-seeding / emigration (multi-GPU)
+    int *mg_bounds = nullptr;                // device copy of the rank cell bounds (n_ranks + 1)
+    int *mg_rank_count = nullptr;            // device, per destination rank
+    int mg_ranks = 0;
+    std::vector<int> mg_host_counts;
+    bool move_pending = false;               // advect_move done, advect_finish outstanding
     double *centers = nullptr; // 3 * ppc
     int key_bits = 1;
 
@@ -279,7 +285,7 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
                                 h->rs_hist, h->rs_scan_scratch, h->rs_info, st);
     }
     PhaseScope ps(h, PFEM2_PHASE_REORDER);
-    PFEM2_LAUNCH(k_plan_cells, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->ppc, reseed ? 1 : 0, h->stay, h->arrive,
+    PFEM2_LAUNCH(k_plan_cells, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->own_lo, h->own_hi, h->ppc, reseed ? 1 : 0, h->stay, h->arrive,
                  h->cell_mask, h->packed, h->ctr);
     exclusive_scan_dev<unsigned long long>(h->packed, h->packed, h->n_cells_dev, 1, 0, C, h->scan_scratch64, st);
     PFEM2_LAUNCH(k_plan_finish, 1, 1, 0, st, C, h->packed, h->ctr);
@@ -288,7 +294,7 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
         if (have_stayers)
             PFEM2_LAUNCH(k_scatter_stayers, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->stay_bits,
                          h->cell_start[h->cs], h->packed, h->ctr);
-        PFEM2_LAUNCH(k_scatter_movers, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_movers, h->keys[flip],
+        PFEM2_LAUNCH(k_scatter_movers, grid_for(h->capacity), kThreads, 0, st, src, dst, C, &h->ctr->n_movers, h->keys[flip],
                      h->vals[flip], h->stay, h->packed, h->ctr);
     } else {
         PFEM2_LAUNCH(k_scatter_all, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->packed, h->ctr);
@@ -302,18 +308,20 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
 }
 
 template <int MODE, bool WALK, bool MASK64>
-void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps)
+void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int do_count)
 {
     const int C = h->mesh.n_cells;
     PFEM2_LAUNCH((k_advect_locate<MODE, WALK, MASK64>), grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->geom,
                  h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub, substeps, C, h->ppc, h->level, h->sub_step,
-                 h->ctr, h->stay_bits, h->warp_movers, h->stay, h->arrive, h->cell_mask);
+                 h->ctr, h->stay_bits, h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count);
 }
 
-int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
+// first half of advectParticles: S x (advect + locate); with do_count the per-cell statistics are fused in
+int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_count)
 {
     if (!h) return PFEM2_EINVAL;
     if (!h->seeded) return fail(h, PFEM2_ESTATE, "advect before seed");
+    if (h->move_pending) return fail(h, PFEM2_ESTATE, "advect_move called twice without advect_finish");
     if (substeps < 1) return fail(h, PFEM2_EINVAL, "particleSubsteps must be >= 1");
     CU(cudaSetDevice(h->device));
     int rc;
@@ -337,7 +345,7 @@ int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
         PhaseScope ps(h, PFEM2_PHASE_ADVECT);
         const bool m64 = h->ppc > 32, walk = h->opt.exact_search == 0;
         const int mode = h->opt.subcell_mode ? 1 : 0;
-#define PFEM2_ADV(M, W, B) launch_advect<M, W, B>(h, vel, hsub, substeps)
+#define PFEM2_ADV(M, W, B) launch_advect<M, W, B>(h, vel, hsub, substeps, do_count)
         if (mode == 0) {
             if (walk) { if (m64) PFEM2_ADV(0, true, true); else PFEM2_ADV(0, true, false); }
             else      { if (m64) PFEM2_ADV(0, false, true); else PFEM2_ADV(0, false, false); }
@@ -347,21 +355,72 @@ int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
         }
 #undef PFEM2_ADV
     }
-    const bool stable = h->opt.stable_order != 0;
-    if (stable) {
+    CU(cudaGetLastError());
+    h->move_pending = true;
+    return PFEM2_OK;
+}
+
+// second half: (statistics, if not fused) + re-sort by cell + distribution check / re-seed
+int advect_finish(pfem2_handle *h, NodalVel vel, int need_count)
+{
+    if (!h) return PFEM2_EINVAL;
+    if (!h->move_pending) return fail(h, PFEM2_ESTATE, "advect_finish without advect_move");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    int rc;
+    bool stable = h->opt.stable_order != 0;
+    if (need_count) {
+        // multi-GPU: particles came and went since the move pass; count everybody (all "arrived": no stayer shortcut)
+        PhaseScope ps(h, PFEM2_PHASE_REORDER);
+        const int C = h->mesh.n_cells;
+        const bool m64 = h->ppc > 32;
+        const int mode = h->opt.subcell_mode ? 1 : 0;
+#define PFEM2_CNT(M, B)                                                                                                              \
+    PFEM2_LAUNCH((k_count_all<M, B>), grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], h->ctr, C, h->ppc, h->level, h->sub_step, \
+                 h->stay, h->arrive, h->cell_mask)
+        if (mode == 0) { if (m64) PFEM2_CNT(0, true); else PFEM2_CNT(0, false); }
+        else           { if (m64) PFEM2_CNT(1, true); else PFEM2_CNT(1, false); }
+#undef PFEM2_CNT
+        if (stable) // everybody is a mover: (cell, index) pairs of the whole array, then the stable radix sort
+            PFEM2_LAUNCH(k_all_movers, grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], C, h->ctr, h->keys[0], h->vals[0],
+                         (int *)nullptr /* already counted by k_count_all */, &h->ctr->n_movers);
+    } else if (stable) {
         PhaseScope ps(h, PFEM2_PHASE_SORT);
         exclusive_scan_dev<int>(h->warp_movers, h->warp_movers, &h->ctr->n_warps, 1, 0, (long long)h->capacity / 32 + 1,
                                 h->warp_scan_scratch, st);
         PFEM2_LAUNCH(k_emit_movers, grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], h->ctr, h->stay_bits, h->warp_movers,
                      h->keys[0], h->vals[0]);
     }
-    if ((rc = reorder(h, true, true, stable, vel))) return rc;
+    h->move_pending = false;
+    if ((rc = reorder(h, true, !need_count, stable, vel))) return rc;
     if ((rc = queue_readback(h))) return rc;
     if (h->opt.verbose) {
         if ((rc = sync_counters(h))) return rc;
         printf("Particle handler contains %d particles\n", h->host_count); // particle_handler_2d.cu:341
     }
     return PFEM2_OK;
+}
+
+int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
+{
+    int rc;
+    if ((rc = advect_move(h, vel, dt, substeps, 1))) return rc;
+    return advect_finish(h, vel, 0);
+}
+
+void launch_project_cells(pfem2_handle *h, const ParticleSoA &p)
+{
+    cudaStream_t st = h->stream;
+    const int C = h->mesh.n_cells, ppc = h->ppc;
+    // lanes per cell: about a quarter of the nominal segment length, so each lane keeps several loads in flight
+    if (ppc <= 4)
+        PFEM2_LAUNCH(k_project_cells<2>, grid_for((long long)C * 2), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
+    else if (ppc <= 16)
+        PFEM2_LAUNCH(k_project_cells<4>, grid_for((long long)C * 4), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
+    else if (ppc <= 36)
+        PFEM2_LAUNCH(k_project_cells<8>, grid_for((long long)C * 8), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
+    else
+        PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)C * 16), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
 }
 
 int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
@@ -376,15 +435,7 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
     const int ppc = h->ppc;
     {
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
-    // lanes per cell: about a quarter of the nominal segment length, so each lane keeps several loads in flight
-    if (ppc <= 4)
-        PFEM2_LAUNCH(k_project_cells<2>, grid_for((long long)C * 2), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
-    else if (ppc <= 16)
-        PFEM2_LAUNCH(k_project_cells<4>, grid_for((long long)C * 4), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
-    else if (ppc <= 36)
-        PFEM2_LAUNCH(k_project_cells<8>, grid_for((long long)C * 8), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
-    else
-        PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)C * 16), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
+    launch_project_cells(h, p);
     }
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
     PFEM2_LAUNCH(k_project_nodes, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, N, h->node_off, (const int *)h->node_inc, h->partial,
@@ -497,6 +548,8 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
     }
     h->key_bits = 1;
     while ((1ll << h->key_bits) <= C) ++h->key_bits; // keys 0..C (C = lost)
+    h->own_lo = 0;
+    h->own_hi = C;
 
     // sub-cell centres (:248-274), host arithmetic without contraction
     std::vector<double> cen(3 * (size_t)h->ppc);
@@ -592,6 +645,7 @@ int pfem2_destroy(pfem2_handle *h)
     cudaFree(h->stay); cudaFree(h->cell_mask); cudaFree(h->packed); cudaFree(h->scan_scratch64);
     cudaFree(h->cell_start[0]); cudaFree(h->cell_start[1]); cudaFree(h->partial); cudaFree(h->aos);
     cudaFree(h->n_cells_dev); cudaFree(h->rs_info); cudaFree(h->edge_nbr);
+    cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count);
     for (double *p : h->nodal) cudaFree(p);
     for (auto &r : h->phase_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
@@ -609,11 +663,12 @@ int pfem2_seed(pfem2_handle *h)
     h->cur = 0;
     h->cs = 0;
     PFEM2_LAUNCH(k_set_counters, 1, 1, 0, h->stream, h->ctr, 0, h->capacity);
-    PFEM2_LAUNCH(k_seed, grid_for((long long)C * h->ppc), kThreads, 0, h->stream, C, h->ppc, (const double2 *)h->mesh.d_vertices, h->geom,
-                 h->centers, h->soa[0], h->cell_start[0], h->ctr);
+    PFEM2_LAUNCH(k_seed, grid_for(std::max<long long>((long long)(h->own_hi - h->own_lo) * h->ppc, C + 1)), kThreads, 0, h->stream, C,
+                 h->own_lo, h->own_hi, h->ppc, (const double2 *)h->mesh.d_vertices, h->geom, h->centers, h->soa[0], h->cell_start[0],
+                 h->ctr);
     CU(cudaGetLastError());
     h->seeded = true;
-    h->host_count = C * h->ppc;
+    h->host_count = (h->own_hi - h->own_lo) * h->ppc;
     h->host_added = 0;
     h->readback_pending = false;
     if (h->opt.verbose) {
@@ -836,6 +891,108 @@ int pfem2_get_phase_times(pfem2_handle *h, double *ms, long long *calls, int res
         if (calls) calls[k] = h->phase_calls[k];
         if (reset) { h->phase_ms[k] = 0; h->phase_calls[k] = 0; }
     }
+    return PFEM2_OK;
+}
+
+int pfem2_set_owned_cells(pfem2_handle *h, int cell_lo, int cell_hi)
+{
+    if (!h) return PFEM2_EINVAL;
+    if (cell_lo < 0 || cell_hi > h->mesh.n_cells || cell_lo > cell_hi) return fail(h, PFEM2_EINVAL, "bad owned cell range");
+    if (h->seeded) return fail(h, PFEM2_ESTATE, "set_owned_cells after seed");
+    h->own_lo = cell_lo;
+    h->own_hi = cell_hi;
+    return PFEM2_OK;
+}
+
+int pfem2_advect_move(pfem2_handle *h, const double *vx, const double *vy, double dt, int substeps)
+{
+    return advect_move(h, nodal(vx, vy, nullptr), dt, substeps, 0);
+}
+
+int pfem2_advect_finish(pfem2_handle *h, const double *vx, const double *vy) { return advect_finish(h, nodal(vx, vy, nullptr), 1); }
+
+int pfem2_emigrants_count(pfem2_handle *h, const int *h_bounds, int n_ranks, int *h_counts)
+{
+    if (!h || !h_bounds || !h_counts || n_ranks < 1 || n_ranks > 64) return PFEM2_EINVAL;
+    if (!h->move_pending) return fail(h, PFEM2_ESTATE, "emigrants_count outside advect_move / advect_finish");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (h->mg_ranks != n_ranks) {
+        cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count);
+        h->mg_bounds = h->mg_rank_count = nullptr;
+        CU(cudaMalloc((void **)&h->mg_bounds, sizeof(int) * (n_ranks + 1)));
+        CU(cudaMalloc((void **)&h->mg_rank_count, sizeof(int) * (n_ranks + 1)));
+        h->mg_ranks = n_ranks;
+    }
+    CU(cudaMemcpyAsync(h->mg_bounds, h_bounds, sizeof(int) * (n_ranks + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->mg_rank_count, 0, sizeof(int) * (n_ranks + 1), st));
+    PFEM2_LAUNCH(k_emigrant_count, grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], h->ctr, h->own_lo, h->own_hi, h->mg_bounds,
+                 n_ranks, h->mg_rank_count);
+    h->mg_host_counts.assign(n_ranks, 0);
+    CU(cudaMemcpyAsync(h->mg_host_counts.data(), h->mg_rank_count, sizeof(int) * n_ranks, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int r = 0; r < n_ranks; ++r) h_counts[r] = h->mg_host_counts[r];
+    return PFEM2_OK;
+}
+
+int pfem2_emigrants_pack(pfem2_handle *h, void *d_records, long long capacity_records)
+{
+    if (!h || !d_records) return PFEM2_EINVAL;
+    if (!h->move_pending || h->mg_ranks == 0) return fail(h, PFEM2_ESTATE, "emigrants_pack before emigrants_count");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    std::vector<int> off(h->mg_ranks + 1, 0);
+    for (int r = 0; r < h->mg_ranks; ++r) off[r + 1] = off[r] + h->mg_host_counts[r];
+    if (off[h->mg_ranks] > capacity_records) return fail(h, PFEM2_ECAPACITY, "emigrant buffer too small");
+    CU(cudaMemcpyAsync(h->mg_rank_count, off.data(), sizeof(int) * (h->mg_ranks + 1), cudaMemcpyHostToDevice, st)); // cursors
+    PFEM2_LAUNCH(k_emigrant_pack, grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], h->ctr, h->own_lo, h->own_hi, h->mg_bounds,
+                 h->mg_ranks, h->mg_rank_count, (int4 *)d_records);
+    CU(cudaStreamSynchronize(st)); // `off` is a host temporary
+    return PFEM2_OK;
+}
+
+int pfem2_immigrants_append(pfem2_handle *h, const void *d_records, int n)
+{
+    if (!h || n < 0 || (n > 0 && !d_records)) return PFEM2_EINVAL;
+    if (!h->move_pending) return fail(h, PFEM2_ESTATE, "immigrants_append outside advect_move / advect_finish");
+    if (n == 0) return PFEM2_OK;
+    CU(cudaSetDevice(h->device));
+    if ((long long)h->host_count + n > h->capacity) return fail(h, PFEM2_ECAPACITY, "no room for the immigrants");
+    PFEM2_LAUNCH(k_immigrant_append, grid_for(n), kThreads, 0, h->stream, h->soa[h->cur], h->ctr, (const int4 *)d_records, n);
+    PFEM2_LAUNCH(k_add_count, 1, 1, 0, h->stream, h->ctr, n);
+    h->host_count += n;
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int pfem2_project_accumulate(pfem2_handle *h, double *d_acc3)
+{
+    if (!h || !d_acc3) return PFEM2_EINVAL;
+    if (!h->seeded) return fail(h, PFEM2_ESTATE, "project before seed");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int C = h->mesh.n_cells, N = h->mesh.n_nodes;
+    ParticleSoA p = h->soa[h->cur];
+    {
+        PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
+        launch_project_cells(h, p);
+    }
+    PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
+    PFEM2_LAUNCH(k_project_nodes_acc, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, N, h->node_off, (const int *)h->node_inc, h->partial,
+                 d_acc3);
+    (void)C;
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int pfem2_project_finalize(pfem2_handle *h, const double *d_acc3, double *d_vx, double *d_vy)
+{
+    if (!h || !d_acc3 || !d_vx || !d_vy) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    const int N = h->mesh.n_nodes;
+    PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
+    PFEM2_LAUNCH(k_project_finalize, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, N, d_acc3, d_vx, d_vy);
+    CU(cudaGetLastError());
     return PFEM2_OK;
 }
 

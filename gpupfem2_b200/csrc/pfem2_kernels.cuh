@@ -62,12 +62,15 @@ k_inv_jacobi(int n_cells, const double2 *__restrict__ vertices, const unsigned *
 // One thread per particle: coalesced SoA stores.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_seed(int n_cells, int ppc, const double2 *__restrict__ vertices, const CellGeom *__restrict__ geom,
+k_seed(int n_cells, int own_lo, int own_hi, int ppc, const double2 *__restrict__ vertices, const CellGeom *__restrict__ geom,
        const double *__restrict__ centers, ParticleSoA p, int *__restrict__ cell_start, Counters *ctr)
 {
-    const long long total = (long long)n_cells * ppc;
+    const long long total = (long long)(own_hi - own_lo) * ppc;
+    // cells outside the owned range [own_lo, own_hi) get empty segments
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= n_cells; c += gridDim.x * blockDim.x)
+        if (c < own_lo || c >= own_hi) cell_start[c] = c < own_lo ? 0 : (int)total;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i / ppc), s = (int)(i - (long long)c * ppc);
+        const int c = own_lo + (int)(i / ppc), s = (int)(i - (long long)(c - own_lo) * ppc);
         const uint4 nn = __ldg(reinterpret_cast<const uint4 *>(&geom[c].n0));
         const double2 v0 = __ldg(&vertices[nn.x]), v1 = __ldg(&vertices[nn.y]), v2 = __ldg(&vertices[nn.z]);
         const double L0 = __ldg(&centers[3 * s]), L1 = __ldg(&centers[3 * s + 1]), L2 = __ldg(&centers[3 * s + 2]);
@@ -78,7 +81,6 @@ k_seed(int n_cells, int ppc, const double2 *__restrict__ vertices, const CellGeo
         if (s == 0) cell_start[c] = (int)i;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        cell_start[n_cells] = (int)total;
         ctr->count = (int)total;
         ctr->live = (int)total;
         ctr->added = 0;
@@ -160,6 +162,42 @@ __device__ __forceinline__ bool locate_mover(const CellGeom *__restrict__ geom, 
     return true;
 }
 
+// Per-cell survivor counts and sub-cell occupancy (kCountParticlesInSubcells :173-181) for one warp of particles:
+// lanes that end in the same cell form one group (match_any); its leader issues one atomic per counter for the
+// whole group.  sb / mb are the warp ballots of "stayed in its cell" / "changed cell".
+template <int SUBCELL_MODE, bool MASK64>
+__device__ __forceinline__ void accumulate_cell_stats(bool live, unsigned c, double L0, double L1, double L2, unsigned sb, unsigned mb,
+                                                      int lane, int n_cells, int ppc, int level, double sub_step,
+                                                      int *__restrict__ stay, int *__restrict__ arrive,
+                                                      unsigned long long *__restrict__ cell_mask)
+{
+    unsigned fc = 0xffffffffu;
+    unsigned long long bit = 0;
+    if (live) {
+        const int sub = SUBCELL_MODE == 0 ? subcell_index(L0, L1, L2, level, sub_step) : subcell_index_clamped(L0, L1, L2, level, sub_step);
+        // reference: ++hist[cellID * ppc + sub] in unsigned arithmetic, unchecked
+        const unsigned long long flat = (unsigned long long)(unsigned)(c * (unsigned)ppc + (unsigned)sub);
+        if (flat < (unsigned long long)n_cells * ppc) {
+            fc = (unsigned)(flat / (unsigned)ppc);
+            bit = 1ull << (unsigned)(flat - (unsigned long long)fc * ppc);
+        }
+    }
+    const bool own_word = live && fc == c; // false only for the tolerance-band spill into another cell's word
+    const unsigned peers = __match_any_sync(0xffffffffu, live ? c : 0xffffffffu);
+    const unsigned long long gbit = own_word ? bit : 0ull;
+    unsigned lo = __reduce_or_sync(peers, (unsigned)gbit);
+    unsigned hi = 0;
+    if (MASK64) hi = __reduce_or_sync(peers, (unsigned)(gbit >> 32));
+    if (live && (peers & ((1u << lane) - 1)) == 0) {
+        const int ns = __popc(peers & sb), na = __popc(peers & mb);
+        if (ns) atomicAdd(stay + c, ns);
+        if (na) atomicAdd(arrive + c, na);
+        const unsigned long long word = (unsigned long long)lo | ((unsigned long long)hi << 32);
+        if (word) atomicOr(cell_mask + c, word);
+    }
+    if (live && !own_word && fc != 0xffffffffu) atomicOr(cell_mask + fc, bit);
+}
+
 // ---------------------------------------------------------------------------------------------
 // advect + locate, all S substeps fused in one pass over the particles
 //   kAdvectParticles :54-70, kCheckParticleInCell :117-131, kCheckParticleInNeighbors :133-162.
@@ -179,7 +217,7 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
                 const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, NodalVel vel, double h, int substeps,
                 int n_cells, int ppc, int level, double sub_step, Counters *ctr, unsigned *__restrict__ stay_bits,
                 int *__restrict__ warp_movers, int *__restrict__ stay, int *__restrict__ arrive,
-                unsigned long long *__restrict__ cell_mask)
+                unsigned long long *__restrict__ cell_mask, int do_count)
 {
     const double *__restrict__ Vx, *__restrict__ Vy;
     {
@@ -253,36 +291,9 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
             stay_bits[base >> 5] = sb;
             warp_movers[base >> 5] = __popc(mb);
         }
-        // per-cell survivor counts and sub-cell occupancy: lanes that end in the same cell form one group
-        // (match_any); its leader issues one atomic per counter for the whole group
-        {
-            unsigned fc = 0xffffffffu;
-            unsigned long long bit = 0;
-            if (live) {
-                const int sub = SUBCELL_MODE == 0 ? subcell_index(L0, L1, L2, level, sub_step)
-                                                  : subcell_index_clamped(L0, L1, L2, level, sub_step);
-                // reference: ++hist[cellID * ppc + sub] in unsigned arithmetic, unchecked
-                const unsigned long long flat = (unsigned long long)(unsigned)(c * (unsigned)ppc + (unsigned)sub);
-                if (flat < (unsigned long long)n_cells * ppc) {
-                    fc = (unsigned)(flat / (unsigned)ppc);
-                    bit = 1ull << (unsigned)(flat - (unsigned long long)fc * ppc);
-                }
-            }
-            const bool own_word = live && fc == c; // false only for the tolerance-band spill into another cell's word
-            const unsigned peers = __match_any_sync(0xffffffffu, live ? c : 0xffffffffu);
-            const unsigned long long gbit = own_word ? bit : 0ull;
-            unsigned lo = __reduce_or_sync(peers, (unsigned)gbit);
-            unsigned hi = 0;
-            if (MASK64) hi = __reduce_or_sync(peers, (unsigned)(gbit >> 32));
-            if (live && (peers & ((1u << lane) - 1)) == 0) {
-                const int ns = __popc(peers & sb), na = __popc(peers & mb);
-                if (ns) atomicAdd(stay + c, ns);
-                if (na) atomicAdd(arrive + c, na);
-                const unsigned long long word = (unsigned long long)lo | ((unsigned long long)hi << 32);
-                if (word) atomicOr(cell_mask + c, word);
-            }
-            if (live && !own_word && fc != 0xffffffffu) atomicOr(cell_mask + fc, bit);
-        }
+        if (do_count)
+            accumulate_cell_stats<SUBCELL_MODE, MASK64>(live, c, L0, L1, L2, sb, mb, lane, n_cells, ppc, level, sub_step, stay, arrive,
+                                                        cell_mask);
     }
     // block-level reduction of the two statistics counters
     __shared__ int s_mov, s_lost;
@@ -328,10 +339,10 @@ k_all_movers(ParticleSoA p, int n_cells, Counters *ctr, unsigned *__restrict__ k
     const int n = ctr->count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         unsigned c = ld_cell(p.tail + i);
-        if (c >= (unsigned)n_cells) c = (unsigned)n_cells - 1; // caller validated; keep memory safe regardless
+        if (c >= (unsigned)n_cells) c = (unsigned)n_cells; // lost / handed-over particles sort behind every cell and are dropped
         keys[i] = c;
         vals[i] = (unsigned)i;
-        atomicAdd(arrive + c, 1);
+        if (arrive && c < (unsigned)n_cells) atomicAdd(arrive + c, 1);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *n_movers = n;
 }
@@ -341,14 +352,14 @@ k_all_movers(ParticleSoA p, int n_cells, Counters *ctr, unsigned *__restrict__ k
 //   packed[c] = (stay + arrive + missing)(c) | arrive(c) << 32   (one 64-bit scan yields both prefix sums)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_plan_cells(int n_cells, int ppc, int reseed, const int *__restrict__ stay, const int *__restrict__ arrive,
+k_plan_cells(int n_cells, int own_lo, int own_hi, int ppc, int reseed, const int *__restrict__ stay, const int *__restrict__ arrive,
              const unsigned long long *__restrict__ cell_mask, unsigned long long *__restrict__ packed, Counters *ctr)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     int missing = 0;
     if (c < n_cells) {
         const unsigned long long full = ppc >= 64 ? ~0ull : ((1ull << ppc) - 1ull);
-        missing = reseed ? ppc - __popcll(cell_mask[c] & full) : 0;
+        missing = (reseed && c >= own_lo && c < own_hi) ? ppc - __popcll(cell_mask[c] & full) : 0; // only owned cells are re-seeded
         const unsigned a = (unsigned)arrive[c];
         packed[c] = (unsigned long long)((unsigned)stay[c] + a + (unsigned)missing) | ((unsigned long long)a << 32);
     }
@@ -466,14 +477,15 @@ k_scatter_all(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_old_pt
 
 // movers, sorted by new cell (stable: array order within a cell), go right behind the cell's stayers
 __global__ void __launch_bounds__(kThreads)
-k_scatter_movers(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_movers, const unsigned *__restrict__ keys_sorted,
-                 const unsigned *__restrict__ vals_sorted, const int *__restrict__ stay,
+k_scatter_movers(ParticleSoA src, ParticleSoA dst, int n_cells, const int *__restrict__ n_movers,
+                 const unsigned *__restrict__ keys_sorted, const unsigned *__restrict__ vals_sorted, const int *__restrict__ stay,
                  const unsigned long long *__restrict__ packed_start, const Counters *ctr)
 {
     if (ctr->overflow) return;
     const int m = *n_movers;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
         const unsigned c = keys_sorted[j];
+        if (c >= (unsigned)n_cells) continue; // lost
         const unsigned s = vals_sorted[j];
         const unsigned long long ps = packed_start[c];
         const int d = (int)(unsigned)(ps & 0xffffffffull) + __ldg(stay + c) + (j - (int)(unsigned)(ps >> 32));
@@ -515,6 +527,147 @@ k_reseed(int n_cells, int ppc, const double2 *__restrict__ vertices, const CellG
         dst.vel[d] = make_double2(interp3(L0, L1, L2, ax0, ax1, ax2), interp3(L0, L1, L2, ay0, ay1, ay2));
         ++d;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU (strip partition): the move pass runs without statistics; after particles that left the
+// owned cell range have been handed to their new owner and the immigrants appended, one pass over all live
+// particles accumulates the per-cell counts and occupancy masks (everybody counts as "arrived").
+// ---------------------------------------------------------------------------------------------
+template <int SUBCELL_MODE, bool MASK64>
+__global__ void __launch_bounds__(kThreads)
+k_count_all(ParticleSoA p, const Counters *ctr, int n_cells, int ppc, int level, double sub_step, int *__restrict__ stay,
+            int *__restrict__ arrive, unsigned long long *__restrict__ cell_mask)
+{
+    const int n = ctr->count;
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        bool live = false;
+        unsigned c = 0;
+        double L0 = 0, L1 = 0, L2 = 0;
+        if (i < n) {
+            const ParticleTail tl = ld_tail(p.tail + i);
+            c = tl.cell;
+            live = c != kLostCell;
+            if (live) {
+                const double2 lab = p.lab[i];
+                L0 = lab.x;
+                L1 = lab.y;
+                L2 = tl.l2;
+            }
+        }
+        const unsigned mb = __ballot_sync(0xffffffffu, live);
+        accumulate_cell_stats<SUBCELL_MODE, MASK64>(live, c, L0, L1, L2, 0u, mb, lane, n_cells, ppc, level, sub_step, stay, arrive, cell_mask);
+    }
+}
+
+// destination rank of a cell: bounds[r] <= cell < bounds[r + 1]   (n_ranks <= 64)
+__device__ __forceinline__ int rank_of_cell(unsigned c, const int *__restrict__ bounds, int n_ranks)
+{
+    int r = 0;
+    while (r + 1 < n_ranks && (int)c >= bounds[r + 1]) ++r;
+    return r;
+}
+
+// emigrants = live particles whose cell is outside [own_lo, own_hi).  Pass 1 counts them per destination rank.
+__global__ void __launch_bounds__(kThreads)
+k_emigrant_count(ParticleSoA p, const Counters *ctr, int own_lo, int own_hi, const int *__restrict__ bounds, int n_ranks,
+                 int *__restrict__ rank_count)
+{
+    const int n = ctr->count;
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        int r = -1;
+        if (i < n) {
+            const unsigned c = ld_cell(p.tail + i);
+            if (c != kLostCell && ((int)c < own_lo || (int)c >= own_hi)) r = rank_of_cell(c, bounds, n_ranks);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, r);
+        if (r >= 0 && (peers & ((1u << lane) - 1)) == 0) atomicAdd(rank_count + r, __popc(peers));
+    }
+}
+
+// Pass 2 packs them as 64-byte records {pos, lab, tail, vel} grouped by destination rank (rank_cursor starts at the
+// exclusive prefix of the counts) and removes them from the local array (cell = lost).
+__global__ void __launch_bounds__(kThreads)
+k_emigrant_pack(ParticleSoA p, const Counters *ctr, int own_lo, int own_hi, const int *__restrict__ bounds, int n_ranks,
+                int *__restrict__ rank_cursor, int4 *__restrict__ out)
+{
+    const int n = ctr->count;
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        int r = -1;
+        if (i < n) {
+            const unsigned c = ld_cell(p.tail + i);
+            if (c != kLostCell && ((int)c < own_lo || (int)c >= own_hi)) r = rank_of_cell(c, bounds, n_ranks);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, r);
+        if (r < 0) continue;
+        const int leader = __ffs(peers) - 1;
+        int slot = 0;
+        if (lane == leader) slot = atomicAdd(rank_cursor + r, __popc(peers));
+        slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1));
+        int4 *rec = out + 4 * (size_t)slot;
+        rec[0] = *reinterpret_cast<const int4 *>(p.pos + i);
+        rec[1] = *reinterpret_cast<const int4 *>(p.lab + i);
+        rec[2] = *reinterpret_cast<const int4 *>(p.tail + i);
+        rec[3] = *reinterpret_cast<const int4 *>(p.vel + i);
+        st_cell(p.tail + i, kLostCell);
+    }
+}
+
+// immigrants: 64-byte records appended behind the current array
+__global__ void __launch_bounds__(kThreads)
+k_immigrant_append(ParticleSoA p, Counters *ctr, const int4 *__restrict__ in, int m)
+{
+    const int n = ctr->count;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const int4 *rec = in + 4 * (size_t)j;
+        *reinterpret_cast<int4 *>(p.pos + n + j) = rec[0];
+        *reinterpret_cast<int4 *>(p.lab + n + j) = rec[1];
+        *reinterpret_cast<int4 *>(p.tail + n + j) = rec[2];
+        *reinterpret_cast<int4 *>(p.vel + n + j) = rec[3];
+    }
+}
+__global__ void k_add_count(Counters *ctr, int m)
+{
+    ctr->count += m;
+    ctr->n_old = ctr->count;
+    ctr->n_warps = (ctr->count + 31) >> 5;
+}
+
+// projection, multi-GPU flavour: per-node accumulators {sum L v_x, sum L v_y, sum L} without the division, so that the
+// contributions of the strips sharing an interface node can be added before kFinalizeVelocityProjection's division
+__global__ void __launch_bounds__(kThreads)
+k_project_nodes_acc(int n_nodes, const int *__restrict__ node_off, const int *__restrict__ node_inc,
+                    const double *__restrict__ partial, double *__restrict__ acc3)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    double sx = 0.0, sy = 0.0, sw = 0.0;
+    const int e = __ldg(node_off + i + 1);
+    for (int q = __ldg(node_off + i); q < e; ++q) {
+        const double *a = partial + 3 * (size_t)__ldg(node_inc + q);
+        sx = __dadd_rn(sx, a[0]);
+        sy = __dadd_rn(sy, a[1]);
+        sw = __dadd_rn(sw, a[2]);
+    }
+    acc3[3 * (size_t)i] = sx;
+    acc3[3 * (size_t)i + 1] = sy;
+    acc3[3 * (size_t)i + 2] = sw;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_project_finalize(int n_nodes, const double *__restrict__ acc3, double *__restrict__ vx, double *__restrict__ vy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const double sw = acc3[3 * (size_t)i + 2];
+    vx[i] = __ddiv_rn(acc3[3 * (size_t)i], sw);
+    vy[i] = __ddiv_rn(acc3[3 * (size_t)i + 1], sw);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -126,6 +126,24 @@ int pfem2_device_arrays(pfem2_handle *h, const double **d_pos, const double **d_
 /* per-cell segment table of the sorted storage: particles of cell c are [start[c], start[c+1]) */
 int pfem2_cell_starts(pfem2_handle *h, const int **d_cell_start);
 
+/* ---- multi-GPU building blocks (strip partition of the cell index range; no reference counterpart:
+ * the reference is single-GPU).  One handle per GPU over the SAME global mesh; each handle owns the cells
+ * [cell_lo, cell_hi) and the particles inside them.  A step is
+ *     advect_move ; emigrants_count ; emigrants_pack ; <exchange records over NCCL> ; immigrants_append ; advect_finish ;
+ *     project_accumulate ; <sum interface-node accumulators over NCCL> ; project_finalize ; correct
+ * Records are 64 bytes: {x, y | L0, L1 | L2, cell, id | vx, vy}. ---- */
+int pfem2_set_owned_cells(pfem2_handle *h, int cell_lo, int cell_hi); /* before pfem2_seed; seeds / re-seeds only these cells */
+int pfem2_advect_move(pfem2_handle *h, const double *d_vx, const double *d_vy, double dt, int substeps);
+/* per destination rank (cells [h_bounds[r], h_bounds[r+1])) the number of live particles that left the owned range */
+int pfem2_emigrants_count(pfem2_handle *h, const int *h_bounds, int n_ranks, int *h_counts);
+/* packs them grouped by destination rank in rank order and removes them locally */
+int pfem2_emigrants_pack(pfem2_handle *h, void *d_records, long long capacity_records);
+int pfem2_immigrants_append(pfem2_handle *h, const void *d_records, int n);
+int pfem2_advect_finish(pfem2_handle *h, const double *d_vx, const double *d_vy);
+/* d_acc3: n_nodes x {sum L v_x, sum L v_y, sum L} of the particles this handle holds (no division) */
+int pfem2_project_accumulate(pfem2_handle *h, double *d_acc3);
+int pfem2_project_finalize(pfem2_handle *h, const double *d_acc3, double *d_vx, double *d_vy);
+
 /* ---- mesh preparation helpers (the step right before the path; reference src/mesh_2d.cu) ---- */
 /* kCalculateInvJacobi, mesh_2d.cu:21-34, same operation order -> same bits */
 int pfem2_mesh_inv_jacobi(int n_cells, const double *d_vertices, const unsigned *d_cells, double *d_inv_jacobi, void *stream);

@@ -41,6 +41,9 @@ def lib():
         L.orc_init_velocity.argtypes = [C.c_void_p, _dp, _dp]
         L.orc_advect.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int]
         L.orc_project.argtypes = [C.c_void_p, _dp, _dp]
+        L.orc_move.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int]
+        L.orc_check_distribution.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int]
+        L.orc_project_accumulate.argtypes = [C.c_void_p, _dp]
         L.orc_correct.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
         L.orc_count.argtypes = [C.c_void_p]
         L.orc_last_stats.argtypes = [C.c_void_p, _ip, _ip]
@@ -129,6 +132,17 @@ class OracleHandler:
 
     def advect_particles(self, fx, fy, dt, substeps):
         return lib().orc_advect(self._h, _d(fx), _d(fy), dt, substeps)
+
+    def move(self, fx, fy, dt, substeps):
+        return lib().orc_move(self._h, _d(fx), _d(fy), dt, substeps)
+
+    def check_distribution(self, fx, fy, own_lo, own_hi):
+        return lib().orc_check_distribution(self._h, _d(fx), _d(fy), own_lo, own_hi)
+
+    def project_accumulate(self):
+        acc = np.zeros((self.mesh.n_nodes, 3), dtype=np.float64)
+        lib().orc_project_accumulate(self._h, _d(acc))
+        return acc
 
     def project_velocity_onto_grid(self, wx, wy):
         lib().orc_project(self._h, _d(wx), _d(wy))

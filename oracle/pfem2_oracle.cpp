@@ -337,7 +337,10 @@ void orc_init_velocity(orc_handle *h, const double *vx, const double *vy)
 
 // advectParticles, :328-342 = S x (kAdvectParticles :54-70 ; sortParticlesInCells :363-395) ;
 // checkParticleDistribution :397-423
-int orc_advect(orc_handle *h, const double *vx, const double *vy, double dt, int substeps)
+static int check_distribution(orc_handle *h, const double *vx, const double *vy, int own_lo, int own_hi);
+
+// the S substeps of advectParticles (:333-338) without the distribution check; multi-rank tests call the two halves
+int orc_move(orc_handle *h, const double *vx, const double *vy, double dt, int substeps)
 {
     const double hstep = dt / substeps; // :330, host double
     std::memset(h->lost, 0, sizeof(h->lost));
@@ -398,6 +401,23 @@ int orc_advect(orc_handle *h, const double *vx, const double *vy, double dt, int
         }
     }
 
+    return h->count();
+}
+
+int orc_advect(orc_handle *h, const double *vx, const double *vy, double dt, int substeps)
+{
+    orc_move(h, vx, vy, dt, substeps);
+    return check_distribution(h, vx, vy, 0, h->n_cells);
+}
+
+// re-seeding restricted to the owned cell range [own_lo, own_hi) (the reference is single-GPU: whole mesh)
+int orc_check_distribution(orc_handle *h, const double *vx, const double *vy, int own_lo, int own_hi)
+{
+    return check_distribution(h, vx, vy, own_lo, own_hi);
+}
+
+static int check_distribution(orc_handle *h, const double *vx, const double *vy, int own_lo, int own_hi)
+{
     // checkParticleDistribution :397-423
     const int C = h->n_cells, ppc = h->ppc;
     const long long hist_size = (long long)C * ppc;
@@ -411,7 +431,7 @@ int orc_advect(orc_handle *h, const double *vx, const double *vy, double dt, int
         if (k < hist_size) ++h->hist[(size_t)k];
     }
     int added = 0;
-    for (int c = 0; c < C; ++c) { // kCountParticlesToBeAdded :183-195 ; kAddParticlesToCell :197-236
+    for (int c = own_lo; c < own_hi; ++c) { // kCountParticlesToBeAdded :183-195 ; kAddParticlesToCell :197-236
         const unsigned *tri = &h->cells[3 * (size_t)c];
         for (int s = 0; s < ppc; ++s) {
             if (h->hist[(size_t)c * ppc + s] != 0) continue;
@@ -434,7 +454,24 @@ int orc_advect(orc_handle *h, const double *vx, const double *vy, double dt, int
 // projectVelocityOntoGrid :350-361 = kProjectParticleVelocityOntoGrid :90-107 (t = L_i * v, then sum; the
 // reference sums with fp64 atomics in scheduling order) ; kFinalizeVelocityProjection :109-115 (IEEE division).
 // Summation order here: per cell in particle order, then per node over incident cells ascending.
+static void project_acc(orc_handle *h, double *acc3);
+
 void orc_project(orc_handle *h, double *vx, double *vy)
+{
+    const int N = h->n_nodes;
+    std::vector<double> acc(3 * (size_t)N);
+    project_acc(h, acc.data());
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; ++i) {
+        vx[i] = acc[3 * (size_t)i] / acc[3 * (size_t)i + 2];
+        vy[i] = acc[3 * (size_t)i + 1] / acc[3 * (size_t)i + 2];
+    }
+}
+
+// per-node accumulators {sum L v_x, sum L v_y, sum L} without the division (multi-rank tests add the strips' parts)
+void orc_project_accumulate(orc_handle *h, double *acc3) { project_acc(h, acc3); }
+
+static void project_acc(orc_handle *h, double *acc3)
 {
     const int C = h->n_cells, N = h->n_nodes, n = h->count();
     std::vector<int> start(C + 1, 0);
@@ -467,8 +504,9 @@ void orc_project(orc_handle *h, double *vx, double *vy)
             const double *a = &part[3 * (size_t)h->node_inc[q]];
             sx += a[0]; sy += a[1]; sw += a[2];
         }
-        vx[i] = sx / sw;
-        vy[i] = sy / sw;
+        acc3[3 * (size_t)i] = sx;
+        acc3[3 * (size_t)i + 1] = sy;
+        acc3[3 * (size_t)i + 2] = sw;
     }
 }
 

@@ -44,6 +44,10 @@ void orc_subcell_centers(const orc_handle *h, double *out);
 int orc_seed(orc_handle *h);                                                  /* :304-320 -> particle count */
 void orc_init_velocity(orc_handle *h, const double *vx, const double *vy);    /* :322-326 */
 int orc_advect(orc_handle *h, const double *vx, const double *vy, double dt, int substeps); /* :328-342 */
+/* the two halves of orc_advect, and the projection without its division, for multi-rank (strip partition) tests */
+int orc_move(orc_handle *h, const double *vx, const double *vy, double dt, int substeps);
+int orc_check_distribution(orc_handle *h, const double *vx, const double *vy, int own_lo, int own_hi);
+void orc_project_accumulate(orc_handle *h, double *acc3);
 void orc_project(orc_handle *h, double *vx, double *vy);                      /* :350-361, writes in place */
 void orc_correct(orc_handle *h, const double *vx, const double *vy,
                  const double *vx_old, const double *vy_old);                 /* :344-348 */

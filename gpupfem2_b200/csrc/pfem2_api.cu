@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -297,7 +298,20 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
         PFEM2_LAUNCH(k_scatter_movers, grid_for(h->capacity), kThreads, 0, st, src, dst, C, &h->ctr->n_movers, h->keys[flip],
                      h->vals[flip], h->stay, h->packed, h->ctr);
     } else {
-        PFEM2_LAUNCH(k_scatter_all, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->packed, h->ctr);
+        PFEM2_LAUNCH(k_init_cursor, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->packed, h->cursor);
+        if (h->opt.scatter_tma) {
+            constexpr int kStages = 3;
+            static bool attr_set = false;
+            const size_t smem = scatter_smem_bytes<kStages>(kThreads);
+            if (!attr_set) {
+                CU(cudaFuncSetAttribute(k_scatter_all_tma<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            PFEM2_LAUNCH(k_scatter_all_tma<kStages>, grid_for(h->capacity, kThreads, g_num_sms * 4), kThreads, smem, st, src, dst,
+                         &h->ctr->n_old, h->cursor, h->ctr);
+        } else {
+            PFEM2_LAUNCH(k_scatter_all_regs, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
+        }
     }
     PFEM2_LAUNCH(k_reseed, grid_for(C + 1, kThreads, 1 << 30), kThreads, 0, st, C, h->ppc, (const double2 *)h->mesh.d_vertices,
                  h->geom, h->centers, vel, h->cell_mask, h->stay, h->arrive, h->packed, dst, h->cell_start[h->cs ^ 1], h->ctr);
@@ -311,9 +325,16 @@ template <int MODE, bool WALK, bool MASK64>
 void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int do_count)
 {
     const int C = h->mesh.n_cells;
-    PFEM2_LAUNCH((k_advect_locate<MODE, WALK, MASK64>), grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->geom,
-                 h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub, substeps, C, h->ppc, h->level, h->sub_step,
-                 h->ctr, h->stay_bits, h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count);
+    unsigned *sbits = h->opt.stable_order ? h->stay_bits : nullptr; // only the stable-order path consumes the ballots
+#define PFEM2_ADV_LAUNCH(NSUB)                                                                                                     \
+    PFEM2_LAUNCH((k_advect_locate<MODE, WALK, MASK64, NSUB>), grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->geom,   \
+                 h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub, substeps, C, h->ppc, h->level, h->sub_step,   \
+                 h->ctr, sbits, h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count)
+    if (substeps == 3)
+        PFEM2_ADV_LAUNCH(3);
+    else
+        PFEM2_ADV_LAUNCH(0);
+#undef PFEM2_ADV_LAUNCH
 }
 
 // first half of advectParticles: S x (advect + locate); with do_count the per-cell statistics are fused in

@@ -60,6 +60,8 @@ typedef struct pfem2_options {
                                that returns the same cell (falls back to the ordered scan in the tolerance band) */
     int stable_order;       /* 0 (default): counting-sort scatter, slot order inside a cell depends on atomic retirement
                                order; 1: deterministic order (stayers keep their order, movers radix-sorted by cell) */
+    int scatter_tma;        /* 1: stage the reorder scatter through shared memory with cp.async.bulk (TMA) per-warp pipelines;
+                               0 (default): register-staged variant (measured faster on B200, see profiles/) */
 } pfem2_options;
 
 /* counters of the last pfem2_advect call (device-resident, read back on demand) */

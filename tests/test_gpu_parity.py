@@ -107,6 +107,15 @@ def test_clamped_subcell_mode_matches_oracle(gpu, oracle):
     run_both(gpu, oracle, m, fx, fy, 3, 3, 0.2, 10, subcell_mode=1, stable_order=True)
 
 
+def test_tma_staged_scatter_matches_oracle(gpu, oracle):
+    """pfem2_options.scatter_tma: the cp.async.bulk (TMA) per-warp pipeline variant of the reorder scatter."""
+    m = cases._tiny(True)
+    fx, fy = cases._mix(m, 0.5, 1.0, 0.3, 1.0)
+    run_both(gpu, oracle, m, fx, fy, 4, 3, 0.2, 12, check_every=4, scatter_tma=True)
+    c = cases.build_case("cyl3_l2")
+    run_both(gpu, oracle, c.mesh, c.fx, c.fy, c.level, c.substeps, c.dt, 6, check_every=6, scatter_tma=True)
+
+
 def test_high_cfl_interior_deletions_match_oracle(gpu, oracle):
     """CFL ~ 1.2 per substep: jumps beyond the one-ring are deleted inside the domain."""
     m = cases._tiny(True)

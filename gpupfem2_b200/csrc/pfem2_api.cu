@@ -45,6 +45,9 @@ struct pfem2_handle {
     int level = 1, ppc = 1;
     double sub_step = 1.0;
     int own_lo = 0, own_hi = 0;              // owned cell range [own_lo, own_hi): seeding / re-seeding / emigration (multi-GPU)
+    int *own_len_dev = nullptr;              // device int: own_hi - own_lo (scan length)
+    int *node_list = nullptr;                // nodes of the owned cells (nullptr = all nodes), multi-GPU
+    int n_node_list = 0;
     int *mg_bounds = nullptr;                // device copy of the rank cell bounds (n_ranks + 1)
     int *mg_rank_count = nullptr;            // device, per destination rank
     int mg_ranks = 0;
@@ -286,10 +289,11 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
                                 h->rs_hist, h->rs_scan_scratch, h->rs_info, st);
     }
     PhaseScope ps(h, PFEM2_PHASE_REORDER);
-    PFEM2_LAUNCH(k_plan_cells, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->own_lo, h->own_hi, h->ppc, reseed ? 1 : 0, h->stay, h->arrive,
+    const int lo = h->own_lo, hi = h->own_hi, own_n = hi - lo; // cell-wise work only over the owned range
+    PFEM2_LAUNCH(k_plan_cells, grid_for(own_n, kThreads, 1 << 30), kThreads, 0, st, C, lo, hi, h->ppc, reseed ? 1 : 0, h->stay, h->arrive,
                  h->cell_mask, h->packed, h->ctr);
-    exclusive_scan_dev<unsigned long long>(h->packed, h->packed, h->n_cells_dev, 1, 0, C, h->scan_scratch64, st);
-    PFEM2_LAUNCH(k_plan_finish, 1, 1, 0, st, C, h->packed, h->ctr);
+    exclusive_scan_dev<unsigned long long>(h->packed + lo, h->packed + lo, h->own_len_dev, 1, 0, own_n, h->scan_scratch64, st);
+    PFEM2_LAUNCH(k_plan_finish, 1, 1, 0, st, hi, h->packed, h->ctr);
     ParticleSoA src = h->soa[h->cur], dst = h->soa[h->cur ^ 1];
     if (stable) {
         if (have_stayers)
@@ -298,7 +302,7 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
         PFEM2_LAUNCH(k_scatter_movers, grid_for(h->capacity), kThreads, 0, st, src, dst, C, &h->ctr->n_movers, h->keys[flip],
                      h->vals[flip], h->stay, h->packed, h->ctr);
     } else {
-        PFEM2_LAUNCH(k_init_cursor, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->packed, h->cursor);
+        PFEM2_LAUNCH(k_init_cursor, grid_for(own_n, kThreads, 1 << 30), kThreads, 0, st, lo, hi, h->packed, h->cursor);
         if (h->opt.scatter_tma) {
             constexpr int kStages = 3;
             static bool attr_set = false;
@@ -313,7 +317,7 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
             PFEM2_LAUNCH(k_scatter_all_regs, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
         }
     }
-    PFEM2_LAUNCH(k_reseed, grid_for(C + 1, kThreads, 1 << 30), kThreads, 0, st, C, h->ppc, (const double2 *)h->mesh.d_vertices,
+    PFEM2_LAUNCH(k_reseed, grid_for(own_n + 1, kThreads, 1 << 30), kThreads, 0, st, lo, hi, h->ppc, (const double2 *)h->mesh.d_vertices,
                  h->geom, h->centers, vel, h->cell_mask, h->stay, h->arrive, h->packed, dst, h->cell_start[h->cs ^ 1], h->ctr);
     h->cur ^= 1;
     h->cs ^= 1;
@@ -359,8 +363,13 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells;
     const double hsub = dt / substeps; // particle_handler_2d.cu:330, host double
-    CU(cudaMemsetAsync(h->stay, 0, sizeof(int) * 3 * ((size_t)C + 1), st)); // stay, arrive, cursor: one allocation
-    CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * ((size_t)C + 1), st));
+    {   // per-cell scratch of the owned range (+ a few cells for the tolerance-band spill of the occupancy bits)
+        const size_t lo = (size_t)h->own_lo, len = (size_t)std::min(C, h->own_hi + 4) - lo + 1;
+        CU(cudaMemsetAsync(h->stay + lo, 0, sizeof(int) * len, st));
+        CU(cudaMemsetAsync(h->arrive + lo, 0, sizeof(int) * len, st));
+        CU(cudaMemsetAsync(h->cursor + lo, 0, sizeof(int) * len, st));
+        CU(cudaMemsetAsync(h->cell_mask + lo, 0, sizeof(unsigned long long) * len, st));
+    }
     PFEM2_LAUNCH(k_begin_advect, 1, 1, 0, st, h->ctr, h->capacity);
     {
         PhaseScope ps(h, PFEM2_PHASE_ADVECT);
@@ -435,13 +444,13 @@ void launch_project_cells(pfem2_handle *h, const ParticleSoA &p)
     const int C = h->mesh.n_cells, ppc = h->ppc;
     // lanes per cell: about a quarter of the nominal segment length, so each lane keeps several loads in flight
     if (ppc <= 4)
-        PFEM2_LAUNCH(k_project_cells<2>, grid_for((long long)C * 2), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
+        PFEM2_LAUNCH(k_project_cells<2>, grid_for((long long)(h->own_hi - h->own_lo) * 2), kThreads, 0, st, h->own_lo, h->own_hi, p, h->cell_start[h->cs], h->partial);
     else if (ppc <= 16)
-        PFEM2_LAUNCH(k_project_cells<4>, grid_for((long long)C * 4), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
+        PFEM2_LAUNCH(k_project_cells<4>, grid_for((long long)(h->own_hi - h->own_lo) * 4), kThreads, 0, st, h->own_lo, h->own_hi, p, h->cell_start[h->cs], h->partial);
     else if (ppc <= 36)
-        PFEM2_LAUNCH(k_project_cells<8>, grid_for((long long)C * 8), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
+        PFEM2_LAUNCH(k_project_cells<8>, grid_for((long long)(h->own_hi - h->own_lo) * 8), kThreads, 0, st, h->own_lo, h->own_hi, p, h->cell_start[h->cs], h->partial);
     else
-        PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)C * 16), kThreads, 0, st, C, p, h->cell_start[h->cs], h->partial);
+        PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)(h->own_hi - h->own_lo) * 16), kThreads, 0, st, h->own_lo, h->own_hi, p, h->cell_start[h->cs], h->partial);
 }
 
 int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
@@ -609,6 +618,7 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
     h->arrive = h->stay + ((size_t)C + 1);
     h->cursor = h->arrive + ((size_t)C + 1);
     TRY(dev_alloc(h, &h->n_cells_dev, 1));
+    TRY(dev_alloc(h, &h->own_len_dev, 1));
     TRY(dev_alloc(h, &h->rs_info, 4));
     TRY(dev_alloc(h, &h->edge_nbr, (size_t)C));
     TRY(dev_alloc(h, &h->cell_mask, (size_t)C + 1));
@@ -649,6 +659,12 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
                      mesh->d_nbr_indices, hmin, dmax, h->edge_nbr);
     }
     TRY(build_node_incidence(h));
+    {
+        cudaError_t e = cudaMemsetAsync(h->partial, 0, sizeof(double) * 9 * (size_t)C, h->stream); // was scratch above
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->own_len_dev, &C, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { h->error = cudaGetErrorString(e); TRY(PFEM2_ECUDA); }
+    }
 #undef TRY
     *out = h;
     return PFEM2_OK;
@@ -666,7 +682,7 @@ int pfem2_destroy(pfem2_handle *h)
     cudaFree(h->stay); cudaFree(h->cell_mask); cudaFree(h->packed); cudaFree(h->scan_scratch64);
     cudaFree(h->cell_start[0]); cudaFree(h->cell_start[1]); cudaFree(h->partial); cudaFree(h->aos);
     cudaFree(h->n_cells_dev); cudaFree(h->rs_info); cudaFree(h->edge_nbr);
-    cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count);
+    cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count); cudaFree(h->own_len_dev); cudaFree(h->node_list);
     for (double *p : h->nodal) cudaFree(p);
     for (auto &r : h->phase_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
@@ -858,8 +874,13 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
         CU(cudaStreamSynchronize(st));
     }
     PFEM2_LAUNCH(k_set_counters, 1, 1, 0, st, h->ctr, n, h->capacity);
-    CU(cudaMemsetAsync(h->stay, 0, sizeof(int) * 3 * ((size_t)C + 1), st));
-    CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * ((size_t)C + 1), st));
+    {   // per-cell scratch of the owned range (+ a few cells for the tolerance-band spill of the occupancy bits)
+        const size_t lo = (size_t)h->own_lo, len = (size_t)std::min(C, h->own_hi + 4) - lo + 1;
+        CU(cudaMemsetAsync(h->stay + lo, 0, sizeof(int) * len, st));
+        CU(cudaMemsetAsync(h->arrive + lo, 0, sizeof(int) * len, st));
+        CU(cudaMemsetAsync(h->cursor + lo, 0, sizeof(int) * len, st));
+        CU(cudaMemsetAsync(h->cell_mask + lo, 0, sizeof(unsigned long long) * len, st));
+    }
     PFEM2_LAUNCH(k_all_movers, grid_for(h->capacity), kThreads, 0, st, p, C, h->ctr, h->keys[0], h->vals[0], h->arrive, &h->ctr->n_movers);
     if ((rc = reorder(h, false, false, true, nodal(nullptr, nullptr, nullptr)))) return rc;
     h->seeded = true;
@@ -922,6 +943,33 @@ int pfem2_set_owned_cells(pfem2_handle *h, int cell_lo, int cell_hi)
     if (h->seeded) return fail(h, PFEM2_ESTATE, "set_owned_cells after seed");
     h->own_lo = cell_lo;
     h->own_hi = cell_hi;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int own_n = cell_hi - cell_lo, N = h->mesh.n_nodes;
+    CU(cudaMemcpyAsync(h->own_len_dev, &own_n, sizeof(int), cudaMemcpyHostToDevice, st));
+    // compact list of the nodes the owned cells touch
+    int *flag = nullptr, *pos = nullptr, *scratch = nullptr, *n_dev = nullptr;
+    CU(cudaMalloc((void **)&flag, sizeof(int) * ((size_t)N + 1)));
+    CU(cudaMalloc((void **)&pos, sizeof(int) * ((size_t)N + 1)));
+    CU(cudaMalloc((void **)&scratch, sizeof(int) * scan_scratch_elems<int>(N)));
+    CU(cudaMalloc((void **)&n_dev, sizeof(int)));
+    CU(cudaMemsetAsync(flag, 0, sizeof(int) * ((size_t)N + 1), st));
+    CU(cudaMemcpyAsync(n_dev, &N, sizeof(int), cudaMemcpyHostToDevice, st));
+    if (own_n > 0) PFEM2_LAUNCH(k_mark_nodes, grid_for(own_n, kThreads, 1 << 30), kThreads, 0, st, cell_lo, cell_hi, h->mesh.d_cells, flag);
+    exclusive_scan_dev<int>(flag, pos, n_dev, 1, 0, N, scratch, st);
+    int total = 0;
+    CU(cudaMemcpyAsync(&total, pos + N, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(h->node_list);
+    h->node_list = nullptr;
+    h->n_node_list = total;
+    if (own_n < h->mesh.n_cells) {
+        CU(cudaMalloc((void **)&h->node_list, sizeof(int) * (size_t)std::max(total, 1)));
+        PFEM2_LAUNCH(k_compact_nodes, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, N, flag, pos, h->node_list);
+        CU(cudaStreamSynchronize(st));
+    }
+    cudaFree(flag); cudaFree(pos); cudaFree(scratch); cudaFree(n_dev);
+    CU(cudaGetLastError());
     return PFEM2_OK;
 }
 
@@ -999,8 +1047,9 @@ int pfem2_project_accumulate(pfem2_handle *h, double *d_acc3)
         launch_project_cells(h, p);
     }
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
-    PFEM2_LAUNCH(k_project_nodes_acc, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, N, h->node_off, (const int *)h->node_inc, h->partial,
-                 d_acc3);
+    const int nl = h->node_list ? h->n_node_list : N;
+    PFEM2_LAUNCH(k_project_nodes_acc, grid_for(nl, kThreads, 1 << 30), kThreads, 0, st, nl, h->node_list, h->node_off,
+                 (const int *)h->node_inc, h->partial, d_acc3);
     (void)C;
     CU(cudaGetLastError());
     return PFEM2_OK;
@@ -1012,7 +1061,8 @@ int pfem2_project_finalize(pfem2_handle *h, const double *d_acc3, double *d_vx, 
     CU(cudaSetDevice(h->device));
     const int N = h->mesh.n_nodes;
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
-    PFEM2_LAUNCH(k_project_finalize, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, N, d_acc3, d_vx, d_vy);
+    const int nl = h->node_list ? h->n_node_list : N;
+    PFEM2_LAUNCH(k_project_finalize, grid_for(nl, kThreads, 1 << 30), kThreads, 0, h->stream, nl, h->node_list, d_acc3, d_vx, d_vy);
     CU(cudaGetLastError());
     return PFEM2_OK;
 }

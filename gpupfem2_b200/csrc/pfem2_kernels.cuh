@@ -377,9 +377,11 @@ __global__ void __launch_bounds__(kThreads)
 k_plan_cells(int n_cells, int own_lo, int own_hi, int ppc, int reseed, const int *__restrict__ stay, const int *__restrict__ arrive,
              const unsigned long long *__restrict__ cell_mask, unsigned long long *__restrict__ packed, Counters *ctr)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // only the owned cell range [own_lo, own_hi) can hold particles (the whole mesh on a single GPU)
+    const int c = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
     int missing = 0;
-    if (c < n_cells) {
+    (void)n_cells;
+    if (c < own_hi) {
         const unsigned long long full = ppc >= 64 ? ~0ull : ((1ull << ppc) - 1ull);
         missing = (reseed && c >= own_lo && c < own_hi) ? ppc - __popcll(cell_mask[c] & full) : 0; // only owned cells are re-seeded
         const unsigned a = (unsigned)arrive[c];
@@ -395,9 +397,9 @@ k_plan_cells(int n_cells, int own_lo, int own_hi, int ppc, int reseed, const int
     }
 }
 
-__global__ void k_plan_finish(int n_cells, const unsigned long long *__restrict__ packed_start, Counters *ctr)
+__global__ void k_plan_finish(int own_hi, const unsigned long long *__restrict__ packed_start, Counters *ctr)
 {
-    const unsigned long long t = packed_start[n_cells];
+    const unsigned long long t = packed_start[own_hi];
     const long long total = (long long)(unsigned)(t & 0xffffffffull);
     ctr->live = (int)total - ctr->added;
     if (total > ctr->capacity) {
@@ -581,10 +583,10 @@ template <int S> constexpr size_t scatter_smem_bytes(int threads) { return (size
 
 // cursor[c] = new segment start of cell c (low half of the scanned plan word), for the fast scatter
 __global__ void __launch_bounds__(kThreads)
-k_init_cursor(int n_cells, const unsigned long long *__restrict__ packed_start, int *__restrict__ cursor)
+k_init_cursor(int own_lo, int own_hi, const unsigned long long *__restrict__ packed_start, int *__restrict__ cursor)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n_cells) cursor[c] = (int)(unsigned)(packed_start[c] & 0xffffffffull);
+    const int c = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < own_hi) cursor[c] = (int)(unsigned)(packed_start[c] & 0xffffffffull);
 }
 
 // movers, sorted by new cell (stable: array order within a cell), go right behind the cell's stayers
@@ -609,16 +611,16 @@ k_scatter_movers(ParticleSoA src, ParticleSoA dst, int n_cells, const int *__res
 // interpolated from the current nodal field; written right behind the cell's survivors.  Also
 // materialises the segment table cell_start[].
 __global__ void __launch_bounds__(kThreads)
-k_reseed(int n_cells, int ppc, const double2 *__restrict__ vertices, const CellGeom *__restrict__ geom,
+k_reseed(int own_lo, int own_hi, int ppc, const double2 *__restrict__ vertices, const CellGeom *__restrict__ geom,
          const double *__restrict__ centers, NodalVel vel, const unsigned long long *__restrict__ cell_mask,
          const int *__restrict__ stay, const int *__restrict__ arrive, const unsigned long long *__restrict__ packed_start,
          ParticleSoA dst, int *__restrict__ cell_start, const Counters *ctr)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > n_cells) return;
+    const int c = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > own_hi) return;
     const int start = (int)(unsigned)(packed_start[c] & 0xffffffffull);
     cell_start[c] = start;
-    if (c == n_cells || ctr->overflow) return;
+    if (c == own_hi || ctr->overflow) return;
     const int live = stay[c] + arrive[c];
     const int missing = (int)(unsigned)(packed_start[c + 1] & 0xffffffffull) - start - live;
     if (missing <= 0) return;
@@ -754,11 +756,13 @@ __global__ void k_add_count(Counters *ctr, int m)
 // projection, multi-GPU flavour: per-node accumulators {sum L v_x, sum L v_y, sum L} without the division, so that the
 // contributions of the strips sharing an interface node can be added before kFinalizeVelocityProjection's division
 __global__ void __launch_bounds__(kThreads)
-k_project_nodes_acc(int n_nodes, const int *__restrict__ node_off, const int *__restrict__ node_inc,
-                    const double *__restrict__ partial, double *__restrict__ acc3)
+k_project_nodes_acc(int n_list, const int *__restrict__ node_list, const int *__restrict__ node_off,
+                    const int *__restrict__ node_inc, const double *__restrict__ partial, double *__restrict__ acc3)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
+    // node_list: the nodes of the owned cells (nullptr = all nodes)
+    const int q0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q0 >= n_list) return;
+    const int i = node_list ? node_list[q0] : q0;
     double sx = 0.0, sy = 0.0, sw = 0.0;
     const int e = __ldg(node_off + i + 1);
     for (int q = __ldg(node_off + i); q < e; ++q) {
@@ -773,10 +777,12 @@ k_project_nodes_acc(int n_nodes, const int *__restrict__ node_off, const int *__
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_project_finalize(int n_nodes, const double *__restrict__ acc3, double *__restrict__ vx, double *__restrict__ vy)
+k_project_finalize(int n_list, const int *__restrict__ node_list, const double *__restrict__ acc3, double *__restrict__ vx,
+                   double *__restrict__ vy)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
+    const int q0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q0 >= n_list) return;
+    const int i = node_list ? node_list[q0] : q0;
     const double sw = acc3[3 * (size_t)i + 2];
     vx[i] = __ddiv_rn(acc3[3 * (size_t)i], sw);
     vy[i] = __ddiv_rn(acc3[3 * (size_t)i + 1], sw);
@@ -792,12 +798,13 @@ k_project_finalize(int n_nodes, const double *__restrict__ acc3, double *__restr
 // ---------------------------------------------------------------------------------------------
 template <int G>
 __global__ void __launch_bounds__(kThreads)
-k_project_cells(int n_cells, ParticleSoA p, const int *__restrict__ cell_start, double *__restrict__ partial)
+k_project_cells(int c_lo, int n_cells, ParticleSoA p, const int *__restrict__ cell_start, double *__restrict__ partial)
 {
+    // cells [c_lo, n_cells): the owned range (partials of cells that can never hold particles stay zero)
     const int lane = threadIdx.x & (G - 1);
     constexpr int groups_per_warp = 32 / G, groups_per_block = kThreads / G;
     // the loop bound is warp-uniform (the full-mask shuffles below need all 32 lanes), cells are guarded inside
-    for (int cw = blockIdx.x * groups_per_block + (threadIdx.x >> 5) * groups_per_warp; cw < n_cells;
+    for (int cw = c_lo + blockIdx.x * groups_per_block + (threadIdx.x >> 5) * groups_per_warp; cw < n_cells;
          cw += gridDim.x * groups_per_block) {
         const int c = cw + ((threadIdx.x & 31) / G);
         const bool valid = c < n_cells;
@@ -1039,6 +1046,23 @@ k_build_locate_data(int n_cells, CellGeom *__restrict__ geom, const int *__restr
     if (!(m >= 1e-5)) m = 1e-5;
     if (!(m < 0.3)) m = 2.0; // degenerate cell: never take the fast path into it
     geom[c].pad = __float_as_uint(__double2float_ru(m * 1.0001));
+}
+
+// nodes touched by the owned cells -> compact list (multi-GPU: per-node work only for these)
+__global__ void __launch_bounds__(kThreads)
+k_mark_nodes(int c_lo, int c_hi, const unsigned *__restrict__ cells, int *__restrict__ flag)
+{
+    const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_hi) return;
+    flag[cells[3 * (size_t)c]] = 1;
+    flag[cells[3 * (size_t)c + 1]] = 1;
+    flag[cells[3 * (size_t)c + 2]] = 1;
+}
+__global__ void __launch_bounds__(kThreads)
+k_compact_nodes(int n_nodes, const int *__restrict__ flag, const int *__restrict__ pos, int *__restrict__ list)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes && flag[i]) list[pos[i]] = i;
 }
 
 __global__ void k_set_counters(Counters *ctr, int count, int capacity)

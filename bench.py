@@ -40,9 +40,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES = {  # algorithmic bytes per particle per launch (64 B fp64 SoA state)
-    "advect_locate": 88,  # R(x,y,L,cell)=44 + W(x,y,L,cell)=44, independent of S
+    # advect+locate: R(x,y,L,cell)=44 + W(x,y,L,cell)=44, independent of S; the velocity correction of the previous
+    # step is folded into this pass (pfem2_options.defer_correct), so its R(L,cell,v)=44 + W(v)=16 count here
+    "advect_locate": 88 + 60,
     "project_cells": 44,  # R(L,cell,v)
-    "correct": 60,        # R(L,cell,v)=44 + W(v)=16
 }
 ALG_BYTES_STEP = 192
 

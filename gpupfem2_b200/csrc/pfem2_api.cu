@@ -53,6 +53,8 @@ struct pfem2_handle {
     int mg_ranks = 0;
     std::vector<int> mg_host_counts;
     bool move_pending = false;               // advect_move done, advect_finish outstanding
+    double *dv[2] = {nullptr, nullptr};      // deferred velocity correction: nodal increment snapshot (n_nodes each)
+    bool dv_pending = false;
     double *centers = nullptr; // 3 * ppc
     int key_bits = 1;
 
@@ -333,7 +335,8 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
 #define PFEM2_ADV_LAUNCH(NSUB)                                                                                                     \
     PFEM2_LAUNCH((k_advect_locate<MODE, WALK, MASK64, NSUB>), grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->geom,   \
                  h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub, substeps, C, h->ppc, h->level, h->sub_step,   \
-                 h->ctr, sbits, h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count)
+                 h->ctr, sbits, h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count, h->dv_pending ? h->dv[0] : nullptr,            \
+                 h->dv_pending ? h->dv[1] : nullptr)
     if (substeps == 3)
         PFEM2_ADV_LAUNCH(3);
     else
@@ -386,6 +389,7 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
 #undef PFEM2_ADV
     }
     CU(cudaGetLastError());
+    h->dv_pending = false; // the move pass applied the deferred correction
     h->move_pending = true;
     return PFEM2_OK;
 }
@@ -438,6 +442,8 @@ int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
     return advect_finish(h, vel, 0);
 }
 
+int flush_correct(pfem2_handle *h);
+
 void launch_project_cells(pfem2_handle *h, const ParticleSoA &p)
 {
     cudaStream_t st = h->stream;
@@ -458,6 +464,10 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
     if (!h) return PFEM2_EINVAL;
     if (!h->seeded) return fail(h, PFEM2_ESTATE, "project before seed");
     CU(cudaSetDevice(h->device));
+    {
+        const int rcf = flush_correct(h);
+        if (rcf) return rcf;
+    }
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells, N = h->mesh.n_nodes;
     ParticleSoA p = h->soa[h->cur];
@@ -474,11 +484,8 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
     return PFEM2_OK;
 }
 
-int do_correct(pfem2_handle *h, NodalVel v, NodalVel vold, bool has_old)
+int apply_correct_now(pfem2_handle *h, NodalVel v, NodalVel vold, bool has_old)
 {
-    if (!h) return PFEM2_EINVAL;
-    if (!h->seeded) return fail(h, PFEM2_ESTATE, "correct before seed");
-    CU(cudaSetDevice(h->device));
     ParticleSoA p = h->soa[h->cur];
     const int grid = grid_for(h->capacity);
     PhaseScope ps(h, PFEM2_PHASE_CORRECT);
@@ -487,6 +494,32 @@ int do_correct(pfem2_handle *h, NodalVel v, NodalVel vold, bool has_old)
     else
         PFEM2_LAUNCH(k_correct<false>, grid, kThreads, 0, h->stream, p, h->geom, v, vold, h->ctr);
     CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+// apply a deferred correction now (before anything reads particle velocities other than the next advect)
+int flush_correct(pfem2_handle *h)
+{
+    if (!h->dv_pending) return PFEM2_OK;
+    h->dv_pending = false;
+    return apply_correct_now(h, nodal(h->dv[0], h->dv[1], nullptr), nodal(nullptr, nullptr, nullptr), false);
+}
+
+int do_correct(pfem2_handle *h, NodalVel v, NodalVel vold, bool has_old)
+{
+    if (!h) return PFEM2_EINVAL;
+    if (!h->seeded) return fail(h, PFEM2_ESTATE, "correct before seed");
+    CU(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = flush_correct(h))) return rc; // two corrections in a row: the first one is applied eagerly
+    if (!h->opt.defer_correct || h->move_pending) return apply_correct_now(h, v, vold, has_old);
+    const int N = h->mesh.n_nodes;
+    for (double *&d : h->dv)
+        if (!d) CU(cudaMalloc((void **)&d, sizeof(double) * (size_t)N));
+    PhaseScope ps(h, PFEM2_PHASE_CORRECT);
+    PFEM2_LAUNCH(k_snapshot_dv, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, N, v, vold, has_old ? 1 : 0, h->dv[0], h->dv[1]);
+    CU(cudaGetLastError());
+    h->dv_pending = true;
     return PFEM2_OK;
 }
 
@@ -531,6 +564,7 @@ void pfem2_default_options(pfem2_options *o)
     o->stream = nullptr;
     o->device = -1;
     o->verbose = 0;
+    o->defer_correct = 1;
 }
 
 const char *pfem2_last_error(const pfem2_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
@@ -683,6 +717,7 @@ int pfem2_destroy(pfem2_handle *h)
     cudaFree(h->cell_start[0]); cudaFree(h->cell_start[1]); cudaFree(h->partial); cudaFree(h->aos);
     cudaFree(h->n_cells_dev); cudaFree(h->rs_info); cudaFree(h->edge_nbr);
     cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count); cudaFree(h->own_len_dev); cudaFree(h->node_list);
+    cudaFree(h->dv[0]); cudaFree(h->dv[1]);
     for (double *p : h->nodal) cudaFree(p);
     for (auto &r : h->phase_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
@@ -705,6 +740,7 @@ int pfem2_seed(pfem2_handle *h)
                  h->ctr);
     CU(cudaGetLastError());
     h->seeded = true;
+    h->dv_pending = false;
     h->host_count = (h->own_hi - h->own_lo) * h->ppc;
     h->host_added = 0;
     h->readback_pending = false;
@@ -770,6 +806,7 @@ int pfem2_export_aos(pfem2_handle *h, const void **d_particles96, int *count)
     CU(cudaSetDevice(h->device));
     int rc;
     if ((rc = sync_counters(h))) return rc;
+    if ((rc = flush_correct(h))) return rc;
     const size_t need = (size_t)std::max(h->capacity, 1) * 96;
     if (h->aos_bytes < need) {
         if (h->aos) cudaFree(h->aos);
@@ -814,6 +851,7 @@ int pfem2_download(pfem2_handle *h, double *x, double *y, double *l0, double *l1
     CU(cudaSetDevice(h->device));
     int rc;
     if ((rc = sync_counters(h))) return rc;
+    if ((rc = flush_correct(h))) return rc;
     const size_t n = (size_t)h->host_count;
     const ParticleSoA &p = h->soa[h->cur];
     std::vector<double2> hp(n), hl(n), hv(n);
@@ -846,6 +884,7 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
     CU(cudaSetDevice(h->device));
     int rc;
     if ((rc = sync_counters(h))) return rc;
+    h->dv_pending = false; // the uploaded state replaces everything, including a correction not yet applied
     if (n > h->capacity) {
         h->host_count = 0;
         if ((rc = grow(h, (int)std::min<long long>(2147483000ll, (long long)(1.25 * n) + 4096)))) return rc;
@@ -1039,6 +1078,10 @@ int pfem2_project_accumulate(pfem2_handle *h, double *d_acc3)
     if (!h || !d_acc3) return PFEM2_EINVAL;
     if (!h->seeded) return fail(h, PFEM2_ESTATE, "project before seed");
     CU(cudaSetDevice(h->device));
+    {
+        const int rcf = flush_correct(h);
+        if (rcf) return rcf;
+    }
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells, N = h->mesh.n_nodes;
     ParticleSoA p = h->soa[h->cur];

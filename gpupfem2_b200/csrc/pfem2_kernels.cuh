@@ -216,7 +216,8 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
                 const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, NodalVel vel, double h, int substeps,
                 int n_cells, int ppc, int level, double sub_step, Counters *ctr, unsigned *__restrict__ stay_bits,
                 int *__restrict__ warp_movers, int *__restrict__ stay, int *__restrict__ arrive,
-                unsigned long long *__restrict__ cell_mask, int do_count)
+                unsigned long long *__restrict__ cell_mask, int do_count, const double *__restrict__ dvx,
+                const double *__restrict__ dvy)
 {
     const double *__restrict__ Vx, *__restrict__ Vy;
     {
@@ -269,6 +270,12 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
             int4 e = __ldg(edge_nbr + c); // prefetched with the cell record so the first walk hop has no extra dependent load
             double ax0 = __ldg(Vx + g.n0), ax1 = __ldg(Vx + g.n1), ax2 = __ldg(Vx + g.n2);
             double ay0 = __ldg(Vy + g.n0), ay1 = __ldg(Vy + g.n1), ay2 = __ldg(Vy + g.n2);
+            if (dvx) { // pending velocity correction, with the cell / local position the particle had at the correct call
+                const double2 v = p.vel[i];
+                p.vel[i] = make_double2(
+                    __dadd_rn(v.x, interp3(L0, L1, L2, __ldg(dvx + g.n0), __ldg(dvx + g.n1), __ldg(dvx + g.n2))),
+                    __dadd_rn(v.y, interp3(L0, L1, L2, __ldg(dvy + g.n0), __ldg(dvy + g.n1), __ldg(dvy + g.n2))));
+            }
             const int nsub = NSUB > 0 ? NSUB : substeps;
             // kept rolled on purpose: unrolling lets stayers run ahead into the next substep's code while the movers of the
             // warp are still in the walk, which costs more issue slots than it saves (measured 14.0 vs 10.8 ms)
@@ -918,6 +925,23 @@ k_correct(ParticleSoA p, const CellGeom *__restrict__ geom, NodalVel vel, NodalV
         p.vel[i] = make_double2(__dadd_rn(vel.x, interp3(L0, L1, L2, dx0, dx1, dx2)),
                                 __dadd_rn(vel.y, interp3(L0, L1, L2, dy0, dy1, dy2)));
     }
+}
+
+// Deferred correction: correctParticleVelocity only snapshots the nodal increment
+// dV = V - Vold (N values, plain subtraction exactly as kCorrectParticleVelocity computes it per use); the particle
+// update v += sum_i L_i dV_i is folded into the next advect pass, which reads the particle anyway.  The increment
+// is evaluated with the particle's cell and local position at the time of the correct call (nothing moves between
+// the two), so the bits are those of the eager kernel.  Any reader of particle velocities flushes first.
+__global__ void __launch_bounds__(kThreads)
+k_snapshot_dv(int n_nodes, NodalVel vel, NodalVel vel_old, int has_old, double *__restrict__ dvx, double *__restrict__ dvy)
+{
+    const double *Vx, *Vy, *Ox = nullptr, *Oy = nullptr;
+    vel.resolve(Vx, Vy);
+    if (has_old) vel_old.resolve(Ox, Oy);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    dvx[i] = has_old ? __dsub_rn(Vx[i], Ox[i]) : Vx[i];
+    dvy[i] = has_old ? __dsub_rn(Vy[i], Oy[i]) : Vy[i];
 }
 
 // ---------------------------------------------------------------------------------------------

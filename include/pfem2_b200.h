@@ -62,6 +62,9 @@ typedef struct pfem2_options {
                                order; 1: deterministic order (stayers keep their order, movers radix-sorted by cell) */
     int scatter_tma;        /* 1: stage the reorder scatter through shared memory with cp.async.bulk (TMA) per-warp pipelines;
                                0 (default): register-staged variant (measured faster on B200, see profiles/) */
+    int defer_correct;      /* 1 (default): correctParticleVelocity snapshots the nodal increment and the particle update is
+                               folded into the next advect pass (bit-identical; applied eagerly before any other reader);
+                               0: eager kernel */
 } pfem2_options;
 
 /* counters of the last pfem2_advect call (device-resident, read back on demand) */

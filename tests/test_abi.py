@@ -33,7 +33,7 @@ def test_default_options_and_version():
     o = _lib.Options()
     L.pfem2_default_options(ctypes.byref(o))
     assert o.struct_size == ctypes.sizeof(_lib.Options)
-    assert o.subcell_mode == 0 and o.max_division_level == 4 and o.device == -1
+    assert o.subcell_mode == 0 and o.max_division_level == 4 and o.device == -1 and o.defer_correct == 1
     assert b"sm_100a" in L.pfem2_version()
 
 

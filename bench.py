@@ -222,8 +222,16 @@ def run_ours(args):
     dom = max(ALG_BYTES, key=lambda n: phases[n][0])
     dom_ms = phases[dom][0] / args.steps
     achieved = ALG_BYTES[dom] * pmean / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/r01_traffic.json)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if args.workload == "channel16m" and dom in tj:
+            traffic = tj[dom]["bytes_per_particle"] * pmean
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "alg_bytes_per_particle": ALG_BYTES[dom],
+                "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled to this run's particle count)" if traffic else None,
+                "peak_source": peak_src, "alg_bytes_per_particle": ALG_BYTES[dom],
                 "step": {"achieved": ALG_BYTES_STEP * value / 1e9, "frac": ALG_BYTES_STEP * value / 1e9 / peak,
                          "alg_bytes_per_particle_step": ALG_BYTES_STEP},
                 "phases": per_phase}

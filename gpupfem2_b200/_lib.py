@@ -19,7 +19,7 @@ SYMBOLS = (
     "pfem2_default_options", "pfem2_last_error", "pfem2_version", "pfem2_create", "pfem2_destroy", "pfem2_seed",
     "pfem2_init_velocity", "pfem2_init_velocity_ptrs", "pfem2_advect", "pfem2_advect_ptrs", "pfem2_project",
     "pfem2_project_ptrs", "pfem2_correct", "pfem2_correct_ptrs", "pfem2_particle_count", "pfem2_get_stats",
-    "pfem2_export_aos", "pfem2_step_host", "pfem2_download", "pfem2_upload", "pfem2_device_arrays", "pfem2_cell_starts",
+    "pfem2_export_aos", "pfem2_step_host", "pfem2_download", "pfem2_upload", "pfem2_device_records", "pfem2_cell_starts",
     "pfem2_mesh_inv_jacobi", "pfem2_mesh_one_ring", "pfem2_sort_pairs", "pfem2_kernel_launches", "pfem2_set_profiling",
     "pfem2_get_phase_times", "pfem2_set_owned_cells", "pfem2_advect_move", "pfem2_emigrants_count", "pfem2_emigrants_pack",
     "pfem2_immigrants_append", "pfem2_advect_finish", "pfem2_project_accumulate", "pfem2_project_finalize",
@@ -78,7 +78,7 @@ def load():
     L.pfem2_step_host.argtypes = [vp, vp, vp, vp, vp, d, i, C.POINTER(i)]
     L.pfem2_download.argtypes = [vp] + [vp] * 9
     L.pfem2_upload.argtypes = [vp, i] + [vp] * 9
-    L.pfem2_device_arrays.argtypes = [vp] + [C.POINTER(vp)] * 4
+    L.pfem2_device_records.argtypes = [vp, C.POINTER(vp)]
     L.pfem2_cell_starts.argtypes = [vp, C.POINTER(vp)]
     L.pfem2_mesh_inv_jacobi.argtypes = [i, vp, vp, vp, vp]
     L.pfem2_mesh_one_ring.argtypes = [i, i, vp, vp, vp, C.POINTER(i), vp]

@@ -169,17 +169,16 @@ int grid_for(long long n, int threads = kThreads, int max_blocks = 0)
 
 int alloc_soa(pfem2_handle *h, ParticleSoA &s, int cap)
 {
-    int rc;
-    if ((rc = dev_alloc(h, &s.pos, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.lab, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.tail, cap))) return rc;
-    if ((rc = dev_alloc(h, &s.vel, cap))) return rc;
+    ParticleRec *r = nullptr;
+    const int rc = dev_alloc(h, &r, cap);
+    if (rc) return rc;
+    s.bind(r);
     return PFEM2_OK;
 }
 
 void free_soa(ParticleSoA &s)
 {
-    cudaFree(s.pos); cudaFree(s.lab); cudaFree(s.tail); cudaFree(s.vel);
+    cudaFree(s.records());
     s = ParticleSoA{};
 }
 
@@ -233,10 +232,7 @@ int grow(pfem2_handle *h, int new_cap)
     ParticleSoA fresh{};
     int rc;
     if ((rc = alloc_soa(h, fresh, new_cap))) return rc;
-    auto cp = [&](auto *dst, const auto *src) {
-        return cudaMemcpyAsync(dst, src, (size_t)n * sizeof(*dst), cudaMemcpyDeviceToDevice, h->stream);
-    };
-    CU(cp(fresh.pos, old.pos)); CU(cp(fresh.lab, old.lab)); CU(cp(fresh.tail, old.tail)); CU(cp(fresh.vel, old.vel));
+    if (n) CU(cudaMemcpyAsync(fresh.records(), old.records(), (size_t)n * sizeof(ParticleRec), cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     free_soa(old);
     h->soa[h->cur] = fresh;
@@ -854,25 +850,19 @@ int pfem2_download(pfem2_handle *h, double *x, double *y, double *l0, double *l1
     if ((rc = flush_correct(h))) return rc;
     const size_t n = (size_t)h->host_count;
     const ParticleSoA &p = h->soa[h->cur];
-    std::vector<double2> hp(n), hl(n), hv(n);
-    std::vector<ParticleTail> ht(n);
-    if (n) {
-        CU(cudaMemcpyAsync(hp.data(), p.pos, n * 16, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaMemcpyAsync(hl.data(), p.lab, n * 16, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaMemcpyAsync(ht.data(), p.tail, n * 16, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaMemcpyAsync(hv.data(), p.vel, n * 16, cudaMemcpyDeviceToHost, h->stream));
-    }
+    std::vector<ParticleRec> hr(n);
+    if (n) CU(cudaMemcpyAsync(hr.data(), p.records(), n * sizeof(ParticleRec), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     for (size_t i = 0; i < n; ++i) {
-        if (x) x[i] = hp[i].x;
-        if (y) y[i] = hp[i].y;
-        if (l0) l0[i] = hl[i].x;
-        if (l1) l1[i] = hl[i].y;
-        if (l2) l2[i] = ht[i].l2;
-        if (vx) vx[i] = hv[i].x;
-        if (vy) vy[i] = hv[i].y;
-        if (cell) cell[i] = ht[i].cell;
-        if (id) id[i] = ht[i].id;
+        if (x) x[i] = hr[i].pos.x;
+        if (y) y[i] = hr[i].pos.y;
+        if (l0) l0[i] = hr[i].lab.x;
+        if (l1) l1[i] = hr[i].lab.y;
+        if (l2) l2[i] = hr[i].tail.l2;
+        if (vx) vx[i] = hr[i].vel.x;
+        if (vy) vy[i] = hr[i].vel.y;
+        if (cell) cell[i] = hr[i].tail.cell;
+        if (id) id[i] = hr[i].tail.id;
     }
     return PFEM2_OK;
 }
@@ -893,23 +883,17 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
     const int C = h->mesh.n_cells;
     ParticleSoA &p = h->soa[h->cur];
     {
-        std::vector<double2> hp(n), hl(n), hv(n);
-        std::vector<ParticleTail> ht(n);
+        std::vector<ParticleRec> hr(n);
         for (int i = 0; i < n; ++i) {
             if (cell[i] >= (unsigned)C) return fail(h, PFEM2_EINVAL, "upload: cell index out of range");
-            hp[i] = make_double2(x[i], y[i]);
-            hl[i] = make_double2(l0[i], l1[i]);
-            hv[i] = make_double2(vx[i], vy[i]);
-            ht[i].l2 = l2[i];
-            ht[i].cell = cell[i];
-            ht[i].id = id ? id[i] : 0u;
+            hr[i].pos = make_double2(x[i], y[i]);
+            hr[i].lab = make_double2(l0[i], l1[i]);
+            hr[i].vel = make_double2(vx[i], vy[i]);
+            hr[i].tail.l2 = l2[i];
+            hr[i].tail.cell = cell[i];
+            hr[i].tail.id = id ? id[i] : 0u;
         }
-        if (n) {
-            CU(cudaMemcpyAsync(p.pos, hp.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(p.lab, hl.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(p.tail, ht.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(p.vel, hv.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
-        }
+        if (n) CU(cudaMemcpyAsync(p.records(), hr.data(), (size_t)n * sizeof(ParticleRec), cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));
     }
     PFEM2_LAUNCH(k_set_counters, 1, 1, 0, st, h->ctr, n, h->capacity);
@@ -927,14 +911,10 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
     return sync_counters(h);
 }
 
-int pfem2_device_arrays(pfem2_handle *h, const double **d_pos, const double **d_lab, const void **d_tail, const double **d_vel)
+int pfem2_device_records(pfem2_handle *h, const void **d_records)
 {
-    if (!h) return PFEM2_EINVAL;
-    const ParticleSoA &p = h->soa[h->cur];
-    if (d_pos) *d_pos = (const double *)p.pos;
-    if (d_lab) *d_lab = (const double *)p.lab;
-    if (d_tail) *d_tail = p.tail;
-    if (d_vel) *d_vel = (const double *)p.vel;
+    if (!h || !d_records) return PFEM2_EINVAL;
+    *d_records = h->soa[h->cur].records();
     return PFEM2_OK;
 }
 

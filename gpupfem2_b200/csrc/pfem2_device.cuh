@@ -26,24 +26,51 @@ struct __align__(16) CellGeom {
 };
 static_assert(sizeof(CellGeom) == 64, "CellGeom must be one 64-byte record");
 
-// Structure-of-arrays particle storage: four arrays of 16-byte records (64 B of state per particle), so every
-// access -- streaming or scattered -- is one 128-bit load / store and a warp touches whole 32-byte sectors.
-//   pos  = Particle2D::position            (x, y)
-//   lab  = Particle2D::localPosition.x, .y (first two barycentrics)
-//   tail = localPosition.z, cellID, ID
-//   vel  = Particle2D::velocity            (vx, vy)
+// Particle storage: ONE array of 64-byte records (exactly two 32-byte DRAM sectors, 64-byte aligned), each made of
+// four 16-byte fields, so every access is a 128-bit load / store:
+//   +0  pos  = Particle2D::position            (x, y)
+//   +16 lab  = Particle2D::localPosition.x, .y (first two barycentrics)
+//   +32 tail = localPosition.z, cellID, ID
+//   +48 vel  = Particle2D::velocity            (vx, vy)
+// Why records and not four field arrays: the per-step re-sort scatters particles in short runs (3-4 records); with
+// whole-sector records every store completes its sectors, which measured 3x the scatter bandwidth of the field-array
+// layout on B200 (profiles/r01_scatter_pattern_microbench.md).  The kernels address the fields through strided views,
+// so `p.pos[i]`, `p.tail + i` read like a structure of arrays.
 struct __align__(16) ParticleTail {
     double l2;
     unsigned cell;
     unsigned id;
 };
-static_assert(sizeof(ParticleTail) == 16, "ParticleTail must be a 16-byte record");
+static_assert(sizeof(ParticleTail) == 16, "ParticleTail must be a 16-byte field");
+
+struct __align__(64) ParticleRec {
+    double2 pos;
+    double2 lab;
+    ParticleTail tail;
+    double2 vel;
+};
+static_assert(sizeof(ParticleRec) == 64, "a particle is one 64-byte record");
+
+template <class T> struct FieldView { // field of record i at base + 64 i
+    char *base;
+    __host__ __device__ __forceinline__ T &operator[](long long i) const { return *reinterpret_cast<T *>(base + i * (long long)sizeof(ParticleRec)); }
+    __host__ __device__ __forceinline__ T *operator+(long long i) const { return reinterpret_cast<T *>(base + i * (long long)sizeof(ParticleRec)); }
+};
 
 struct ParticleSoA {
-    double2 *pos;
-    double2 *lab;
-    ParticleTail *tail;
-    double2 *vel;
+    FieldView<double2> pos;
+    FieldView<double2> lab;
+    FieldView<ParticleTail> tail;
+    FieldView<double2> vel;
+    __host__ __device__ ParticleRec *records() const { return reinterpret_cast<ParticleRec *>(pos.base); }
+    __host__ void bind(ParticleRec *r)
+    {
+        char *b = reinterpret_cast<char *>(r);
+        pos.base = b;
+        lab.base = b + 16;
+        tail.base = b + 32;
+        vel.base = b + 48;
+    }
 };
 
 __device__ __forceinline__ ParticleTail ld_tail(const ParticleTail *p)

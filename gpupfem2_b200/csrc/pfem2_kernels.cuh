@@ -1,7 +1,7 @@
 // pfem2_kernels.cuh -- the particle-step kernels (sm_100a).
 //
-// Data layout in HBM: particles are four SoA arrays of 16-byte records (64 B of state per
-// particle), kept PHYSICALLY SORTED BY OWNING CELL after every advect, so cell c owns the contiguous segment
+// Data layout in HBM: particles are one array of 64-byte records (four 16-byte fields, accessed
+// through strided field views), kept PHYSICALLY SORTED BY OWNING CELL after every advect, so cell c owns the segment
 // [cell_start[c], cell_start[c+1]).  Mesh data the path reads is repacked once into one 64-byte
 // CellGeom record per cell.  All particle counts live in device memory (Counters); kernels are
 // grid-stride and read the live count themselves, so a step issues no device->host copy.
@@ -512,12 +512,9 @@ k_scatter_all_regs(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_o
     }
 }
 
-// One warp-tile of 32 particles staged in shared memory by the copy engine (4 bulk copies of 512 B).
+// One warp-tile of 32 particle records staged in shared memory by the copy engine (one bulk copy of 2 KB).
 struct __align__(128) ScatterStage {
-    double2 pos[32];
-    double2 lab[32];
-    int4 tail[32];
-    double2 vel[32];
+    int4 rec[32][4]; // 32 whole particle records: [.][0] pos, [1] lab, [2] tail, [3] vel
 };
 static_assert(sizeof(ScatterStage) == 2048, "one scatter stage is 2 KB");
 
@@ -548,12 +545,9 @@ k_scatter_all_tma(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_ol
     auto issue = [&](int tile, int k) {
         if (lane == 0) {
             const int base = tile << 5;
-            const uint32_t bytes = (uint32_t)min(32, n - base) * 16u;
-            mbar_arrive_expect_tx(bars + k, 4u * bytes);
-            bulk_g2s(stage[k].pos, src.pos + base, bytes, bars + k);
-            bulk_g2s(stage[k].lab, src.lab + base, bytes, bars + k);
-            bulk_g2s(stage[k].tail, src.tail + base, bytes, bars + k);
-            bulk_g2s(stage[k].vel, src.vel + base, bytes, bars + k);
+            const uint32_t bytes = (uint32_t)min(32, n - base) * (uint32_t)sizeof(ParticleRec);
+            mbar_arrive_expect_tx(bars + k, bytes);
+            bulk_g2s(stage[k].rec, src.records() + base, bytes, bars + k);
         }
     };
 #pragma unroll
@@ -570,7 +564,7 @@ k_scatter_all_tma(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_ol
         }
         mbar_wait(bars + k, (uint32_t)((it / S) & 1));
         const int i = (tile << 5) + lane;
-        const unsigned c = i < n ? (unsigned)stage[k].tail[lane].z : kLostCell;
+        const unsigned c = i < n ? (unsigned)stage[k].rec[lane][2].z : kLostCell;
         // cursor[c] starts at the new segment start of cell c: one atomicAdd per (warp, cell) group reserves a run
         const unsigned peers = __match_any_sync(0xffffffffu, c);
         int run = 0;
@@ -578,10 +572,11 @@ k_scatter_all_tma(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_ol
         run = __shfl_sync(0xffffffffu, run, __ffs(peers) - 1);
         if (c != kLostCell) {
             const int d = run + __popc(peers & ((1u << lane) - 1));
-            dst.pos[d] = stage[k].pos[lane];
-            dst.lab[d] = stage[k].lab[lane];
-            *reinterpret_cast<int4 *>(dst.tail + d) = stage[k].tail[lane];
-            dst.vel[d] = stage[k].vel[lane];
+            int4 *out = reinterpret_cast<int4 *>(dst.records() + d);
+            out[0] = stage[k].rec[lane][0];
+            out[1] = stage[k].rec[lane][1];
+            out[2] = stage[k].rec[lane][2];
+            out[3] = stage[k].rec[lane][3];
         }
         __syncwarp(); // every lane has read stage k before it is refilled
     }

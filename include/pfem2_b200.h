@@ -124,10 +124,10 @@ int pfem2_download(pfem2_handle *h, double *h_x, double *h_y, double *h_l0, doub
                    double *h_vx, double *h_vy, unsigned *h_cell, unsigned *h_id);
 int pfem2_upload(pfem2_handle *h, int n, const double *h_x, const double *h_y, const double *h_l0, const double *h_l1,
                  const double *h_l2, const double *h_vx, const double *h_vy, const unsigned *h_cell, const unsigned *h_id);
-/* device pointers to the live particle arrays, four arrays of 16-byte records (valid until the next mutating call):
- *   pos  double2 (x, y) ; lab double2 (first two barycentrics) ; tail { double l2; unsigned cell; unsigned id; } ;
- *   vel  double2 (vx, vy) */
-int pfem2_device_arrays(pfem2_handle *h, const double **d_pos, const double **d_lab, const void **d_tail, const double **d_vel);
+/* device pointer to the live particle array: 64-byte records
+ *   { double x, y; double L0, L1; double L2; unsigned cell; unsigned id; double vx, vy; }
+ * sorted by cell after every advect (valid until the next mutating call) */
+int pfem2_device_records(pfem2_handle *h, const void **d_records);
 /* per-cell segment table of the sorted storage: particles of cell c are [start[c], start[c+1]) */
 int pfem2_cell_starts(pfem2_handle *h, const int **d_cell_start);
 
@@ -136,7 +136,7 @@ int pfem2_cell_starts(pfem2_handle *h, const int **d_cell_start);
  * [cell_lo, cell_hi) and the particles inside them.  A step is
  *     advect_move ; emigrants_count ; emigrants_pack ; <exchange records over NCCL> ; immigrants_append ; advect_finish ;
  *     project_accumulate ; <sum interface-node accumulators over NCCL> ; project_finalize ; correct
- * Records are 64 bytes: {x, y | L0, L1 | L2, cell, id | vx, vy}. ---- */
+ * Records are the library's 64-byte particle records: {x, y | L0, L1 | L2, cell, id | vx, vy}. ---- */
 int pfem2_set_owned_cells(pfem2_handle *h, int cell_lo, int cell_hi); /* before pfem2_seed; seeds / re-seeds only these cells */
 int pfem2_advect_move(pfem2_handle *h, const double *d_vx, const double *d_vy, double dt, int substeps);
 /* per destination rank (cells [h_bounds[r], h_bounds[r+1])) the number of live particles that left the owned range */

@@ -174,7 +174,8 @@ def run_ours(args):
     t_setup = time.time()
     dm, level, F, dt = build_problem(args, rank, world, device)
     W = (torch.zeros_like(F[0]), torch.zeros_like(F[0]))
-    h = handler.ParticleHandler2D(dm, level, max_division_level=8, capacity_factor=args.capacity_factor)
+    h = handler.ParticleHandler2D(dm, level, max_division_level=8, capacity_factor=args.capacity_factor,
+                                  scatter_tma=bool(int(os.environ.get("PFEM2_SCATTER_TMA", "0"))))
     h.seed_particles()
     h.init_particle_velocity(F)
     torch.cuda.synchronize()

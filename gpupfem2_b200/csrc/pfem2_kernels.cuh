@@ -229,32 +229,19 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
     const int n = ctr->count;
     const int lane = threadIdx.x & 31;
     int my_movers = 0, my_lost = 0;
-    // Software pipeline over the grid-stride loop: while a particle is processed, the next one of this thread
-    // (pos, lab, tail = 48 B) is already on its way into the thread's private shared-memory slot via cp.async
-    // (LDGSTS: no registers held, no barrier needed since a thread only reads what it copied itself).
-    __shared__ int4 pre[2][3][kThreads];
+    // Particle records are streamed with cache-streaming (evict-first) 128-bit loads / stores so that they do not push
+    // the re-used cell records and nodal velocities out of L1.
     const int stride = gridDim.x * blockDim.x;
-    auto prefetch = [&](int i, int st) {
-        if (i < n) {
-            cp_async16(&pre[st][0][threadIdx.x], p.pos + i);
-            cp_async16(&pre[st][1][threadIdx.x], p.lab + i);
-            cp_async16(&pre[st][2][threadIdx.x], p.tail + i);
-        }
-        cp_async_commit();
-    };
-    int it = 0;
-    prefetch((blockIdx.x * blockDim.x + threadIdx.x), 0);
     // warp-uniform loop (the aggregation below uses full-mask warp intrinsics); base is a multiple of 32
-    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += stride, ++it) {
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += stride) {
         const int i = base + lane;
         const bool valid = i < n;
-        prefetch(i + stride, (it + 1) & 1);
-        cp_async_wait_all_but_one();
         unsigned c0 = 0, c = 0;
         double x = 0, y = 0, L0 = 0, L1 = 0, L2 = 0;
         bool lost = false;
         if (valid) {
-            const int4 r0 = pre[it & 1][0][threadIdx.x], r1 = pre[it & 1][1][threadIdx.x], r2 = pre[it & 1][2][threadIdx.x];
+            int4 *rec = reinterpret_cast<int4 *>(p.records() + i);
+            const int4 r0 = __ldcs(rec), r1 = __ldcs(rec + 1), r2 = __ldcs(rec + 2);
             ParticleTail tl;
             tl.l2 = __hiloint2double(r2.y, r2.x);
             tl.cell = (unsigned)r2.z;
@@ -271,10 +258,12 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
             double ax0 = __ldg(Vx + g.n0), ax1 = __ldg(Vx + g.n1), ax2 = __ldg(Vx + g.n2);
             double ay0 = __ldg(Vy + g.n0), ay1 = __ldg(Vy + g.n1), ay2 = __ldg(Vy + g.n2);
             if (dvx) { // pending velocity correction, with the cell / local position the particle had at the correct call
-                const double2 v = p.vel[i];
-                p.vel[i] = make_double2(
-                    __dadd_rn(v.x, interp3(L0, L1, L2, __ldg(dvx + g.n0), __ldg(dvx + g.n1), __ldg(dvx + g.n2))),
-                    __dadd_rn(v.y, interp3(L0, L1, L2, __ldg(dvy + g.n0), __ldg(dvy + g.n1), __ldg(dvy + g.n2))));
+                const int4 r3 = __ldcs(rec + 3);
+                const double vx = __dadd_rn(__hiloint2double(r3.y, r3.x),
+                                            interp3(L0, L1, L2, __ldg(dvx + g.n0), __ldg(dvx + g.n1), __ldg(dvx + g.n2)));
+                const double vy = __dadd_rn(__hiloint2double(r3.w, r3.z),
+                                            interp3(L0, L1, L2, __ldg(dvy + g.n0), __ldg(dvy + g.n1), __ldg(dvy + g.n2)));
+                __stcs(rec + 3, make_int4(__double2loint(vx), __double2hiint(vx), __double2loint(vy), __double2hiint(vy)));
             }
             const int nsub = NSUB > 0 ? NSUB : substeps;
             // kept rolled on purpose: unrolling lets stayers run ahead into the next substep's code while the movers of the
@@ -303,13 +292,13 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
                     ay0 = __ldg(Vy + g.n0); ay1 = __ldg(Vy + g.n1); ay2 = __ldg(Vy + g.n2);
                 }
             }
-            p.pos[i] = make_double2(x, y);
+            __stcs(rec, make_int4(__double2loint(x), __double2hiint(x), __double2loint(y), __double2hiint(y)));
             if (lost) {
                 st_cell(p.tail + i, kLostCell);
                 ++my_lost;
             } else {
-                p.lab[i] = make_double2(L0, L1);
-                st_tail(p.tail + i, L2, c, tl.id);
+                __stcs(rec + 1, make_int4(__double2loint(L0), __double2hiint(L0), __double2loint(L1), __double2hiint(L1)));
+                __stcs(rec + 2, make_int4(__double2loint(L2), __double2hiint(L2), (int)c, (int)tl.id));
             }
         }
         const bool live = valid && !lost;

@@ -8,6 +8,7 @@
  *
  * It does two things:
  *   ref_harness dump  <case.bin> <out_prefix>     run a case file and dump particle + nodal state
+ *   ref_harness timecase <case.bin> <steps> <warmup>   time the particle step on a case file (shipped meshes)
  *   ref_harness time  <nx> <ny> <lx> <ly> <level> <substeps> <dt> <umax> <steps> <warmup> [colmajor]
  *                                                  time the particle step on a synthetic channel
  *
@@ -203,6 +204,73 @@ static int run_dump(const char *case_path, const char *out_prefix)
     return 0;
 }
 
+/* time a case file (small shipped meshes): same protocol as run_dump, no dumps, CUDA-event + wall timing */
+static int run_timecase(const char *case_path, int steps, int warmup)
+{
+    FILE *f = fopen(case_path, "rb");
+    if (!f) { fprintf(stderr, "cannot open %s\n", case_path); return 2; }
+    int64_t hdr[8];
+    rd(f, hdr, 8);
+    if (hdr[0] != 0x50464d32) { fprintf(stderr, "bad magic\n"); return 2; }
+    const int N = (int)hdr[1], C = (int)hdr[2], nnz = (int)hdr[3], level = (int)hdr[4], S = (int)hdr[5], ndump = (int)hdr[7];
+    double dt;
+    rd(f, &dt, 1);
+    std::vector<int64_t> dumps(ndump);
+    rd(f, dumps.data(), ndump);
+    std::vector<Point2> verts(N);
+    std::vector<uint3> cells(C);
+    std::vector<int> off(C + 1), idx(nnz);
+    std::vector<double> fx(N), fy(N);
+    rd(f, (double *)verts.data(), 2 * (size_t)N);
+    rd(f, (unsigned *)cells.data(), 3 * (size_t)C);
+    rd(f, off.data(), C + 1);
+    rd(f, idx.data(), nnz);
+    rd(f, fx.data(), N);
+    rd(f, fy.data(), N);
+    fclose(f);
+    Mesh2D mesh;
+    inject_mesh(mesh, verts, cells, off, idx);
+    NodalField F, W;
+    F.init(N, fx.data(), fy.data());
+    W.init(N, nullptr, nullptr);
+    fflush(stdout);
+    FILE *real_out = fdopen(dup(fileno(stdout)), "w");
+    if (!freopen("/dev/null", "w", stdout)) return 2;
+    ParticleHandler2D ph(&mesh, level);
+    ph.seedParticles();
+    ph.initParticleVelocity(F.ptrs);
+    for (int s = 0; s < warmup; ++s) {
+        ph.advectParticles(F.ptrs, dt, S);
+        ph.projectVelocityOntoGrid(W.ptrs);
+        ph.correctParticleVelocity(F.ptrs, W.ptrs);
+    }
+    checkCudaErrors(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    long long psteps = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaEventRecord(e0);
+    for (int s = 0; s < steps; ++s) {
+        ph.advectParticles(F.ptrs, dt, S);
+        psteps += ph.getParticleCount();
+        ph.projectVelocityOntoGrid(W.ptrs);
+        ph.correctParticleVelocity(F.ptrs, W.ptrs);
+    }
+    cudaEventRecord(e1);
+    checkCudaErrors(cudaDeviceSynchronize());
+    const auto t1 = std::chrono::steady_clock::now();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(real_out,
+            "{\"impl\": \"reference-cuda\", \"cells\": %d, \"nodes\": %d, \"particles\": %d, \"steps\": %d, "
+            "\"ms_per_step\": %.6f, \"wall_ms_per_step\": %.6f, \"particle_steps_per_s\": %.6e}\n",
+            C, N, ph.getParticleCount(), steps, ms / steps, std::chrono::duration<double, std::milli>(t1 - t0).count() / steps,
+            psteps / (ms * 1e-3));
+    fflush(real_out);
+    return 0;
+}
+
 /* synthetic structured channel (same generator as gpupfem2_b200/mesh.py: structured_channel) */
 static void channel(int nx, int ny, double lx, double ly, bool colmajor, std::vector<Point2> &verts, std::vector<uint3> &cells)
 {
@@ -291,6 +359,7 @@ int main(int argc, char **argv)
 {
     if (argc >= 4 && !strcmp(argv[1], "dump")) return run_dump(argv[2], argv[3]);
     if (argc >= 2 && !strcmp(argv[1], "time")) return run_time(argc, argv);
+    if (argc >= 5 && !strcmp(argv[1], "timecase")) return run_timecase(argv[2], atoi(argv[3]), atoi(argv[4]));
     fprintf(stderr, "usage: ref_harness dump <case.bin> <out_prefix> | time ...\n");
     return 2;
 }

@@ -386,21 +386,20 @@ int orc_move(orc_handle *h, const double *vx, const double *vy, double dt, int s
         if (s < 16) h->lost[s] = lost;
         if (lost) {
             // kDeleteParticles :164-171 -- set semantics; survivors keep their order here
-            size_t w = 0;
-            for (size_t p = 0; p < (size_t)n; ++p) {
-                if (h->cell[p] == LOST) continue;
-                if (w != p) {
-                    h->x[w] = h->x[p]; h->y[w] = h->y[p];
-                    h->l0[w] = h->l0[p]; h->l1[w] = h->l1[p]; h->l2[w] = h->l2[p];
-                    h->vx[w] = h->vx[p]; h->vy[w] = h->vy[p];
-                    h->cell[w] = h->cell[p]; h->id[w] = h->id[p];
-                }
-                ++w;
+            // (holes are filled with live particles taken from the tail: O(lost) moves, order unspecified like the reference)
+            const size_t keep = (size_t)n - (size_t)lost;
+            size_t t = (size_t)n; // one past the candidate tail element
+            for (size_t hole = 0; hole < keep; ++hole) {
+                if (h->cell[hole] != LOST) continue;
+                do { --t; } while (h->cell[t] == LOST);
+                h->x[hole] = h->x[t]; h->y[hole] = h->y[t];
+                h->l0[hole] = h->l0[t]; h->l1[hole] = h->l1[t]; h->l2[hole] = h->l2[t];
+                h->vx[hole] = h->vx[t]; h->vy[hole] = h->vy[t];
+                h->cell[hole] = h->cell[t]; h->id[hole] = h->id[t];
             }
-            resize_all(h, w);
+            resize_all(h, keep);
         }
     }
-
     return h->count();
 }
 
@@ -423,28 +422,43 @@ static int check_distribution(orc_handle *h, const double *vx, const double *vy,
     const long long hist_size = (long long)C * ppc;
     h->hist.assign((size_t)hist_size, 0);
     const int n = h->count();
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < n; ++p) { // kCountParticlesInSubcells :173-181
         const int sub = h->mode == 0 ? subcell(h->l0[p], h->l1[p], h->l2[p], h->level, h->step)
                                      : subcell_clamped(h->l0[p], h->l1[p], h->l2[p], h->level, h->step);
         // reference: unchecked flat index (unsigned arithmetic); out-of-range writes hit no counter
         const long long k = (long long)(unsigned)(h->cell[p] * (unsigned)ppc + (unsigned)sub);
-        if (k < hist_size) ++h->hist[(size_t)k];
+        if (k < hist_size) {
+#pragma omp atomic
+            ++h->hist[(size_t)k];
+        }
     }
-    int added = 0;
-    for (int c = own_lo; c < own_hi; ++c) { // kCountParticlesToBeAdded :183-195 ; kAddParticlesToCell :197-236
+    // kCountParticlesToBeAdded :183-195 ; kAddParticlesToCell :197-236 -- new particles are appended in cell order
+    std::vector<int> add_start((size_t)(own_hi - own_lo) + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int c = own_lo; c < own_hi; ++c) {
+        int m = 0;
+        for (int s = 0; s < ppc; ++s) m += h->hist[(size_t)c * ppc + s] == 0;
+        add_start[(size_t)(c - own_lo) + 1] = m;
+    }
+    for (size_t k = 1; k < add_start.size(); ++k) add_start[k] += add_start[k - 1];
+    const int added = add_start.back();
+    const size_t old_n = (size_t)n;
+    resize_all(h, old_n + (size_t)added);
+#pragma omp parallel for schedule(static)
+    for (int c = own_lo; c < own_hi; ++c) {
         const unsigned *tri = &h->cells[3 * (size_t)c];
+        size_t w = old_n + (size_t)add_start[(size_t)(c - own_lo)];
         for (int s = 0; s < ppc; ++s) {
             if (h->hist[(size_t)c * ppc + s] != 0) continue;
             const double *L = &h->centers[3 * s];
-            double px, py;
-            to_global(h, c, L, px, py);
-            h->x.push_back(px); h->y.push_back(py);
-            h->l0.push_back(L[0]); h->l1.push_back(L[1]); h->l2.push_back(L[2]);
-            h->vx.push_back(interp(vx, tri, L[0], L[1], L[2])); // :223-227
-            h->vy.push_back(interp(vy, tri, L[0], L[1], L[2]));
-            h->cell.push_back((unsigned)c);
-            h->id.push_back((unsigned)(h->x.size() - 1));
-            ++added;
+            to_global(h, c, L, h->x[w], h->y[w]);
+            h->l0[w] = L[0]; h->l1[w] = L[1]; h->l2[w] = L[2];
+            h->vx[w] = interp(vx, tri, L[0], L[1], L[2]); // :223-227
+            h->vy[w] = interp(vy, tri, L[0], L[1], L[2]);
+            h->cell[w] = (unsigned)c;
+            h->id[w] = (unsigned)w;
+            ++w;
         }
     }
     h->added = added;

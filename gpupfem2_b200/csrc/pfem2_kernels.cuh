@@ -731,10 +731,10 @@ k_immigrant_append(ParticleSoA p, Counters *ctr, const int4 *__restrict__ in, in
     const int n = ctr->count;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
         const int4 *rec = in + 4 * (size_t)j;
-        *reinterpret_cast<int4 *>(p.pos + n + j) = rec[0];
-        *reinterpret_cast<int4 *>(p.lab + n + j) = rec[1];
-        *reinterpret_cast<int4 *>(p.tail + n + j) = rec[2];
-        *reinterpret_cast<int4 *>(p.vel + n + j) = rec[3];
+        *reinterpret_cast<int4 *>(p.pos + (n + j)) = rec[0];
+        *reinterpret_cast<int4 *>(p.lab + (n + j)) = rec[1];
+        *reinterpret_cast<int4 *>(p.tail + (n + j)) = rec[2];
+        *reinterpret_cast<int4 *>(p.vel + (n + j)) = rec[3];
     }
 }
 __global__ void k_add_count(Counters *ctr, int m)

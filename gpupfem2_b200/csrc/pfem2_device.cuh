@@ -127,11 +127,27 @@ __device__ __forceinline__ void to_local(const CellGeom &g, double px, double py
     L2 = __dsub_rn(__dsub_rn(1.0, L0), L1);
 }
 
-// GEOMETRY::isPointInsideUnitTriangle (geometry.cuh:37-46); NaN compares false everywhere -> inside
+// GEOMETRY::isPointInsideUnitTriangle (geometry.cuh:37-46); NaN compares false everywhere -> inside.
+// Written as two chains of three ordered fp64 compares on predicates (6 DSETP): the plain C++ form
+// `(L0 > hi) | (L0 < lo) | ...` is turned into max3 / min3 by the compiler, and fp64 max / min are emulated with
+// ~12 instructions each on sm_100a (45 instructions for this test in the hot loop of the advect pass).
 __device__ __forceinline__ bool inside_unit(double L0, double L1, double L2)
 {
-    const bool out = (L0 > kTolHi) | (L0 < kTolLo) | (L1 > kTolHi) | (L1 < kTolLo) | (L2 > kTolHi) | (L2 < kTolLo);
-    return !out;
+    int out;
+    asm("{\n\t"
+        ".reg .pred ph, pl;\n\t"
+        "setp.gt.f64 ph, %1, %4;\n\t"
+        "setp.lt.f64 pl, %1, %5;\n\t"
+        "setp.gt.or.f64 ph, %2, %4, ph;\n\t"
+        "setp.lt.or.f64 pl, %2, %5, pl;\n\t"
+        "setp.gt.or.f64 ph, %3, %4, ph;\n\t"
+        "setp.lt.or.f64 pl, %3, %5, pl;\n\t"
+        "or.pred ph, ph, pl;\n\t"
+        "selp.s32 %0, 1, 0, ph;\n\t"
+        "}"
+        : "=r"(out)
+        : "d"(L0), "d"(L1), "d"(L2), "d"(kTolHi), "d"(kTolLo));
+    return out == 0;
 }
 
 // determineSubcell (particle_handler_2d.cu:10-33) as compiled:

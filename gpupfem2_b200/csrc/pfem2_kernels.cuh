@@ -130,29 +130,32 @@ constexpr int kWalkHops = 3;
 template <bool WALK>
 __device__ __forceinline__ bool locate_mover(const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
                                              const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx,
-                                             CellGeom &g, int4 &e, unsigned &c, double x, double y, double a0, double a1,
-                                             double a2, double &L0, double &L1, double &L2)
+                                             CellGeom &g, int4 &e, unsigned &c, double x, double y, double &L0, double &L1,
+                                             double &L2)
 {
+    // on entry L0..L2 are the (rejected) local coordinates in cell c; on success they are those in the new cell
     if (WALK) {
         const unsigned o0 = g.n0, o1 = g.n1, o2 = g.n2; // nodes of the cell the particle started the substep in
 #pragma unroll 1
         for (int hop = 0; hop < kWalkHops; ++hop) {
-            const int nxt = (a0 <= a1 && a0 <= a2) ? e.x : ((a1 <= a2) ? e.y : e.z);
+            const int nxt = (L0 <= L1 && L0 <= L2) ? e.x : ((L1 <= L2) ? e.y : e.z);
             if (nxt < 0) break; // domain boundary: let the ordered scan decide
             // the candidate's record replaces g / e in place (every exit below either keeps it or reloads)
             g = load_geom(geom, (unsigned)nxt);
             e = __ldg(edge_nbr + nxt);
-            to_local(g, x, y, a0, a1, a2);
+            to_local(g, x, y, L0, L1, L2);
             const double m = (double)__uint_as_float(g.pad);
-            if (a0 > m && a1 > m && a2 > m) { // strictly interior: unique acceptor
-                const bool in_ring = g.n0 == o0 || g.n0 == o1 || g.n0 == o2 || g.n1 == o0 || g.n1 == o1 || g.n1 == o2 ||
-                                     g.n2 == o0 || g.n2 == o1 || g.n2 == o2;
-                if (!in_ring) return false; // acceptor outside the one-ring -> deleted
+            if (L0 > m && L1 > m && L2 > m) { // strictly interior: unique acceptor
+                // the first hop crosses an edge of the start cell (two shared vertices): always inside the one-ring
+                if (hop > 0) {
+                    const bool in_ring = g.n0 == o0 || g.n0 == o1 || g.n0 == o2 || g.n1 == o0 || g.n1 == o1 || g.n1 == o2 ||
+                                         g.n2 == o0 || g.n2 == o1 || g.n2 == o2;
+                    if (!in_ring) return false; // acceptor outside the one-ring -> deleted
+                }
                 c = (unsigned)nxt;
-                L0 = a0; L1 = a1; L2 = a2;
                 return true;
             }
-            if (inside_unit(a0, a1, a2)) break; // accepted inside the tolerance band: ties possible -> ordered scan
+            if (inside_unit(L0, L1, L2)) break; // accepted inside the tolerance band: ties possible -> ordered scan
         }
     }
     if (!ring_scan(geom, nbr_off, nbr_idx, c, x, y, L0, L1, L2)) return false;
@@ -175,10 +178,15 @@ __device__ __forceinline__ void accumulate_cell_stats(bool live, unsigned c, dou
     if (live) {
         const int sub = SUBCELL_MODE == 0 ? subcell_index(L0, L1, L2, level, sub_step) : subcell_index_clamped(L0, L1, L2, level, sub_step);
         // reference: ++hist[cellID * ppc + sub] in unsigned arithmetic, unchecked
-        const unsigned long long flat = (unsigned long long)(unsigned)(c * (unsigned)ppc + (unsigned)sub);
-        if (flat < (unsigned long long)n_cells * ppc) {
-            fc = (unsigned)(flat / (unsigned)ppc);
-            bit = 1ull << (unsigned)(flat - (unsigned long long)fc * ppc);
+        if ((unsigned)sub < (unsigned)ppc) { // the regular case: the particle's own word (no division)
+            fc = c;
+            bit = 1ull << sub;
+        } else { // tolerance band: the index spills into a neighbouring cell's word, or out of the histogram
+            const unsigned long long flat = (unsigned long long)(unsigned)(c * (unsigned)ppc + (unsigned)sub);
+            if (flat < (unsigned long long)n_cells * ppc) {
+                fc = (unsigned)(flat / (unsigned)ppc);
+                bit = 1ull << (unsigned)(flat - (unsigned long long)fc * ppc);
+            }
         }
     }
     const bool own_word = live && fc == c; // false only for the tolerance-band spill into another cell's word
@@ -228,7 +236,9 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
     }
     const int n = ctr->count;
     const int lane = threadIdx.x & 31;
-    int my_movers = 0, my_lost = 0;
+    __shared__ int s_mov, s_lost;
+    if (threadIdx.x == 0) s_mov = s_lost = 0;
+    __syncthreads();
     // Particle records are streamed with cache-streaming (evict-first) 128-bit loads / stores so that they do not push
     // the re-used cell records and nodal velocities out of L1.
     const int stride = gridDim.x * blockDim.x;
@@ -237,21 +247,19 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
         const int i = base + lane;
         const bool valid = i < n;
         unsigned c0 = 0, c = 0;
-        double x = 0, y = 0, L0 = 0, L1 = 0, L2 = 0;
+        double L0 = 0, L1 = 0, L2 = 0;
+        int moved = 0; // substeps in which the particle left its cell
         bool lost = false;
         if (valid) {
             int4 *rec = reinterpret_cast<int4 *>(p.records() + i);
             const int4 r0 = __ldcs(rec), r1 = __ldcs(rec + 1), r2 = __ldcs(rec + 2);
-            ParticleTail tl;
-            tl.l2 = __hiloint2double(r2.y, r2.x);
-            tl.cell = (unsigned)r2.z;
-            tl.id = (unsigned)r2.w;
-            c0 = c = tl.cell;
-            x = __hiloint2double(r0.y, r0.x);
-            y = __hiloint2double(r0.w, r0.z);
+            const unsigned id = (unsigned)r2.w;
+            c0 = c = (unsigned)r2.z;
+            double x = __hiloint2double(r0.y, r0.x);
+            double y = __hiloint2double(r0.w, r0.z);
             L0 = __hiloint2double(r1.y, r1.x);
             L1 = __hiloint2double(r1.w, r1.z);
-            L2 = tl.l2;
+            L2 = __hiloint2double(r2.y, r2.x);
             // cell record and its six nodal velocities stay in registers while the particle stays in the cell
             CellGeom g = load_geom(geom, c);
             int4 e = __ldg(edge_nbr + c); // prefetched with the cell record so the first walk hop has no extra dependent load
@@ -275,15 +283,12 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
                 const double uy = interp3(L0, L1, L2, ay0, ay1, ay2);
                 x = __fma_rn(ux, h, x);
                 y = __fma_rn(uy, h, y);
-                // own cell first (wins even if a neighbour would also accept)
-                double a0, a1, a2;
-                to_local(g, x, y, a0, a1, a2);
-                if (inside_unit(a0, a1, a2)) {
-                    L0 = a0; L1 = a1; L2 = a2;
-                    continue;
-                }
-                ++my_movers;
-                if (!locate_mover<WALK>(geom, edge_nbr, nbr_off, nbr_idx, g, e, c, x, y, a0, a1, a2, L0, L1, L2)) {
+                // own cell first (wins even if a neighbour would also accept); L is overwritten: every path below
+                // either replaces it again or never reads it (a lost particle stores no local position)
+                to_local(g, x, y, L0, L1, L2);
+                if (inside_unit(L0, L1, L2)) continue;
+                ++moved;
+                if (!locate_mover<WALK>(geom, edge_nbr, nbr_off, nbr_idx, g, e, c, x, y, L0, L1, L2)) {
                     lost = true;
                     break;
                 }
@@ -295,30 +300,29 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
             __stcs(rec, make_int4(__double2loint(x), __double2hiint(x), __double2loint(y), __double2hiint(y)));
             if (lost) {
                 st_cell(p.tail + i, kLostCell);
-                ++my_lost;
             } else {
                 __stcs(rec + 1, make_int4(__double2loint(L0), __double2hiint(L0), __double2loint(L1), __double2hiint(L1)));
-                __stcs(rec + 2, make_int4(__double2loint(L2), __double2hiint(L2), (int)c, (int)tl.id));
+                __stcs(rec + 2, make_int4(__double2loint(L2), __double2hiint(L2), (int)c, (int)id));
             }
         }
         const bool live = valid && !lost;
         const bool stays = live && c == c0;
         const unsigned sb = __ballot_sync(0xffffffffu, stays);
         const unsigned mb = __ballot_sync(0xffffffffu, live && !stays);
-        if (stay_bits && lane == 0) { // only the stable-order path consumes these
-            stay_bits[base >> 5] = sb;
-            warp_movers[base >> 5] = __popc(mb);
+        const unsigned lb = __ballot_sync(0xffffffffu, lost);
+        const int wm = __reduce_add_sync(0xffffffffu, moved);
+        if (lane == 0) { // the two statistics counters: one shared-memory atomic per warp and iteration
+            if (wm) atomicAdd(&s_mov, wm);
+            if (lb) atomicAdd(&s_lost, __popc(lb));
+            if (stay_bits) { // only the stable-order path consumes these
+                stay_bits[base >> 5] = sb;
+                warp_movers[base >> 5] = __popc(mb);
+            }
         }
         if (do_count)
             accumulate_cell_stats<SUBCELL_MODE, MASK64>(live, c, L0, L1, L2, sb, mb, lane, n_cells, ppc, level, sub_step, stay, arrive,
                                                         cell_mask);
     }
-    // block-level reduction of the two statistics counters
-    __shared__ int s_mov, s_lost;
-    if (threadIdx.x == 0) s_mov = s_lost = 0;
-    __syncthreads();
-    if (my_movers) atomicAdd(&s_mov, my_movers);
-    if (my_lost) atomicAdd(&s_lost, my_lost);
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_mov) atomicAdd(&ctr->movers, s_mov);

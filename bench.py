@@ -133,7 +133,7 @@ def build_problem(args, rank, world, device):
 
     if args.workload in WORKLOADS:
         nx, ny, lx, ly, level, umax, dt = channel_params(args)
-        dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device)
+        dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=not int(os.environ.get("PFEM2_BENCH_ROWMAJOR", "0")), device=device)
         y = dm.vertices[:, 1].contiguous()
         fx = (4.0 * umax * y * (ly - y) / (ly * ly)).contiguous()
         fy = torch.zeros_like(fx)

@@ -54,7 +54,12 @@ struct pfem2_handle {
     std::vector<int> mg_host_counts;
     bool move_pending = false;               // advect_move done, advect_finish outstanding
     double *dv[2] = {nullptr, nullptr};      // deferred velocity correction: nodal increment snapshot (n_nodes each)
+    double2 *dv2 = nullptr;                  // the same increment interleaved (x, y) per node, for the TMA-tiled advect pass
+    double2 *v2 = nullptr;                   // nodal velocity of the advect in flight, interleaved (packed per call)
     bool dv_pending = false;
+    CUtensorMap tmap[2];                     // [rows x 64 B] view of the two record buffers (32-row boxes, 64-byte swizzle)
+    void *tmap_base[2] = {nullptr, nullptr}; // what the maps were encoded for
+    int tmap_rows[2] = {0, 0};
     double *centers = nullptr; // 3 * ppc
     int key_bits = 1;
 
@@ -312,7 +317,11 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
             PFEM2_LAUNCH(k_scatter_all_tma<kStages>, grid_for(h->capacity, kThreads, g_num_sms * 4), kThreads, smem, st, src, dst,
                          &h->ctr->n_old, h->cursor, h->ctr);
         } else {
-            PFEM2_LAUNCH(k_scatter_all_regs, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
+            static const int quads = getenv("PFEM2_SCATTER_QUADS") ? atoi(getenv("PFEM2_SCATTER_QUADS")) : 1; // 0: one lane per record
+            if (quads)
+                PFEM2_LAUNCH(k_scatter_all_quads, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
+            else
+                PFEM2_LAUNCH(k_scatter_all_regs, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
         }
     }
     PFEM2_LAUNCH(k_reseed, grid_for(own_n + 1, kThreads, 1 << 30), kThreads, 0, st, lo, hi, h->ppc, (const double2 *)h->mesh.d_vertices,
@@ -323,17 +332,89 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
     return PFEM2_OK;
 }
 
+// Tensor map of a record buffer for the TMA-tiled advect pass.  cuTensorMapEncodeTiled is a driver entry point; it is
+// resolved through the runtime so that the library carries no link-time dependency on libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int record_tensor_map(pfem2_handle *h, int k)
+{
+    void *base = h->soa[k].records();
+    if (h->tmap_base[k] == base && h->tmap_rows[k] == h->capacity) return PFEM2_OK;
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, PFEM2_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t dims[2] = {16, (cuuint64_t)h->capacity}; // int32 elements per record, records
+    const cuuint64_t strides[1] = {sizeof(ParticleRec)};     // bytes between records
+    const cuuint32_t box[2] = {16, 32};                      // one warp tile: 32 whole records
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&h->tmap[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return fail(h, PFEM2_ECUDA, buf);
+    }
+    h->tmap_base[k] = base;
+    h->tmap_rows[k] = h->capacity;
+    return PFEM2_OK;
+}
+
+bool advect_tma_enabled()
+{
+    static const int on = getenv("PFEM2_ADVECT_TMA") ? atoi(getenv("PFEM2_ADVECT_TMA")) : 1; // 0: per-lane global loads / stores
+    return on != 0;
+}
+
 template <int MODE, bool WALK, bool MASK64>
 void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int do_count)
 {
     const int C = h->mesh.n_cells;
+    if (advect_tma_enabled()) { // default: particle tiles moved by the copy engine, nodal velocity interleaved
+        unsigned *sb = h->opt.stable_order ? h->stay_bits : nullptr;
+        const int N = h->mesh.n_nodes;
+        PFEM2_LAUNCH(k_pack_nodal, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, N, vel, h->v2);
+        const size_t smem = advect_tma_smem_bytes(kThreads);
+        const int grid = grid_for(h->capacity, kThreads, g_num_sms * 4); // persistent: 4 resident blocks per SM
+#define PFEM2_ADV_TMA(NSUB)                                                                                                          \
+    PFEM2_LAUNCH((k_advect_locate_tma<MODE, WALK, MASK64, NSUB>), grid, kThreads, smem, h->stream, h->tmap[h->cur], h->geom, h->edge_nbr,   \
+                 h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, hsub, substeps, C, h->ppc, h->level, h->sub_step, h->ctr, sb,         \
+                 h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count, h->dv_pending ? h->dv2 : nullptr)
+        if (substeps == 3)
+            PFEM2_ADV_TMA(3);
+        else
+            PFEM2_ADV_TMA(0);
+#undef PFEM2_ADV_TMA
+        return;
+    }
     unsigned *sbits = h->opt.stable_order ? h->stay_bits : nullptr; // only the stable-order path consumes the ballots
 #define PFEM2_ADV_LAUNCH(NSUB)                                                                                                     \
     PFEM2_LAUNCH((k_advect_locate<MODE, WALK, MASK64, NSUB>), grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->geom,   \
                  h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub, substeps, C, h->ppc, h->level, h->sub_step,   \
                  h->ctr, sbits, h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count, h->dv_pending ? h->dv[0] : nullptr,            \
                  h->dv_pending ? h->dv[1] : nullptr)
-    if (substeps == 3)
+    static const int tune = getenv("PFEM2_ADV_TUNE") ? atoi(getenv("PFEM2_ADV_TUNE")) : 0; // experiments only
+    if (substeps == 3 && MODE == 0 && WALK && !MASK64 && tune) {
+#define PFEM2_ADV_TUNED(T)                                                                                                          \
+    PFEM2_LAUNCH((k_advect_locate<0, true, false, 3, T>), grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->geom,   \
+                 h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub, substeps, C, h->ppc, h->level, h->sub_step,   \
+                 h->ctr, sbits, h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count, h->dv_pending ? h->dv[0] : nullptr,            \
+                 h->dv_pending ? h->dv[1] : nullptr)
+        switch (tune) {
+        case 1: PFEM2_ADV_TUNED(1); break;
+        case 2: PFEM2_ADV_TUNED(2); break;
+        case 3: PFEM2_ADV_TUNED(3); break;
+        case 4: PFEM2_ADV_TUNED(4); break;
+        default: PFEM2_ADV_TUNED(5); break;
+        }
+#undef PFEM2_ADV_TUNED
+    } else if (substeps == 3)
         PFEM2_ADV_LAUNCH(3);
     else
         PFEM2_ADV_LAUNCH(0);
@@ -370,6 +451,10 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
         CU(cudaMemsetAsync(h->cell_mask + lo, 0, sizeof(unsigned long long) * len, st));
     }
     PFEM2_LAUNCH(k_begin_advect, 1, 1, 0, st, h->ctr, h->capacity);
+    if (advect_tma_enabled()) {
+        if ((rc = record_tensor_map(h, h->cur))) return rc;
+        if (!h->v2) CU(cudaMalloc((void **)&h->v2, sizeof(double2) * (size_t)h->mesh.n_nodes));
+    }
     {
         PhaseScope ps(h, PFEM2_PHASE_ADVECT);
         const bool m64 = h->ppc > 32, walk = h->opt.exact_search == 0;
@@ -512,8 +597,10 @@ int do_correct(pfem2_handle *h, NodalVel v, NodalVel vold, bool has_old)
     const int N = h->mesh.n_nodes;
     for (double *&d : h->dv)
         if (!d) CU(cudaMalloc((void **)&d, sizeof(double) * (size_t)N));
+    if (!h->dv2) CU(cudaMalloc((void **)&h->dv2, sizeof(double2) * (size_t)N));
     PhaseScope ps(h, PFEM2_PHASE_CORRECT);
-    PFEM2_LAUNCH(k_snapshot_dv, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, N, v, vold, has_old ? 1 : 0, h->dv[0], h->dv[1]);
+    PFEM2_LAUNCH(k_snapshot_dv, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, N, v, vold, has_old ? 1 : 0, h->dv[0], h->dv[1],
+                 h->dv2);
     CU(cudaGetLastError());
     h->dv_pending = true;
     return PFEM2_OK;
@@ -714,6 +801,7 @@ int pfem2_destroy(pfem2_handle *h)
     cudaFree(h->n_cells_dev); cudaFree(h->rs_info); cudaFree(h->edge_nbr);
     cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count); cudaFree(h->own_len_dev); cudaFree(h->node_list);
     cudaFree(h->dv[0]); cudaFree(h->dv[1]);
+    cudaFree(h->dv2); cudaFree(h->v2);
     for (double *p : h->nodal) cudaFree(p);
     for (auto &r : h->phase_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);

@@ -11,6 +11,8 @@
 #include "pfem2_sort.cuh"
 #include "pfem2_tma.cuh"
 
+#include <cuda.h> // CUtensorMap (type only; the encoder is resolved at run time through cudaGetDriverEntryPoint)
+
 namespace pfem2 {
 
 constexpr int kThreads = 256;
@@ -218,8 +220,8 @@ __device__ __forceinline__ void accumulate_cell_stats(bool live, unsigned c, dou
 //   stay[c], arrive[c]  survivors that stayed in / moved into cell c,
 //   cell_mask[c]        sub-cell occupancy bits, flat unclamped index like kCountParticlesInSubcells (:173-181).
 // ---------------------------------------------------------------------------------------------
-template <int SUBCELL_MODE, bool WALK, bool MASK64, int NSUB>
-__global__ void __launch_bounds__(kThreads, 4)
+template <int SUBCELL_MODE, bool WALK, bool MASK64, int NSUB, int TUNE = 0>
+__global__ void __launch_bounds__(kThreads, (TUNE & 2) ? 3 : ((TUNE & 4) ? 5 : 4))
 k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
                 const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, NodalVel vel, double h, int substeps,
                 int n_cells, int ppc, int level, double sub_step, Counters *ctr, unsigned *__restrict__ stay_bits,
@@ -252,6 +254,13 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
         bool lost = false;
         if (valid) {
             int4 *rec = reinterpret_cast<int4 *>(p.records() + i);
+            if (TUNE & 1) { // next iteration's record -> L2
+                if (i + stride < n) {
+                    const char *nx = reinterpret_cast<const char *>(p.records() + i + stride);
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nx));
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nx + 32));
+                }
+            }
             const int4 r0 = __ldcs(rec), r1 = __ldcs(rec + 1), r2 = __ldcs(rec + 2);
             const unsigned id = (unsigned)r2.w;
             c0 = c = (unsigned)r2.z;
@@ -328,6 +337,168 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
         if (s_mov) atomicAdd(&ctr->movers, s_mov);
         if (s_lost) atomicAdd(&ctr->lost, s_lost);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// advect + locate, TMA-tiled variant (default).  Same arithmetic and the same outputs as k_advect_locate, different
+// data movement: the one-lane-per-record 128-bit global loads / stores of k_advect_locate touch 16 cache lines per warp
+// instruction (64-byte record stride), and with the gathered cell / nodal loads of the walk on top the L1 data pipe
+// -- not HBM, not instruction issue -- was the busiest unit of that kernel (l1tex__data_pipe_lsu_wavefronts 76 %,
+// profiles/r01_adv2_summary.md).  Here every warp owns two 2 KB tiles of shared memory and lets the copy engine move
+// whole 32-record tiles global <-> shared (cp.async.bulk.tensor, 64-byte swizzle so that "lane r reads record r" is
+// bank-conflict free): the LSU sees four shared loads and four shared stores per lane and iteration and nothing else
+// for the particle state; the next tile lands while the current one is computed (ping-pong, one mbarrier per tile).
+// Nodal velocities come interleaved (double2 per node: one 128-bit gather per node instead of two 64-bit ones).
+// ---------------------------------------------------------------------------------------------
+constexpr int kAdvTileBytes = 32 * (int)sizeof(ParticleRec); // one warp tile
+constexpr size_t advect_tma_smem_bytes(int threads) { return (size_t)(threads / 32) * (2 * kAdvTileBytes + 2 * sizeof(uint64_t)) + 1024; }
+
+template <int SUBCELL_MODE, bool WALK, bool MASK64, int NSUB>
+__global__ void __launch_bounds__(kThreads, 4)
+k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
+                    const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, const double2 *__restrict__ V2, double h,
+                    int substeps, int n_cells, int ppc, int level, double sub_step, Counters *ctr, unsigned *__restrict__ stay_bits,
+                    int *__restrict__ warp_movers, int *__restrict__ stay, int *__restrict__ arrive,
+                    unsigned long long *__restrict__ cell_mask, int do_count, const double2 *__restrict__ dV2)
+{
+    extern __shared__ unsigned char adv_smem_raw[];
+    __shared__ int s_mov, s_lost;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    // tiles: 1 KB aligned (the swizzle pattern is a function of the shared-memory address bits 4..8)
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(adv_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *tile0 = smem + (size_t)warp * 2 * kAdvTileBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)warps_per_block * 2 * kAdvTileBytes) + 2 * warp;
+    if (threadIdx.x == 0) s_mov = s_lost = 0;
+    if (lane == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int n = ctr->count;
+    const int tiles = (n + 31) >> 5;
+    const int warp_global = blockIdx.x * warps_per_block + warp;
+    const int warps_total = gridDim.x * warps_per_block;
+    // my record inside a tile: chunk f of row `lane` sits at lane * 64 + ((f ^ sw) << 4)
+    const int sw = (lane >> 1) & 3;
+    const int o0 = lane * 64 + ((0 ^ sw) << 4), o1 = lane * 64 + ((1 ^ sw) << 4), o2 = lane * 64 + ((2 ^ sw) << 4),
+              o3 = lane * 64 + ((3 ^ sw) << 4);
+    if (lane == 0 && warp_global < tiles) {
+        mbar_arrive_expect_tx(bars, kAdvTileBytes);
+        tma_load_tile_2d(tile0, &tmap, 0, warp_global << 5, bars);
+    }
+    int it = 0;
+    for (int tile = warp_global; tile < tiles; tile += warps_total, ++it) {
+        const int b = it & 1;
+        unsigned char *buf = tile0 + b * kAdvTileBytes;
+        // the other buffer: its store (previous iteration) must have finished reading shared memory, then the next tile
+        // is fetched into it
+        if (lane == 0) {
+            bulk_wait_group_read<0>();
+            const int nxt = tile + warps_total;
+            if (nxt < tiles) {
+                mbar_arrive_expect_tx(bars + (b ^ 1), kAdvTileBytes);
+                tma_load_tile_2d(tile0 + (b ^ 1) * kAdvTileBytes, &tmap, 0, nxt << 5, bars + (b ^ 1));
+            }
+        }
+        mbar_wait(bars + b, (uint32_t)((it >> 1) & 1));
+        const int base = tile << 5;
+        const int i = base + lane;
+        const bool valid = i < n;
+        unsigned c0 = 0, c = 0;
+        double L0 = 0, L1 = 0, L2 = 0;
+        int moved = 0; // substeps in which the particle left its cell
+        bool lost = false;
+        if (valid) {
+            const int4 r0 = *reinterpret_cast<const int4 *>(buf + o0), r1 = *reinterpret_cast<const int4 *>(buf + o1),
+                       r2 = *reinterpret_cast<const int4 *>(buf + o2);
+            c0 = c = (unsigned)r2.z;
+            double x = __hiloint2double(r0.y, r0.x);
+            double y = __hiloint2double(r0.w, r0.z);
+            L0 = __hiloint2double(r1.y, r1.x);
+            L1 = __hiloint2double(r1.w, r1.z);
+            L2 = __hiloint2double(r2.y, r2.x);
+            // cell record and its three nodal velocities stay in registers while the particle stays in the cell
+            CellGeom g = load_geom(geom, c);
+            int4 e = __ldg(edge_nbr + c); // prefetched with the cell record so the first walk hop has no extra dependent load
+            double2 a0 = __ldg(V2 + g.n0), a1 = __ldg(V2 + g.n1), a2 = __ldg(V2 + g.n2);
+            if (dV2) { // pending velocity correction, with the cell / local position the particle had at the correct call
+                const int4 r3 = *reinterpret_cast<const int4 *>(buf + o3);
+                const double2 d0 = __ldg(dV2 + g.n0), d1 = __ldg(dV2 + g.n1), d2 = __ldg(dV2 + g.n2);
+                const double vx = __dadd_rn(__hiloint2double(r3.y, r3.x), interp3(L0, L1, L2, d0.x, d1.x, d2.x));
+                const double vy = __dadd_rn(__hiloint2double(r3.w, r3.z), interp3(L0, L1, L2, d0.y, d1.y, d2.y));
+                *reinterpret_cast<int4 *>(buf + o3) = make_int4(__double2loint(vx), __double2hiint(vx), __double2loint(vy), __double2hiint(vy));
+            }
+            const int nsub = NSUB > 0 ? NSUB : substeps;
+#pragma unroll 1
+            for (int s = 0; s < nsub; ++s) {
+                // kAdvectParticles: velocity from the STORED local position and cell
+                const double ux = interp3(L0, L1, L2, a0.x, a1.x, a2.x);
+                const double uy = interp3(L0, L1, L2, a0.y, a1.y, a2.y);
+                x = __fma_rn(ux, h, x);
+                y = __fma_rn(uy, h, y);
+                // own cell first (wins even if a neighbour would also accept)
+                to_local(g, x, y, L0, L1, L2);
+                if (inside_unit(L0, L1, L2)) continue;
+                ++moved;
+                if (!locate_mover<WALK>(geom, edge_nbr, nbr_off, nbr_idx, g, e, c, x, y, L0, L1, L2)) {
+                    lost = true;
+                    break;
+                }
+                if (s + 1 < nsub) {
+                    a0 = __ldg(V2 + g.n0);
+                    a1 = __ldg(V2 + g.n1);
+                    a2 = __ldg(V2 + g.n2);
+                }
+            }
+            *reinterpret_cast<int4 *>(buf + o0) = make_int4(__double2loint(x), __double2hiint(x), __double2loint(y), __double2hiint(y));
+            if (lost) {
+                reinterpret_cast<unsigned *>(buf + o2)[2] = kLostCell;
+            } else {
+                *reinterpret_cast<int4 *>(buf + o1) = make_int4(__double2loint(L0), __double2hiint(L0), __double2loint(L1), __double2hiint(L1));
+                *reinterpret_cast<int4 *>(buf + o2) = make_int4(__double2loint(L2), __double2hiint(L2), (int)c, r2.w);
+            }
+        }
+        // hand the tile back: generic-proxy writes -> visible to the async proxy -> one lane issues the store
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_tile_2d(&tmap, 0, base, buf);
+            bulk_commit_group();
+        }
+        const bool live = valid && !lost;
+        const bool stays = live && c == c0;
+        const unsigned sb = __ballot_sync(0xffffffffu, stays);
+        const unsigned mb = __ballot_sync(0xffffffffu, live && !stays);
+        const unsigned lb = __ballot_sync(0xffffffffu, lost);
+        const int wm = __reduce_add_sync(0xffffffffu, moved);
+        if (lane == 0) {
+            if (wm) atomicAdd(&s_mov, wm);
+            if (lb) atomicAdd(&s_lost, __popc(lb));
+            if (stay_bits) {
+                stay_bits[base >> 5] = sb;
+                warp_movers[base >> 5] = __popc(mb);
+            }
+        }
+        if (do_count)
+            accumulate_cell_stats<SUBCELL_MODE, MASK64>(live, c, L0, L1, L2, sb, mb, lane, n_cells, ppc, level, sub_step, stay, arrive,
+                                                        cell_mask);
+    }
+    if (lane == 0) bulk_wait_group<0>(); // the last stores still read this block's shared memory
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_mov) atomicAdd(&ctr->movers, s_mov);
+        if (s_lost) atomicAdd(&ctr->lost, s_lost);
+    }
+}
+
+// nodal velocity, interleaved for the advect pass: V2[n] = (Vx[n], Vy[n])
+__global__ void __launch_bounds__(kThreads) k_pack_nodal(int n_nodes, NodalVel vel, double2 *__restrict__ V2)
+{
+    const double *Vx, *Vy;
+    vel.resolve(Vx, Vy);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes) V2[i] = make_double2(Vx[i], Vy[i]);
 }
 
 // movers -> (new cell, array index) pairs in array order, at the positions the scan of warp_movers assigns
@@ -501,6 +672,51 @@ k_scatter_all_regs(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_o
             dst.lab[d] = b[u];
             *reinterpret_cast<int4 *>(dst.tail + d) = t[u];
             dst.vel[d] = v[u];
+        }
+    }
+}
+
+// Quad-cooperative variant (default): FOUR lanes per record, lane (4 q + f) moves the 16-byte field f of record q of
+// the warp's 8-record group.  A warp-wide 128-bit load then covers 512 contiguous bytes (4 L1 wavefronts for 8 records)
+// and the four lanes of a quad store one whole 64-byte record (1 wavefront), where the one-lane-per-record form needs
+// 16 wavefronts per load instruction and 4 per stored record: the L1 data pipe, not HBM, bounded that form
+// (l1tex__data_pipe_lsu_wavefronts 67 % at 5.0 TB/s, profiles/r01_final_summary.md).  U groups are in flight per warp.
+__global__ void __launch_bounds__(kThreads)
+k_scatter_all_quads(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_old_ptr, int *__restrict__ cursor, const Counters *ctr)
+{
+    if (ctr->overflow) return;
+    const int n = *n_old_ptr;
+    const int lane = threadIdx.x & 31;
+    const int f = lane & 3, q = lane >> 2;
+    constexpr int U = 8; // 8-record groups per warp and iteration
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int4 *__restrict__ in = reinterpret_cast<const int4 *>(src.records());
+    int4 *__restrict__ out = reinterpret_cast<int4 *>(dst.records());
+    for (long long base = warp_global * (8 * U); base < n; base += warps_total * (8 * U)) {
+        int4 v[U];
+        unsigned c[U], peers[U];
+        int run[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long r = base + u * 8 + q;
+            v[u] = make_int4(0, 0, (int)kLostCell, 0);
+            if (r < n) v[u] = __ldcs(in + r * 4 + f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            c[u] = (unsigned)__shfl_sync(0xffffffffu, v[u].z, (lane & ~3) | 2); // the record's cell sits in field 2 (tail)
+            peers[u] = __match_any_sync(0xffffffffu, c[u]);                      // whole quads: 4 lanes per record
+            run[u] = 0;
+            if (c[u] != kLostCell && (peers[u] & ((1u << lane) - 1)) == 0) run[u] = atomicAdd(cursor + c[u], __popc(peers[u]) >> 2);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int leader = __ffs(peers[u]) - 1;
+            const int r0 = __shfl_sync(0xffffffffu, run[u], leader);
+            if (c[u] == kLostCell) continue;
+            const long long d = r0 + (__popc(peers[u] & ((1u << lane) - 1)) >> 2);
+            out[d * 4 + f] = v[u];
         }
     }
 }
@@ -921,15 +1137,19 @@ k_correct(ParticleSoA p, const CellGeom *__restrict__ geom, NodalVel vel, NodalV
 // is evaluated with the particle's cell and local position at the time of the correct call (nothing moves between
 // the two), so the bits are those of the eager kernel.  Any reader of particle velocities flushes first.
 __global__ void __launch_bounds__(kThreads)
-k_snapshot_dv(int n_nodes, NodalVel vel, NodalVel vel_old, int has_old, double *__restrict__ dvx, double *__restrict__ dvy)
+k_snapshot_dv(int n_nodes, NodalVel vel, NodalVel vel_old, int has_old, double *__restrict__ dvx, double *__restrict__ dvy,
+              double2 *__restrict__ dv2)
 {
     const double *Vx, *Vy, *Ox = nullptr, *Oy = nullptr;
     vel.resolve(Vx, Vy);
     if (has_old) vel_old.resolve(Ox, Oy);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
-    dvx[i] = has_old ? __dsub_rn(Vx[i], Ox[i]) : Vx[i];
-    dvy[i] = has_old ? __dsub_rn(Vy[i], Oy[i]) : Vy[i];
+    const double dx = has_old ? __dsub_rn(Vx[i], Ox[i]) : Vx[i];
+    const double dy = has_old ? __dsub_rn(Vy[i], Oy[i]) : Vy[i];
+    dvx[i] = dx;
+    dvy[i] = dy;
+    dv2[i] = make_double2(dx, dy); // interleaved copy for the TMA-tiled advect pass
 }
 
 // ---------------------------------------------------------------------------------------------

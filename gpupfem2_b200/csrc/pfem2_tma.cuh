@@ -53,6 +53,30 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  : "memory");
 }
 
+// ---- tensor-map (tiled) copies: a 2-D box of the particle record array <-> shared memory, with the 64-byte swizzle.
+// The record array is described as a [rows x 16 int32] tensor (one 64-byte record per row); a box of 32 rows is one
+// warp tile (2 KB).  With CU_TENSOR_MAP_SWIZZLE_64B the 16-byte chunk f of row r lands at
+//     r * 64 + ((f ^ ((r >> 1) & 3)) << 4)            (tile base 512-byte aligned)
+// so that lane r reading "its" record with four 128-bit shared loads is bank-conflict free (a linear 64-byte row
+// stride would be a 4-way conflict).  The copy engine moves the bytes: no LSU wavefronts for the global side.
+__device__ __forceinline__ void tma_load_tile_2d(void *smem_dst, const void *tmap, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_tile_2d(const void *tmap, int x, int y, const void *smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y),
+                 "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N bulk groups of this thread have finished READING their shared-memory source
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // per-thread 16-byte asynchronous copy global -> shared (LDGSTS), L2-only caching
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {

@@ -162,6 +162,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ.pop("NCCL_DEBUG", None)  # its version banner would land on stdout next to the ONE JSON line
         from gpupfem2_b200 import multi_gpu
 
         return multi_gpu.bench_main(args, rank, world, local)

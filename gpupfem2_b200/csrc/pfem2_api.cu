@@ -52,6 +52,9 @@ struct pfem2_handle {
     int *mg_rank_count = nullptr;            // device, per destination rank
     int mg_ranks = 0;
     std::vector<int> mg_host_counts;
+    std::vector<int> mg_host_bounds;         // host copy of mg_bounds (what a fused move pass used)
+    bool mg_fused = false;                   // the move pass in flight listed its emigrants and counted the per-cell statistics
+    int mg_fused_total = 0;                  // emigrants listed by that pass
     bool move_pending = false;               // advect_move done, advect_finish outstanding
     double *dv[2] = {nullptr, nullptr};      // deferred velocity correction: nodal increment snapshot (n_nodes each)
     double2 *dv2 = nullptr;                  // the same increment interleaved (x, y) per node, for the TMA-tiled advect pass
@@ -385,7 +388,8 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
 #define PFEM2_ADV_TMA(NSUB)                                                                                                          \
     PFEM2_LAUNCH((k_advect_locate_tma<MODE, WALK, MASK64, NSUB>), grid, kThreads, smem, h->stream, h->tmap[h->cur], h->geom, h->edge_nbr,   \
                  h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, hsub, substeps, C, h->ppc, h->level, h->sub_step, h->ctr, sb,         \
-                 h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count, h->dv_pending ? h->dv2 : nullptr)
+                 h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count, h->dv_pending ? h->dv2 : nullptr, h->own_lo, h->own_hi,          \
+                 h->mg_bounds, h->mg_ranks, h->mg_rank_count, h->mg_fused ? h->keys[0] : (unsigned *)nullptr)
         if (substeps == 3)
             PFEM2_ADV_TMA(3);
         else
@@ -422,7 +426,7 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
 }
 
 // first half of advectParticles: S x (advect + locate); with do_count the per-cell statistics are fused in
-int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_count)
+int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_count, bool mg_move = false)
 {
     if (!h) return PFEM2_EINVAL;
     if (!h->seeded) return fail(h, PFEM2_ESTATE, "advect before seed");
@@ -451,6 +455,14 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
         CU(cudaMemsetAsync(h->cell_mask + lo, 0, sizeof(unsigned long long) * len, st));
     }
     PFEM2_LAUNCH(k_begin_advect, 1, 1, 0, st, h->ctr, h->capacity);
+    // multi-GPU, from the second step on (the rank bounds arrive with the first emigrants_count call): the move pass lists the
+    // emigrants and counts the per-cell statistics of everybody else itself
+    h->mg_fused = mg_move && advect_tma_enabled() && !h->opt.stable_order && h->mg_ranks > 0 &&
+                  !(getenv("PFEM2_MG_FUSED") && atoi(getenv("PFEM2_MG_FUSED")) == 0);
+    if (h->mg_fused) {
+        do_count = 1;
+        CU(cudaMemsetAsync(h->mg_rank_count, 0, sizeof(int) * (h->mg_ranks + 1), st));
+    }
     if (advect_tma_enabled()) {
         if ((rc = record_tensor_map(h, h->cur))) return rc;
         if (!h->v2) CU(cudaMalloc((void **)&h->v2, sizeof(double2) * (size_t)h->mesh.n_nodes));
@@ -484,6 +496,10 @@ int advect_finish(pfem2_handle *h, NodalVel vel, int need_count)
     cudaStream_t st = h->stream;
     int rc;
     bool stable = h->opt.stable_order != 0;
+    if (need_count && h->mg_fused) {
+        need_count = 0; // the move pass and immigrants_append already counted everybody who is still here
+    }
+    h->mg_fused = false;
     if (need_count) {
         // multi-GPU: particles came and went since the move pass; count everybody (all "arrived": no stayer shortcut)
         PhaseScope ps(h, PFEM2_PHASE_REORDER);
@@ -1082,7 +1098,7 @@ int pfem2_set_owned_cells(pfem2_handle *h, int cell_lo, int cell_hi)
 
 int pfem2_advect_move(pfem2_handle *h, const double *vx, const double *vy, double dt, int substeps)
 {
-    return advect_move(h, nodal(vx, vy, nullptr), dt, substeps, 0);
+    return advect_move(h, nodal(vx, vy, nullptr), dt, substeps, 0, true);
 }
 
 int pfem2_advect_finish(pfem2_handle *h, const double *vx, const double *vy) { return advect_finish(h, nodal(vx, vy, nullptr), 1); }
@@ -1093,6 +1109,18 @@ int pfem2_emigrants_count(pfem2_handle *h, const int *h_bounds, int n_ranks, int
     if (!h->move_pending) return fail(h, PFEM2_ESTATE, "emigrants_count outside advect_move / advect_finish");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
+    if (h->mg_fused && h->mg_ranks == n_ranks && std::equal(h_bounds, h_bounds + n_ranks + 1, h->mg_host_bounds.begin())) {
+        // the move pass counted them (k_advect_locate_tma): rank_count[0..n_ranks) per destination, [n_ranks] = total
+        h->mg_host_counts.assign(n_ranks + 1, 0);
+        CU(cudaMemcpyAsync(h->mg_host_counts.data(), h->mg_rank_count, sizeof(int) * (n_ranks + 1), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        h->mg_fused_total = h->mg_host_counts[n_ranks];
+        for (int r = 0; r < n_ranks; ++r) h_counts[r] = h->mg_host_counts[r];
+        return PFEM2_OK;
+    }
+    if (h->mg_fused) { // different bounds than the move pass used: the statistics stand, the emigrants are searched the old way
+        h->mg_fused_total = -1;
+    }
     if (h->mg_ranks != n_ranks) {
         cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count);
         h->mg_bounds = h->mg_rank_count = nullptr;
@@ -1100,6 +1128,7 @@ int pfem2_emigrants_count(pfem2_handle *h, const int *h_bounds, int n_ranks, int
         CU(cudaMalloc((void **)&h->mg_rank_count, sizeof(int) * (n_ranks + 1)));
         h->mg_ranks = n_ranks;
     }
+    h->mg_host_bounds.assign(h_bounds, h_bounds + n_ranks + 1);
     CU(cudaMemcpyAsync(h->mg_bounds, h_bounds, sizeof(int) * (n_ranks + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(h->mg_rank_count, 0, sizeof(int) * (n_ranks + 1), st));
     PFEM2_LAUNCH(k_emigrant_count, grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], h->ctr, h->own_lo, h->own_hi, h->mg_bounds,
@@ -1121,6 +1150,11 @@ int pfem2_emigrants_pack(pfem2_handle *h, void *d_records, long long capacity_re
     for (int r = 0; r < h->mg_ranks; ++r) off[r + 1] = off[r] + h->mg_host_counts[r];
     if (off[h->mg_ranks] > capacity_records) return fail(h, PFEM2_ECAPACITY, "emigrant buffer too small");
     CU(cudaMemcpyAsync(h->mg_rank_count, off.data(), sizeof(int) * (h->mg_ranks + 1), cudaMemcpyHostToDevice, st)); // cursors
+    if (h->mg_fused && h->mg_fused_total >= 0) {
+        if (h->mg_fused_total > 0)
+            PFEM2_LAUNCH(k_emigrant_pack_list, grid_for(h->mg_fused_total), kThreads, 0, st, h->soa[h->cur], h->keys[0], h->mg_fused_total,
+                         h->mg_bounds, h->mg_ranks, h->mg_rank_count, (int4 *)d_records);
+    } else
     PFEM2_LAUNCH(k_emigrant_pack, grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], h->ctr, h->own_lo, h->own_hi, h->mg_bounds,
                  h->mg_ranks, h->mg_rank_count, (int4 *)d_records);
     CU(cudaStreamSynchronize(st)); // `off` is a host temporary
@@ -1135,6 +1169,16 @@ int pfem2_immigrants_append(pfem2_handle *h, const void *d_records, int n)
     CU(cudaSetDevice(h->device));
     if ((long long)h->host_count + n > h->capacity) return fail(h, PFEM2_ECAPACITY, "no room for the immigrants");
     PFEM2_LAUNCH(k_immigrant_append, grid_for(n), kThreads, 0, h->stream, h->soa[h->cur], h->ctr, (const int4 *)d_records, n);
+    if (h->mg_fused) { // the move pass counted the residents; the immigrants are counted here (no pass over everybody later)
+        const int C = h->mesh.n_cells;
+        const bool m64 = h->ppc > 32;
+#define PFEM2_CNTA(M, B)                                                                                                             \
+    PFEM2_LAUNCH((k_count_appended<M, B>), grid_for(n), kThreads, 0, h->stream, h->soa[h->cur], h->ctr, n, C, h->ppc, h->level,        \
+                 h->sub_step, h->stay, h->arrive, h->cell_mask)
+        if (h->opt.subcell_mode == 0) { if (m64) PFEM2_CNTA(0, true); else PFEM2_CNTA(0, false); }
+        else                          { if (m64) PFEM2_CNTA(1, true); else PFEM2_CNTA(1, false); }
+#undef PFEM2_CNTA
+    }
     PFEM2_LAUNCH(k_add_count, 1, 1, 0, h->stream, h->ctr, n);
     h->host_count += n;
     CU(cudaGetLastError());

@@ -339,6 +339,14 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
     }
 }
 
+// destination rank of a cell: bounds[r] <= cell < bounds[r + 1]   (n_ranks <= 64)
+__device__ __forceinline__ int rank_of_cell(unsigned c, const int *__restrict__ bounds, int n_ranks)
+{
+    int r = 0;
+    while (r + 1 < n_ranks && (int)c >= bounds[r + 1]) ++r;
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // advect + locate, TMA-tiled variant (default).  Same arithmetic and the same outputs as k_advect_locate, different
 // data movement: the one-lane-per-record 128-bit global loads / stores of k_advect_locate touch 16 cache lines per warp
@@ -359,8 +367,13 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
                     const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, const double2 *__restrict__ V2, double h,
                     int substeps, int n_cells, int ppc, int level, double sub_step, Counters *ctr, unsigned *__restrict__ stay_bits,
                     int *__restrict__ warp_movers, int *__restrict__ stay, int *__restrict__ arrive,
-                    unsigned long long *__restrict__ cell_mask, int do_count, const double2 *__restrict__ dV2)
+                    unsigned long long *__restrict__ cell_mask, int do_count, const double2 *__restrict__ dV2, int own_lo, int own_hi,
+                    const int *__restrict__ rank_bounds, int n_ranks, int *__restrict__ rank_count, unsigned *__restrict__ emig_idx)
 {
+    // Multi-GPU (emig_idx != nullptr): a particle whose new cell lies outside the owned range [own_lo, own_hi) is an
+    // emigrant.  It is written back like everybody else (the pack kernel removes it), but it is kept out of the per-cell
+    // statistics, its array index is appended to emig_idx and rank_count[destination] / rank_count[n_ranks] (total) are
+    // bumped, so that neither a counting nor a search pass over the whole array is needed afterwards.
     extern __shared__ unsigned char adv_smem_raw[];
     __shared__ int s_mov, s_lost;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
@@ -466,7 +479,13 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
             tma_store_tile_2d(&tmap, 0, base, buf);
             bulk_commit_group();
         }
-        const bool live = valid && !lost;
+        bool live = valid && !lost;
+        if (emig_idx && live && ((int)c < own_lo || (int)c >= own_hi)) { // rare: a handful per tile row at a strip interface
+            const int slot = atomicAdd(rank_count + n_ranks, 1);
+            emig_idx[slot] = (unsigned)i;
+            atomicAdd(rank_count + rank_of_cell(c, rank_bounds, n_ranks), 1);
+            live = false;
+        }
         const bool stays = live && c == c0;
         const unsigned sb = __ballot_sync(0xffffffffu, stays);
         const unsigned mb = __ballot_sync(0xffffffffu, live && !stays);
@@ -887,14 +906,6 @@ k_count_all(ParticleSoA p, const Counters *ctr, int n_cells, int ppc, int level,
     }
 }
 
-// destination rank of a cell: bounds[r] <= cell < bounds[r + 1]   (n_ranks <= 64)
-__device__ __forceinline__ int rank_of_cell(unsigned c, const int *__restrict__ bounds, int n_ranks)
-{
-    int r = 0;
-    while (r + 1 < n_ranks && (int)c >= bounds[r + 1]) ++r;
-    return r;
-}
-
 // emigrants = live particles whose cell is outside [own_lo, own_hi).  Pass 1 counts them per destination rank.
 __global__ void __launch_bounds__(kThreads)
 k_emigrant_count(ParticleSoA p, const Counters *ctr, int own_lo, int own_hi, const int *__restrict__ bounds, int n_ranks,
@@ -941,6 +952,52 @@ k_emigrant_pack(ParticleSoA p, const Counters *ctr, int own_lo, int own_hi, cons
         rec[2] = *reinterpret_cast<const int4 *>(p.tail + i);
         rec[3] = *reinterpret_cast<const int4 *>(p.vel + i);
         st_cell(p.tail + i, kLostCell);
+    }
+}
+
+// Fused multi-GPU path: the move pass left the array indices of the emigrants in emig_idx (k_advect_locate_tma); pack
+// them grouped by destination rank (rank_cursor starts at the exclusive prefix of the counts) and remove them locally.
+__global__ void __launch_bounds__(kThreads)
+k_emigrant_pack_list(ParticleSoA p, const unsigned *__restrict__ emig_idx, int n_emig, const int *__restrict__ bounds, int n_ranks,
+                     int *__restrict__ rank_cursor, int4 *__restrict__ out)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_emig; j += gridDim.x * blockDim.x) {
+        const unsigned i = emig_idx[j];
+        const int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
+        const int slot = atomicAdd(rank_cursor + rank_of_cell((unsigned)t.z, bounds, n_ranks), 1);
+        int4 *rec = out + 4 * (size_t)slot;
+        rec[0] = *reinterpret_cast<const int4 *>(p.pos + i);
+        rec[1] = *reinterpret_cast<const int4 *>(p.lab + i);
+        rec[2] = t;
+        rec[3] = *reinterpret_cast<const int4 *>(p.vel + i);
+        st_cell(p.tail + i, kLostCell);
+    }
+}
+
+// per-cell statistics of the m records behind the current array end (the immigrants just appended): all "arrived"
+template <int SUBCELL_MODE, bool MASK64>
+__global__ void __launch_bounds__(kThreads)
+k_count_appended(ParticleSoA p, const Counters *ctr, int m, int n_cells, int ppc, int level, double sub_step, int *__restrict__ stay,
+                 int *__restrict__ arrive, unsigned long long *__restrict__ cell_mask)
+{
+    const int n0 = ctr->count;
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < m; base += gridDim.x * blockDim.x) {
+        const int j = base + lane;
+        bool live = false;
+        unsigned c = 0;
+        double L0 = 0, L1 = 0, L2 = 0;
+        if (j < m) {
+            const ParticleTail tl = ld_tail(p.tail + (n0 + j));
+            c = tl.cell;
+            live = c != kLostCell;
+            const double2 lab = p.lab[n0 + j];
+            L0 = lab.x;
+            L1 = lab.y;
+            L2 = tl.l2;
+        }
+        const unsigned mb = __ballot_sync(0xffffffffu, live);
+        accumulate_cell_stats<SUBCELL_MODE, MASK64>(live, c, L0, L1, L2, 0u, mb, lane, n_cells, ppc, level, sub_step, stay, arrive, cell_mask);
     }
 }
 

@@ -148,10 +148,10 @@ class DistributedParticleHandler2D:
 
     def project_velocity_onto_grid(self, vel):
         h, L = self.h, self.L
+        # no host synchronisation: the library works on the legacy default stream, which is also torch's current stream here,
+        # and torch orders the NCCL transfers against it (w.wait() makes the current stream wait for the receive)
         h._check(L.pfem2_project_accumulate(h._h, self.acc3.data_ptr()), "project_accumulate")
-        torch.cuda.synchronize(self.mesh.device)
         exchange_interface(self.acc3, self.iface, self.group)
-        torch.cuda.synchronize(self.mesh.device)
         h._check(L.pfem2_project_finalize(h._h, self.acc3.data_ptr(), vel[0].data_ptr(), vel[1].data_ptr()), "project_finalize")
 
     def correct_particle_velocity(self, vel, vel_old):

@@ -377,14 +377,15 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
     extern __shared__ unsigned char adv_smem_raw[];
     __shared__ int s_mov, s_lost;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    // tiles: 1 KB aligned (the swizzle pattern is a function of the shared-memory address bits 4..8)
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(adv_smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char *tile0 = smem + (size_t)warp * 2 * kAdvTileBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)warps_per_block * 2 * kAdvTileBytes) + 2 * warp;
+    // 32-bit shared-window addresses throughout (ld.shared / st.shared, no generic pointers).  Tiles are 1 KB aligned: the
+    // swizzle pattern is a function of the shared-memory address bits 4..8.
+    const uint32_t smem = (smem_u32(adv_smem_raw) + 1023u) & ~1023u;
+    const uint32_t tile0 = smem + (uint32_t)warp * (2 * kAdvTileBytes);
+    const uint32_t bar0 = smem + (uint32_t)warps_per_block * (2 * kAdvTileBytes) + (uint32_t)warp * 16;
     if (threadIdx.x == 0) s_mov = s_lost = 0;
     if (lane == 0) {
-        mbar_init(bars, 1);
-        mbar_init(bars + 1, 1);
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -392,29 +393,29 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
     const int tiles = (n + 31) >> 5;
     const int warp_global = blockIdx.x * warps_per_block + warp;
     const int warps_total = gridDim.x * warps_per_block;
-    // my record inside a tile: chunk f of row `lane` sits at lane * 64 + ((f ^ sw) << 4)
-    const int sw = (lane >> 1) & 3;
-    const int o0 = lane * 64 + ((0 ^ sw) << 4), o1 = lane * 64 + ((1 ^ sw) << 4), o2 = lane * 64 + ((2 ^ sw) << 4),
-              o3 = lane * 64 + ((3 ^ sw) << 4);
+    // my record inside a tile: the 16-byte field f of row `lane` sits at  lane * 64 + ((f ^ sw) << 4)  =  my0 ^ (f << 4)
+    const uint32_t my0 = (uint32_t)lane * 64 + ((((uint32_t)lane >> 1) & 3) << 4);
     if (lane == 0 && warp_global < tiles) {
-        mbar_arrive_expect_tx(bars, kAdvTileBytes);
-        tma_load_tile_2d(tile0, &tmap, 0, warp_global << 5, bars);
+        mbar_arrive_expect_tx(bar0, kAdvTileBytes);
+        tma_load_tile_2d(tile0, &tmap, 0, warp_global << 5, bar0);
     }
-    int it = 0;
-    for (int tile = warp_global; tile < tiles; tile += warps_total, ++it) {
-        const int b = it & 1;
-        unsigned char *buf = tile0 + b * kAdvTileBytes;
+    uint32_t b = 0, par = 0; // buffer of this iteration (0 / 1) and the phase parity of its mbarrier
+    for (int tile = warp_global; tile < tiles; tile += warps_total) {
+        const uint32_t buf = tile0 + b * kAdvTileBytes;
         // the other buffer: its store (previous iteration) must have finished reading shared memory, then the next tile
         // is fetched into it
         if (lane == 0) {
             bulk_wait_group_read<0>();
             const int nxt = tile + warps_total;
             if (nxt < tiles) {
-                mbar_arrive_expect_tx(bars + (b ^ 1), kAdvTileBytes);
-                tma_load_tile_2d(tile0 + (b ^ 1) * kAdvTileBytes, &tmap, 0, nxt << 5, bars + (b ^ 1));
+                mbar_arrive_expect_tx(bar0 + (b ^ 1) * 8, kAdvTileBytes);
+                tma_load_tile_2d(tile0 + (b ^ 1) * kAdvTileBytes, &tmap, 0, nxt << 5, bar0 + (b ^ 1) * 8);
             }
         }
-        mbar_wait(bars + b, (uint32_t)((it >> 1) & 1));
+        mbar_wait(bar0 + b * 8, par);
+        par ^= b; // each barrier is used every other iteration: its parity flips after the odd buffer's turn
+        b ^= 1;
+        const uint32_t sa0 = buf + my0, sa1 = sa0 ^ 16u, sa2 = sa0 ^ 32u, sa3 = sa0 ^ 48u;
         const int base = tile << 5;
         const int i = base + lane;
         const bool valid = i < n;
@@ -423,8 +424,7 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
         int moved = 0; // substeps in which the particle left its cell
         bool lost = false;
         if (valid) {
-            const int4 r0 = *reinterpret_cast<const int4 *>(buf + o0), r1 = *reinterpret_cast<const int4 *>(buf + o1),
-                       r2 = *reinterpret_cast<const int4 *>(buf + o2);
+            const int4 r0 = lds128(sa0), r1 = lds128(sa1), r2 = lds128(sa2);
             c0 = c = (unsigned)r2.z;
             double x = __hiloint2double(r0.y, r0.x);
             double y = __hiloint2double(r0.w, r0.z);
@@ -436,11 +436,11 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
             int4 e = __ldg(edge_nbr + c); // prefetched with the cell record so the first walk hop has no extra dependent load
             double2 a0 = __ldg(V2 + g.n0), a1 = __ldg(V2 + g.n1), a2 = __ldg(V2 + g.n2);
             if (dV2) { // pending velocity correction, with the cell / local position the particle had at the correct call
-                const int4 r3 = *reinterpret_cast<const int4 *>(buf + o3);
+                const int4 r3 = lds128(sa3);
                 const double2 d0 = __ldg(dV2 + g.n0), d1 = __ldg(dV2 + g.n1), d2 = __ldg(dV2 + g.n2);
                 const double vx = __dadd_rn(__hiloint2double(r3.y, r3.x), interp3(L0, L1, L2, d0.x, d1.x, d2.x));
                 const double vy = __dadd_rn(__hiloint2double(r3.w, r3.z), interp3(L0, L1, L2, d0.y, d1.y, d2.y));
-                *reinterpret_cast<int4 *>(buf + o3) = make_int4(__double2loint(vx), __double2hiint(vx), __double2loint(vy), __double2hiint(vy));
+                sts128(sa3, make_int4(__double2loint(vx), __double2hiint(vx), __double2loint(vy), __double2hiint(vy)));
             }
             const int nsub = NSUB > 0 ? NSUB : substeps;
 #pragma unroll 1
@@ -464,12 +464,12 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
                     a2 = __ldg(V2 + g.n2);
                 }
             }
-            *reinterpret_cast<int4 *>(buf + o0) = make_int4(__double2loint(x), __double2hiint(x), __double2loint(y), __double2hiint(y));
+            sts128(sa0, make_int4(__double2loint(x), __double2hiint(x), __double2loint(y), __double2hiint(y)));
             if (lost) {
-                reinterpret_cast<unsigned *>(buf + o2)[2] = kLostCell;
+                sts32(sa2 + 8, kLostCell);
             } else {
-                *reinterpret_cast<int4 *>(buf + o1) = make_int4(__double2loint(L0), __double2hiint(L0), __double2loint(L1), __double2hiint(L1));
-                *reinterpret_cast<int4 *>(buf + o2) = make_int4(__double2loint(L2), __double2hiint(L2), (int)c, r2.w);
+                sts128(sa1, make_int4(__double2loint(L0), __double2hiint(L0), __double2loint(L1), __double2hiint(L1)));
+                sts128(sa2, make_int4(__double2loint(L2), __double2hiint(L2), (int)c, r2.w));
             }
         }
         // hand the tile back: generic-proxy writes -> visible to the async proxy -> one lane issues the store

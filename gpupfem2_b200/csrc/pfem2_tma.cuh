@@ -72,6 +72,42 @@ __device__ __forceinline__ void tma_store_tile_2d(const void *tmap, int x, int y
                  "r"(smem_u32(smem_src))
                  : "memory");
 }
+// the same with 32-bit shared-window addresses (no generic pointers in the hot loop)
+__device__ __forceinline__ void tma_load_tile_2d(uint32_t smem_dst, const void *tmap, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_dst),
+                 "l"(tmap), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_tile_2d(const void *tmap, int x, int y, uint32_t smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y), "r"(smem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
+}
+// 128-bit shared-memory accesses by 32-bit shared-window address
+__device__ __forceinline__ int4 lds128(uint32_t addr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, int4 v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, unsigned v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the newest N bulk groups of this thread have finished READING their shared-memory source
 template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }

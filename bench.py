@@ -51,7 +51,22 @@ WORKLOADS = {
     # name: (nx, ny, lx, ly, default level)
     "channel16m": (4000, 2000, 20.0, 10.0, 4),
     "channel1m": (1000, 500, 10.0, 5.0, 4),
+    # BASELINE.json configs[4]: 2M triangles PER GPU (nx grows with the GPU count: weak scaling), mean flow + a lattice of
+    # Taylor-Green vortices at CFL ~0.9 per substep: multi-cell traversal (walks of 2-3 cells, jumps beyond the one-ring are
+    # deleted) and strong depletion / accumulation that keeps the re-seeding busy
+    "stress2m": (1000, 1000, 10.0, 10.0, 4),
 }
+WEAK = {"stress2m"}  # nx, lx scale with the number of GPUs
+
+
+def nodal_field(args, x, y, lx, ly, umax):
+    """Synthetic frozen nodal field of a workload from node coordinates (numpy arrays or torch tensors)."""
+    if args.workload == "stress2m":
+        import math
+        mod = __import__("torch") if hasattr(x, "device") else __import__("numpy")
+        k = 2.0 * math.pi / 0.5  # 50-cell vortices
+        return (0.5 * umax + 0.5 * umax * mod.sin(k * x) * mod.cos(k * y), -0.5 * umax * mod.cos(k * x) * mod.sin(k * y))
+    return (4.0 * umax * y * (ly - y) / (ly * ly), 0.0 * y)
 
 
 def peaks():
@@ -105,8 +120,15 @@ class ClockSampler:
         return out
 
 
-def channel_params(args):
+def channel_params(args, world=1):
     nx, ny, lx, ly, lvl = WORKLOADS[args.workload]
+    if args.workload in WEAK:
+        nx, lx = nx * world, lx * world
+    if args.workload == "stress2m":
+        if args.cfl == 0.25:
+            args.cfl = 0.9
+        if args.capacity_factor == 1.3:
+            args.capacity_factor = 3.0  # the reference only ever adds particles: this case doubles its count in ~20 steps
     level = args.level or lvl
     h = lx / nx
     umax = 1.0
@@ -114,11 +136,12 @@ def channel_params(args):
     return nx, ny, lx, ly, level, umax, dt
 
 
-def workload_description(args):
+def workload_description(args, world=1):
     if args.workload in WORKLOADS:
-        nx, ny, lx, ly, level, umax, dt = channel_params(args)
+        nx, ny, lx, ly, level, umax, dt = channel_params(args, world)
+        field = "mean flow + Taylor-Green vortex lattice (50-cell vortices)" if args.workload == "stress2m" else "Poiseuille field"
         return (f"{args.workload}: structured channel {nx}x{ny} quads = {2 * nx * ny} triangles, level {level} "
-                f"({level * level}/cell, {2 * nx * ny * level * level} particles seeded), Poiseuille field, "
+                f"({level * level}/cell, {2 * nx * ny * level * level} particles seeded), {field}, "
                 f"S={args.substeps}, CFL/substep={args.cfl}")
     return f"{args.workload}: shipped mesh (tests/golden fixture), level {args.level or 2}, S={args.substeps}, isolated mode"
 
@@ -133,11 +156,9 @@ def build_problem(args, rank, world, device):
 
     if args.workload in WORKLOADS:
         nx, ny, lx, ly, level, umax, dt = channel_params(args)
-        dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=not int(os.environ.get("PFEM2_BENCH_ROWMAJOR", "0")), device=device)
-        y = dm.vertices[:, 1].contiguous()
-        fx = (4.0 * umax * y * (ly - y) / (ly * ly)).contiguous()
-        fy = torch.zeros_like(fx)
-        return dm, level, (fx, fy), dt
+        dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device)
+        fx, fy = nodal_field(args, dm.vertices[:, 0].contiguous(), dm.vertices[:, 1].contiguous(), lx, ly, umax)
+        return dm, level, (fx.contiguous(), fy.contiguous()), dt
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     from gpupfem2_b200.mesh import HostMesh
 
@@ -176,7 +197,8 @@ def run_ours(args):
     dm, level, F, dt = build_problem(args, rank, world, device)
     W = (torch.zeros_like(F[0]), torch.zeros_like(F[0]))
     h = handler.ParticleHandler2D(dm, level, max_division_level=8, capacity_factor=args.capacity_factor,
-                                  scatter_tma=bool(int(os.environ.get("PFEM2_SCATTER_TMA", "0"))))
+                                  scatter_tma=bool(int(os.environ.get("PFEM2_SCATTER_TMA", "0"))),
+                                  lane_per_record=bool(int(os.environ.get("PFEM2_LANE_PER_RECORD", "0"))))
     h.seed_particles()
     h.init_particle_velocity(F)
     torch.cuda.synchronize()
@@ -258,7 +280,7 @@ def run_ours(args):
     out = {
         "metric": "particle-steps/sec (advect+locate+sort+project+correct)", "value": value, "unit": "particle-steps/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak" if args.workload in WEAK else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_description(args), "particles_mean": pmean, "cells": dm.n_cells, "nodes": dm.n_nodes,
                    "substeps": args.substeps, "dt": dt,
                    "l2": (f"flushed between timed iterations (512 MiB write; state {state_gb:.3f} GB could fit the 126 MB L2)"
@@ -274,14 +296,18 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def oracle_run(nx, ny, lx, ly, level, substeps, cfl, steps, warmup):
+def oracle_run(nx, ny, lx, ly, level, substeps, cfl, steps, warmup, args=None):
     """Time the C++/OpenMP oracle (test infrastructure, used here only as the reported CPU baseline)."""
     from gpupfem2_b200.mesh import poiseuille_field, structured_channel
     from oracle import oracle as orc
     import numpy as np
 
     m = orc.complete_mesh(structured_channel(nx, ny, lx, ly, colmajor=True))
-    fx, fy = poiseuille_field(m, 1.0, ly)
+    if args is not None and args.workload == "stress2m":
+        fx, fy = nodal_field(args, m.vertices[:, 0], m.vertices[:, 1], lx, ly, 1.0)
+        fx, fy = np.ascontiguousarray(fx), np.ascontiguousarray(fy)
+    else:
+        fx, fy = poiseuille_field(m, 1.0, ly)
     dt = cfl * (lx / nx) * substeps
     o = orc.OracleHandler(m, level, max_level=8)
     o.seed_particles()
@@ -302,8 +328,11 @@ def cpu_baseline(args):
     level = args.level or 4
     if args.workload in ("poiseuille", "cylinder"):
         nx, ny, lx, ly, level = 200, 100, 10.0, 5.0, 2
+    if args.workload == "stress2m":
+        nx, ny, lx, ly = 700, 700, 7.0, 7.0  # same cell size and vortex lattice, ~1M triangles
+        channel_params(args)  # sets the workload's CFL
     try:
-        v, ms, cores, cells, p = oracle_run(nx, ny, lx, ly, level, args.substeps, args.cfl, 3, 1)
+        v, ms, cores, cells, p = oracle_run(nx, ny, lx, ly, level, args.substeps, args.cfl, 3, 1, args)
     except Exception as e:  # the oracle is optional infrastructure for this leg
         return {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
     return {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port", "ms_per_step": ms,
@@ -318,7 +347,7 @@ def run_reference(args):
     base = {"metric": "particle-steps/sec (advect+locate+sort+project+correct)", "unit": "particle-steps/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_description(args)}}
-    if args.workload in WORKLOADS and os.path.exists(exe):
+    if args.workload in WORKLOADS and args.workload != "stress2m" and os.path.exists(exe):
         nx, ny, lx, ly, level, umax, dt = channel_params(args)
         level = min(level, 4)  # CONSTANTS::MAX_CELL_DIVISION_LEVEL
         cmd = [exe, "time", str(nx), str(ny), repr(lx), repr(ly), str(level), str(args.substeps), repr(dt), repr(umax),

@@ -320,8 +320,7 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
             PFEM2_LAUNCH(k_scatter_all_tma<kStages>, grid_for(h->capacity, kThreads, g_num_sms * 4), kThreads, smem, st, src, dst,
                          &h->ctr->n_old, h->cursor, h->ctr);
         } else {
-            static const int quads = getenv("PFEM2_SCATTER_QUADS") ? atoi(getenv("PFEM2_SCATTER_QUADS")) : 1; // 0: one lane per record
-            if (quads)
+            if (h->opt.lane_per_record == 0)
                 PFEM2_LAUNCH(k_scatter_all_quads, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
             else
                 PFEM2_LAUNCH(k_scatter_all_regs, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
@@ -369,17 +368,13 @@ int record_tensor_map(pfem2_handle *h, int k)
     return PFEM2_OK;
 }
 
-bool advect_tma_enabled()
-{
-    static const int on = getenv("PFEM2_ADVECT_TMA") ? atoi(getenv("PFEM2_ADVECT_TMA")) : 1; // 0: per-lane global loads / stores
-    return on != 0;
-}
+bool advect_tma_enabled(const pfem2_handle *h) { return h->opt.lane_per_record == 0; }
 
 template <int MODE, bool WALK, bool MASK64>
 void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int do_count)
 {
     const int C = h->mesh.n_cells;
-    if (advect_tma_enabled()) { // default: particle tiles moved by the copy engine, nodal velocity interleaved
+    if (advect_tma_enabled(h)) { // default: particle tiles moved by the copy engine, nodal velocity interleaved
         unsigned *sb = h->opt.stable_order ? h->stay_bits : nullptr;
         const int N = h->mesh.n_nodes;
         PFEM2_LAUNCH(k_pack_nodal, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, N, vel, h->v2);
@@ -403,22 +398,7 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
                  h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub, substeps, C, h->ppc, h->level, h->sub_step,   \
                  h->ctr, sbits, h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count, h->dv_pending ? h->dv[0] : nullptr,            \
                  h->dv_pending ? h->dv[1] : nullptr)
-    static const int tune = getenv("PFEM2_ADV_TUNE") ? atoi(getenv("PFEM2_ADV_TUNE")) : 0; // experiments only
-    if (substeps == 3 && MODE == 0 && WALK && !MASK64 && tune) {
-#define PFEM2_ADV_TUNED(T)                                                                                                          \
-    PFEM2_LAUNCH((k_advect_locate<0, true, false, 3, T>), grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->geom,   \
-                 h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub, substeps, C, h->ppc, h->level, h->sub_step,   \
-                 h->ctr, sbits, h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count, h->dv_pending ? h->dv[0] : nullptr,            \
-                 h->dv_pending ? h->dv[1] : nullptr)
-        switch (tune) {
-        case 1: PFEM2_ADV_TUNED(1); break;
-        case 2: PFEM2_ADV_TUNED(2); break;
-        case 3: PFEM2_ADV_TUNED(3); break;
-        case 4: PFEM2_ADV_TUNED(4); break;
-        default: PFEM2_ADV_TUNED(5); break;
-        }
-#undef PFEM2_ADV_TUNED
-    } else if (substeps == 3)
+    if (substeps == 3)
         PFEM2_ADV_LAUNCH(3);
     else
         PFEM2_ADV_LAUNCH(0);
@@ -457,13 +437,13 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     PFEM2_LAUNCH(k_begin_advect, 1, 1, 0, st, h->ctr, h->capacity);
     // multi-GPU, from the second step on (the rank bounds arrive with the first emigrants_count call): the move pass lists the
     // emigrants and counts the per-cell statistics of everybody else itself
-    h->mg_fused = mg_move && advect_tma_enabled() && !h->opt.stable_order && h->mg_ranks > 0 &&
-                  !(getenv("PFEM2_MG_FUSED") && atoi(getenv("PFEM2_MG_FUSED")) == 0);
+    h->mg_fused = mg_move && advect_tma_enabled(h) && !h->opt.stable_order && h->mg_ranks > 0 &&
+                  !(getenv("PFEM2_MG_FUSED") && atoi(getenv("PFEM2_MG_FUSED")) == 0); // env: A/B measurements only
     if (h->mg_fused) {
         do_count = 1;
         CU(cudaMemsetAsync(h->mg_rank_count, 0, sizeof(int) * (h->mg_ranks + 1), st));
     }
-    if (advect_tma_enabled()) {
+    if (advect_tma_enabled(h)) {
         if ((rc = record_tensor_map(h, h->cur))) return rc;
         if (!h->v2) CU(cudaMalloc((void **)&h->v2, sizeof(double2) * (size_t)h->mesh.n_nodes));
     }

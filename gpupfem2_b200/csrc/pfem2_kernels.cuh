@@ -220,8 +220,8 @@ __device__ __forceinline__ void accumulate_cell_stats(bool live, unsigned c, dou
 //   stay[c], arrive[c]  survivors that stayed in / moved into cell c,
 //   cell_mask[c]        sub-cell occupancy bits, flat unclamped index like kCountParticlesInSubcells (:173-181).
 // ---------------------------------------------------------------------------------------------
-template <int SUBCELL_MODE, bool WALK, bool MASK64, int NSUB, int TUNE = 0>
-__global__ void __launch_bounds__(kThreads, (TUNE & 2) ? 3 : ((TUNE & 4) ? 5 : 4))
+template <int SUBCELL_MODE, bool WALK, bool MASK64, int NSUB>
+__global__ void __launch_bounds__(kThreads, 4)
 k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
                 const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, NodalVel vel, double h, int substeps,
                 int n_cells, int ppc, int level, double sub_step, Counters *ctr, unsigned *__restrict__ stay_bits,
@@ -254,13 +254,6 @@ k_advect_locate(ParticleSoA p, const CellGeom *__restrict__ geom, const int4 *__
         bool lost = false;
         if (valid) {
             int4 *rec = reinterpret_cast<int4 *>(p.records() + i);
-            if (TUNE & 1) { // next iteration's record -> L2
-                if (i + stride < n) {
-                    const char *nx = reinterpret_cast<const char *>(p.records() + i + stride);
-                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nx));
-                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nx + 32));
-                }
-            }
             const int4 r0 = __ldcs(rec), r1 = __ldcs(rec + 1), r2 = __ldcs(rec + 2);
             const unsigned id = (unsigned)r2.w;
             c0 = c = (unsigned)r2.z;

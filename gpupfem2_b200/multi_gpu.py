@@ -192,11 +192,11 @@ def bench_main(args, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device(device))
     if args.workload not in bench.WORKLOADS:
         raise SystemExit("multi-GPU bench runs the synthetic channel workloads")
-    nx, ny, lx, ly, level, umax, dt = bench.channel_params(args)
+    nx, ny, lx, ly, level, umax, dt = bench.channel_params(args, world)
     dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device)
-    y = dm.vertices[:, 1].contiguous()
-    F = ((4.0 * umax * y * (ly - y) / (ly * ly)).contiguous(), torch.zeros_like(y))
-    W = (torch.zeros_like(y), torch.zeros_like(y))
+    fx, fy = bench.nodal_field(args, dm.vertices[:, 0].contiguous(), dm.vertices[:, 1].contiguous(), lx, ly, umax)
+    F = (fx.contiguous(), fy.contiguous())
+    W = (torch.zeros_like(F[0]), torch.zeros_like(F[0]))
     bounds = strip_bounds(dm.n_cells, world, align=2 * ny)
     h = DistributedParticleHandler2D(dm, level, bounds, rank, world, max_division_level=8, capacity_factor=args.capacity_factor)
     h.seed_particles()
@@ -243,8 +243,9 @@ def bench_main(args, rank, world, local):
         out = {
             "metric": "particle-steps/sec (advect+locate+sort+project+correct)", "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": bench.workload_description(args) + f", strip-partitioned over {world} GPUs (quad columns)",
+            "higher_is_better": True, "scaling": "weak" if args.workload in bench.WEAK else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": bench.workload_description(args, world) + f", strip-partitioned over {world} GPUs (quad columns)",
                        "particles_mean": psteps / args.steps, "cells": dm.n_cells, "nodes": dm.n_nodes, "substeps": args.substeps, "dt": dt,
                        "l2": "inputs larger than L2", "timing": "CUDA events on rank-local default stream, max over ranks, barrier on both sides",
                        "migrated_particles_per_step": float(tsum[2]) / args.steps,

@@ -65,6 +65,10 @@ typedef struct pfem2_options {
     int defer_correct;      /* 1 (default): correctParticleVelocity snapshots the nodal increment and the particle update is
                                folded into the next advect pass (bit-identical; applied eagerly before any other reader);
                                0: eager kernel */
+    int lane_per_record;    /* 0 (default): the advect pass moves 32-record tiles global <-> shared with the copy engine
+                               (cp.async.bulk.tensor, 64-byte swizzle) and the reorder scatter uses four lanes per record;
+                               1: one lane per 64-byte record with 128-bit global loads / stores in both (the earlier kernels:
+                               same results, bounded by L1 data-pipe wavefronts; kept for A/B measurements) */
 } pfem2_options;
 
 /* counters of the last pfem2_advect call (device-resident, read back on demand) */

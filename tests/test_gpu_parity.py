@@ -370,3 +370,38 @@ def test_walk_fast_path_equals_ordered_scan(gpu, oracle, name):
         assert np.array_equal(a[k], b[k]), k
     assert ha.stats() == hb.stats()
     assert np.array_equal(w[0].cpu().numpy(), w2[0].cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["cyl3_l2", "channel_fast", "tiny_fast", "tiny_l4"])
+def test_tma_tiles_and_quad_scatter_equal_lane_per_record_kernels(gpu, oracle, name):
+    """The default data movement (advect: cp.async.bulk.tensor tiles with the 64-byte swizzle; scatter: four lanes per
+    record) against the one-lane-per-record kernels (pfem2_options.lane_per_record): identical bits in the deterministic
+    order, on meshes whose particle counts are not multiples of the 32-record tile (partial last tile, tensor-map
+    out-of-bounds rows) and with deletions, re-seeding and a pending deferred correction in every advect."""
+    c = cases.build_case(name)
+    oracle.complete_mesh(c.mesh)
+    dm = gpu.DeviceMesh(c.mesh)
+    ha = gpu.ParticleHandler2D(dm, c.level, stable_order=True)
+    hb = gpu.ParticleHandler2D(dm, c.level, stable_order=True, lane_per_record=True)
+    f, w = dev_field(c)
+    w2 = (torch.zeros_like(f[0]), torch.zeros_like(f[0]))
+    for h in (ha, hb):
+        h.seed_particles()
+        h.init_particle_velocity(f)
+    for s in range(10):
+        ha.step(f, w, c.dt, c.substeps)
+        hb.step(f, w2, c.dt, c.substeps)
+        assert ha.get_particle_count() == hb.get_particle_count()
+    a, b = ha.download(), hb.download()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert ha.stats() == hb.stats()
+    assert np.array_equal(w[0].cpu().numpy(), w2[0].cpu().numpy()) and np.array_equal(w[1].cpu().numpy(), w2[1].cpu().numpy())
+
+
+def test_fast_order_quad_scatter_matches_oracle_after_capacity_growth(gpu, oracle):
+    """Fast (atomic-order) path with the quad scatter across a capacity growth: the tensor maps of the record buffers
+    are re-encoded for the new allocation; the canonicalised state still equals the oracle's."""
+    m = cases._tiny(True)
+    fx, fy = cases._mix(m, 0.5, 1.0, 0.35, 1.0)
+    run_both(gpu, oracle, m, fx, fy, 4, 3, 0.2, 14, check_every=7, capacity_factor=1.02)

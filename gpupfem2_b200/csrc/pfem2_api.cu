@@ -321,7 +321,9 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
                          &h->ctr->n_old, h->cursor, h->ctr);
         } else {
             if (h->opt.lane_per_record == 0)
-                PFEM2_LAUNCH(k_scatter_all_quads, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
+                // 12 eight-record groups in flight per warp, 2 blocks per SM (measured on channel16m: U x blocks = 8x3 6.40 ms,
+                // 12x2 6.16, 16x2 6.40, 20x2 7.4, 24x1 7.3, 8x4 6.7, 4x6 6.7 for the whole reorder phase)
+                PFEM2_LAUNCH((k_scatter_all_quads<12, 2>), grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
             else
                 PFEM2_LAUNCH(k_scatter_all_regs, grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
         }

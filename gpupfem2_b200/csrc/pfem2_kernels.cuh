@@ -693,21 +693,23 @@ k_scatter_all_regs(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_o
 // and the four lanes of a quad store one whole 64-byte record (1 wavefront), where the one-lane-per-record form needs
 // 16 wavefronts per load instruction and 4 per stored record: the L1 data pipe, not HBM, bounded that form
 // (l1tex__data_pipe_lsu_wavefronts 67 % at 5.0 TB/s, profiles/r01_final_summary.md).  U groups are in flight per warp.
-__global__ void __launch_bounds__(kThreads)
+template <int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 k_scatter_all_quads(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_old_ptr, int *__restrict__ cursor, const Counters *ctr)
 {
     if (ctr->overflow) return;
     const int n = *n_old_ptr;
     const int lane = threadIdx.x & 31;
     const int f = lane & 3, q = lane >> 2;
-    constexpr int U = 8; // 8-record groups per warp and iteration
+    const unsigned lt = (1u << lane) - 1;
+    // U 8-record groups per warp and iteration: all loads, then all atomics, are in flight together
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
     const int4 *__restrict__ in = reinterpret_cast<const int4 *>(src.records());
     int4 *__restrict__ out = reinterpret_cast<int4 *>(dst.records());
     for (long long base = warp_global * (8 * U); base < n; base += warps_total * (8 * U)) {
         int4 v[U];
-        unsigned c[U], peers[U];
+        unsigned peers[U]; // lanes of the records that go to the same cell (whole quads); 0 = lost / beyond the end
         int run[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -717,17 +719,17 @@ k_scatter_all_quads(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            c[u] = (unsigned)__shfl_sync(0xffffffffu, v[u].z, (lane & ~3) | 2); // the record's cell sits in field 2 (tail)
-            peers[u] = __match_any_sync(0xffffffffu, c[u]);                      // whole quads: 4 lanes per record
+            const unsigned c = (unsigned)__shfl_sync(0xffffffffu, v[u].z, (lane & ~3) | 2); // the record's cell sits in field 2 (tail)
+            peers[u] = __match_any_sync(0xffffffffu, c);
             run[u] = 0;
-            if (c[u] != kLostCell && (peers[u] & ((1u << lane) - 1)) == 0) run[u] = atomicAdd(cursor + c[u], __popc(peers[u]) >> 2);
+            if (c == kLostCell) peers[u] = 0;
+            else if ((peers[u] & lt) == 0) run[u] = atomicAdd(cursor + c, __popc(peers[u]) >> 2);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int leader = __ffs(peers[u]) - 1;
-            const int r0 = __shfl_sync(0xffffffffu, run[u], leader);
-            if (c[u] == kLostCell) continue;
-            const long long d = r0 + (__popc(peers[u] & ((1u << lane) - 1)) >> 2);
+            const int r0 = __shfl_sync(0xffffffffu, run[u], peers[u] ? __ffs(peers[u]) - 1 : 0);
+            if (peers[u] == 0) continue;
+            const long long d = r0 + (__popc(peers[u] & lt) >> 2);
             out[d * 4 + f] = v[u];
         }
     }

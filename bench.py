@@ -46,6 +46,7 @@ ALG_BYTES = {  # algorithmic bytes per particle per launch (64 B fp
     "project_cells": 44,  # R(L,cell,v)
 }
 ALG_BYTES_STEP = 192
+TRAFFIC_FILE = "r01b_traffic.json"  # latest committed ncu --set full capture of the three main kernels
 
 WORKLOADS = {
     # name: (nx, ny, lx, ly, default level)
@@ -86,7 +87,7 @@ class ClockSampler:
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -247,14 +248,14 @@ def run_ours(args):
     dom_ms = phases[dom][0] / args.steps
     achieved = ALG_BYTES[dom] * pmean / (dom_ms * 1e-3) / 1e9
     traffic = None
-    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/r01_traffic.json)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/r01b_traffic.json)
+        tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
         if args.workload == "channel16m" and dom in tj:
             traffic = tj[dom]["bytes_per_particle"] * pmean
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled to this run's particle count)" if traffic else None,
+                "traffic": traffic, "traffic_source": f"profiles/{TRAFFIC_FILE} (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled to this run's particle count)" if traffic else None,
                 "peak_source": peak_src, "alg_bytes_per_particle": ALG_BYTES[dom],
                 "step": {"achieved": ALG_BYTES_STEP * value / 1e9, "frac": ALG_BYTES_STEP * value / 1e9 / peak,
                          "alg_bytes_per_particle_step": ALG_BYTES_STEP},
@@ -378,7 +379,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="channel16m", choices=list(WORKLOADS) + ["poiseuille", "cylinder"])

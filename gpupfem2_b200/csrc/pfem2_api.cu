@@ -385,7 +385,7 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
 #define PFEM2_ADV_TMA(NSUB)                                                                                                          \
     PFEM2_LAUNCH((k_advect_locate_tma<MODE, WALK, MASK64, NSUB>), grid, kThreads, smem, h->stream, h->tmap[h->cur], h->geom, h->edge_nbr,   \
                  h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, hsub, substeps, C, h->ppc, h->level, h->sub_step, h->ctr, sb,         \
-                 h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count, h->dv_pending ? h->dv2 : nullptr, h->own_lo, h->own_hi,          \
+                 h->warp_movers, h->stay, h->opt.stable_order ? h->arrive : (int *)nullptr, h->cell_mask, do_count, h->dv_pending ? h->dv2 : nullptr, h->own_lo, h->own_hi,          \
                  h->mg_bounds, h->mg_ranks, h->mg_rank_count, h->mg_fused ? h->keys[0] : (unsigned *)nullptr)
         if (substeps == 3)
             PFEM2_ADV_TMA(3);
@@ -398,7 +398,7 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
 #define PFEM2_ADV_LAUNCH(NSUB)                                                                                                     \
     PFEM2_LAUNCH((k_advect_locate<MODE, WALK, MASK64, NSUB>), grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->geom,   \
                  h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, vel, hsub, substeps, C, h->ppc, h->level, h->sub_step,   \
-                 h->ctr, sbits, h->warp_movers, h->stay, h->arrive, h->cell_mask, do_count, h->dv_pending ? h->dv[0] : nullptr,            \
+                 h->ctr, sbits, h->warp_movers, h->stay, h->opt.stable_order ? h->arrive : (int *)nullptr, h->cell_mask, do_count, h->dv_pending ? h->dv[0] : nullptr,            \
                  h->dv_pending ? h->dv[1] : nullptr)
     if (substeps == 3)
         PFEM2_ADV_LAUNCH(3);

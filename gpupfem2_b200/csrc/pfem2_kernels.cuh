@@ -199,8 +199,12 @@ __device__ __forceinline__ void accumulate_cell_stats(bool live, unsigned c, dou
     if (MASK64) hi = __reduce_or_sync(peers, (unsigned)(gbit >> 32));
     if (live && (peers & ((1u << lane) - 1)) == 0) {
         const int ns = __popc(peers & sb), na = __popc(peers & mb);
-        if (ns) atomicAdd(stay + c, ns);
-        if (na) atomicAdd(arrive + c, na);
+        if (arrive) { // the stable-order path places stayers and movers separately
+            if (ns) atomicAdd(stay + c, ns);
+            if (na) atomicAdd(arrive + c, na);
+        } else { // fast order: only the sum is needed (arrive[] stays zero)
+            atomicAdd(stay + c, ns + na);
+        }
         const unsigned long long word = (unsigned long long)lo | ((unsigned long long)hi << 32);
         if (word) atomicOr(cell_mask + c, word);
     }
@@ -1075,8 +1079,28 @@ k_project_cells(int c_lo, int n_cells, ParticleSoA p, const int *__restrict__ ce
         double acc[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-        // each lane walks the segment with stride G; two particles in flight per lane
+        // each lane walks the segment with stride G; four (then two) particles in flight per lane
         int i = b + lane;
+        for (; i + 3 * G < e; i += 4 * G) {
+            double2 l4[4], v4[4];
+            double z4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                l4[u] = p.lab[i + u * G];
+                v4[u] = p.vel[i + u * G];
+                z4[u] = p.tail[i + u * G].l2;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double Lu[3] = {l4[u].x, l4[u].y, z4[u]};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    acc[3 * k + 0] = __dadd_rn(acc[3 * k + 0], __dmul_rn(Lu[k], v4[u].x));
+                    acc[3 * k + 1] = __dadd_rn(acc[3 * k + 1], __dmul_rn(Lu[k], v4[u].y));
+                    acc[3 * k + 2] = __dadd_rn(acc[3 * k + 2], Lu[k]);
+                }
+            }
+        }
         for (; i + G < e; i += 2 * G) {
             const double2 la = p.lab[i], lb = p.lab[i + G];
             const double2 va = p.vel[i], vb = p.vel[i + G];

@@ -199,7 +199,8 @@ def run_ours(args):
     W = (torch.zeros_like(F[0]), torch.zeros_like(F[0]))
     h = handler.ParticleHandler2D(dm, level, max_division_level=8, capacity_factor=args.capacity_factor,
                                   scatter_tma=bool(int(os.environ.get("PFEM2_SCATTER_TMA", "0"))),
-                                  lane_per_record=bool(int(os.environ.get("PFEM2_LANE_PER_RECORD", "0"))))
+                                  lane_per_record=bool(int(os.environ.get("PFEM2_LANE_PER_RECORD", "0"))),
+                                  host_pipeline=int(os.environ.get("PFEM2_HOST_PIPELINE", "0")))
     h.seed_particles()
     h.init_particle_velocity(F)
     torch.cuda.synchronize()
@@ -275,7 +276,8 @@ def run_ours(args):
     nodal_bytes = 2 * dm.n_nodes * 8
     e2e = {"value": float(sum(e2e_counts)) / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": nodal_bytes,
            "d2h_bytes_per_step": nodal_bytes + 32, "ms_per_step": t_e2e / args.steps * 1e3,
-           "api": "pfem2_step_host (C ABI), pinned host nodal buffers in, projected nodal field + count out"}
+           "api": "pfem2_step_host (C ABI), pinned host nodal buffers in, projected nodal field + count out; the call pipelines the "
+                  "upload with the move pass and the projection with the download in chunks of the cell range (pfem2_options.host_pipeline)"}
 
     state_gb = pmean * 64 / 1e9
     out = {

@@ -101,6 +101,19 @@ struct pfem2_handle {
     size_t aos_bytes = 0;
     double *nodal[4] = {nullptr, nullptr, nullptr, nullptr}; // F.x F.y W.x W.y for pfem2_step_host
 
+    // pfem2_step_host pipeline: the step runs in K chunks of the cell range so that the host <-> device copies of the nodal
+    // fields overlap the move pass (upload) and the projection (download)
+    struct HostPipe {
+        int K = 0, substeps = 0;          // what the plan was made for (0 = none yet)
+        std::vector<int> cb, ns;          // cell chunk bounds (K + 1), node slice bounds of the upload (K + 1)
+        std::vector<int> up_slice;        // chunk j may start once upload slices 0..up_slice[j] have landed
+        std::vector<int> dn_ready;        // after projecting chunk j the nodes [0, dn_ready[j]) are final
+        cudaStream_t copy = nullptr;      // non-blocking copy stream
+        std::vector<cudaEvent_t> up_ev, dn_ev;
+        bool active = false;              // a pipelined step is being issued
+        int packed_slices = 0;            // upload slices already interleaved into v2
+    } pipe;
+
     // optional per-phase CUDA-event timing (pfem2_set_profiling)
     bool profiling = false;
     struct PhaseRec { int phase; cudaEvent_t a, b; };
@@ -379,18 +392,43 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
     if (advect_tma_enabled(h)) { // default: particle tiles moved by the copy engine, nodal velocity interleaved
         unsigned *sb = h->opt.stable_order ? h->stay_bits : nullptr;
         const int N = h->mesh.n_nodes;
-        PFEM2_LAUNCH(k_pack_nodal, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, N, vel, h->v2);
         const size_t smem = advect_tma_smem_bytes(kThreads);
-        const int grid = grid_for(h->capacity, kThreads, g_num_sms * 4); // persistent: 4 resident blocks per SM
+        const int *cstart = nullptr;
+        int c_lo = 0, c_hi = 0;
 #define PFEM2_ADV_TMA(NSUB)                                                                                                          \
     PFEM2_LAUNCH((k_advect_locate_tma<MODE, WALK, MASK64, NSUB>), grid, kThreads, smem, h->stream, h->tmap[h->cur], h->geom, h->edge_nbr,   \
                  h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, hsub, substeps, C, h->ppc, h->level, h->sub_step, h->ctr, sb,         \
                  h->warp_movers, h->stay, h->opt.stable_order ? h->arrive : (int *)nullptr, h->cell_mask, do_count, h->dv_pending ? h->dv2 : nullptr, h->own_lo, h->own_hi,          \
-                 h->mg_bounds, h->mg_ranks, h->mg_rank_count, h->mg_fused ? h->keys[0] : (unsigned *)nullptr)
-        if (substeps == 3)
-            PFEM2_ADV_TMA(3);
-        else
-            PFEM2_ADV_TMA(0);
+                 h->mg_bounds, h->mg_ranks, h->mg_rank_count, h->mg_fused ? h->keys[0] : (unsigned *)nullptr, cstart, c_lo, c_hi)
+        if (!h->pipe.active) {
+            PFEM2_LAUNCH(k_pack_nodal, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, 0, N, vel, h->v2);
+            const int grid = grid_for(h->capacity, kThreads, g_num_sms * 4); // persistent: 4 resident blocks per SM
+            if (substeps == 3)
+                PFEM2_ADV_TMA(3);
+            else
+                PFEM2_ADV_TMA(0);
+        } else {
+            // pfem2_step_host: chunk j of the cell range starts as soon as the slices of the nodal field it can touch have
+            // landed (events recorded on the copy stream) and have been interleaved into v2
+            pfem2_handle::HostPipe &pp = h->pipe;
+            cstart = h->cell_start[h->cs];
+            const int grid = grid_for((long long)h->capacity / pp.K + 1, kThreads, g_num_sms * 4);
+            for (int j = 0; j < pp.K; ++j) {
+                for (; pp.packed_slices <= pp.up_slice[j]; ++pp.packed_slices) {
+                    const int s0 = pp.ns[pp.packed_slices], s1 = pp.ns[pp.packed_slices + 1];
+                    cudaStreamWaitEvent(h->stream, pp.up_ev[pp.packed_slices], 0);
+                    if (s1 > s0) PFEM2_LAUNCH(k_pack_nodal, grid_for(s1 - s0, kThreads, 1 << 30), kThreads, 0, h->stream, s0, s1, vel, h->v2);
+                }
+                c_lo = pp.cb[j];
+                c_hi = pp.cb[j + 1];
+                if (substeps == 3)
+                    PFEM2_ADV_TMA(3);
+                else
+                    PFEM2_ADV_TMA(0);
+            }
+            for (; pp.packed_slices < pp.K; ++pp.packed_slices) // (not reached: the last chunk needs every slice)
+                cudaStreamWaitEvent(h->stream, pp.up_ev[pp.packed_slices], 0);
+        }
 #undef PFEM2_ADV_TMA
         return;
     }
@@ -523,19 +561,24 @@ int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
 
 int flush_correct(pfem2_handle *h);
 
-void launch_project_cells(pfem2_handle *h, const ParticleSoA &p)
+void launch_project_cells(pfem2_handle *h, const ParticleSoA &p, int c_lo = -1, int c_hi = -1)
 {
     cudaStream_t st = h->stream;
-    const int C = h->mesh.n_cells, ppc = h->ppc;
+    const int ppc = h->ppc;
+    if (c_lo < 0) { // the owned range
+        c_lo = h->own_lo;
+        c_hi = h->own_hi;
+    }
+    const long long nc = c_hi - c_lo;
     // lanes per cell: about a quarter of the nominal segment length, so each lane keeps several loads in flight
     if (ppc <= 4)
-        PFEM2_LAUNCH(k_project_cells<2>, grid_for((long long)(h->own_hi - h->own_lo) * 2), kThreads, 0, st, h->own_lo, h->own_hi, p, h->cell_start[h->cs], h->partial);
+        PFEM2_LAUNCH(k_project_cells<2>, grid_for(nc * 2), kThreads, 0, st, c_lo, c_hi, p, h->cell_start[h->cs], h->partial);
     else if (ppc <= 16)
-        PFEM2_LAUNCH(k_project_cells<4>, grid_for((long long)(h->own_hi - h->own_lo) * 4), kThreads, 0, st, h->own_lo, h->own_hi, p, h->cell_start[h->cs], h->partial);
+        PFEM2_LAUNCH(k_project_cells<4>, grid_for(nc * 4), kThreads, 0, st, c_lo, c_hi, p, h->cell_start[h->cs], h->partial);
     else if (ppc <= 36)
-        PFEM2_LAUNCH(k_project_cells<8>, grid_for((long long)(h->own_hi - h->own_lo) * 8), kThreads, 0, st, h->own_lo, h->own_hi, p, h->cell_start[h->cs], h->partial);
+        PFEM2_LAUNCH(k_project_cells<8>, grid_for(nc * 8), kThreads, 0, st, c_lo, c_hi, p, h->cell_start[h->cs], h->partial);
     else
-        PFEM2_LAUNCH(k_project_cells<16>, grid_for((long long)(h->own_hi - h->own_lo) * 16), kThreads, 0, st, h->own_lo, h->own_hi, p, h->cell_start[h->cs], h->partial);
+        PFEM2_LAUNCH(k_project_cells<16>, grid_for(nc * 16), kThreads, 0, st, c_lo, c_hi, p, h->cell_start[h->cs], h->partial);
 }
 
 int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
@@ -557,7 +600,7 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
     launch_project_cells(h, p);
     }
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
-    PFEM2_LAUNCH(k_project_nodes, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, N, h->node_off, (const int *)h->node_inc, h->partial,
+    PFEM2_LAUNCH(k_project_nodes, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, 0, N, h->node_off, (const int *)h->node_inc, h->partial,
                  vx, vy, table);
     CU(cudaGetLastError());
     return PFEM2_OK;
@@ -800,6 +843,9 @@ int pfem2_destroy(pfem2_handle *h)
     cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count); cudaFree(h->own_len_dev); cudaFree(h->node_list);
     cudaFree(h->dv[0]); cudaFree(h->dv[1]);
     cudaFree(h->dv2); cudaFree(h->v2);
+    if (h->pipe.copy) cudaStreamDestroy(h->pipe.copy);
+    for (cudaEvent_t e : h->pipe.up_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->pipe.dn_ev) cudaEventDestroy(e);
     for (double *p : h->nodal) cudaFree(p);
     for (auto &r : h->phase_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
@@ -903,23 +949,147 @@ int pfem2_export_aos(pfem2_handle *h, const void **d_particles96, int *count)
     return PFEM2_OK;
 }
 
+// Plan of the pipelined pfem2_step_host for K chunks (made once per (K, substeps)): cell chunk bounds, node slices of the
+// upload, and per chunk the upload slices it depends on / the node prefix that is final after its projection.  The
+// dependencies are derived from the mesh itself (band width of the one-ring lists x substeps), so any numbering is handled:
+// a numbering without locality simply yields "wait for the whole upload" and "download at the end".
+int plan_host_pipe(pfem2_handle *h, int K, int substeps)
+{
+    pfem2_handle::HostPipe &pp = h->pipe;
+    if (pp.K == K && pp.substeps == substeps) return PFEM2_OK;
+    const int C = h->mesh.n_cells, N = h->mesh.n_nodes;
+    cudaStream_t st = h->stream;
+    if (!pp.copy) CU(cudaStreamCreateWithFlags(&pp.copy, cudaStreamNonBlocking));
+    while ((int)pp.up_ev.size() < K) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        pp.up_ev.push_back(a);
+        pp.dn_ev.push_back(b);
+    }
+    pp.cb.resize(K + 1);
+    pp.ns.resize(K + 1);
+    for (int j = 0; j <= K; ++j) pp.cb[j] = (int)((long long)C * j / K);
+    int *dev = nullptr; // [band | cb (K+1) | up_need (K) | dn_ready (K)]
+    CU(cudaMalloc((void **)&dev, sizeof(int) * (size_t)(3 * K + 2)));
+    std::vector<int> init(3 * K + 2, 0);
+    for (int j = 0; j <= K; ++j) init[1 + j] = pp.cb[j];
+    for (int j = 0; j < K; ++j) init[2 + 2 * K + j] = N; // dn_ready starts at "everything"
+    CU(cudaMemcpyAsync(dev, init.data(), sizeof(int) * init.size(), cudaMemcpyHostToDevice, st));
+    PFEM2_LAUNCH(k_band_width, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, dev);
+    int band = 0;
+    CU(cudaMemcpyAsync(&band, dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const long long ext = std::min<long long>((long long)band * substeps, C);
+    PFEM2_LAUNCH(k_chunk_node_ranges, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, h->geom, K, dev + 1, (int)ext, dev + 2 + K,
+                 dev + 2 + 2 * K);
+    std::vector<int> out(3 * K + 2);
+    CU(cudaMemcpyAsync(out.data(), dev, sizeof(int) * out.size(), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(dev);
+    // upload slice j = exactly the node prefix chunk j needs on top of what the chunks before it needed (chunks run in
+    // order, so the dependency only grows); download prefix after chunk j likewise
+    pp.up_slice.assign(K, 0);
+    pp.dn_ready.assign(K, 0);
+    int prev_up = 0, prev_dn = 0;
+    pp.ns[0] = 0;
+    for (int j = 0; j < K; ++j) {
+        const int need = (j == K - 1) ? N : std::min(std::max(out[2 + K + j], 1), N); // node prefix [0, need) must have landed
+        prev_up = std::max(prev_up, need);
+        pp.ns[j + 1] = prev_up;
+        pp.up_slice[j] = j;
+        const int ready = (j == K - 1) ? N : std::min(out[2 + 2 * K + j], N);
+        prev_dn = std::max(prev_dn, ready);
+        pp.dn_ready[j] = prev_dn;
+    }
+    pp.K = K;
+    pp.substeps = substeps;
+    return PFEM2_OK;
+}
+
+int host_pipe_chunks(const pfem2_handle *h)
+{
+    if (h->opt.host_pipeline == 1 || !advect_tma_enabled(h) || h->opt.stable_order) return 1;
+    if (h->own_lo != 0 || h->own_hi != h->mesh.n_cells) return 1; // multi-GPU strips exchange particles between the phases
+    if (h->opt.host_pipeline > 1) return std::min(h->opt.host_pipeline, 16);
+    return h->mesh.n_cells < (1 << 18) ? 1 : 4; // small meshes are launch-bound: one chunk
+}
+
 int pfem2_step_host(pfem2_handle *h, const double *fx, const double *fy, double *wx, double *wy, double dt, int substeps,
                     int *count_out)
 {
     if (!h || !fx || !fy || !wx || !wy) return PFEM2_EINVAL;
     CU(cudaSetDevice(h->device));
-    const size_t nb = sizeof(double) * (size_t)h->mesh.n_nodes;
+    const int N = h->mesh.n_nodes;
+    const size_t nb = sizeof(double) * (size_t)N;
     for (double *&p : h->nodal)
         if (!p) CU(cudaMalloc((void **)&p, nb));
     cudaStream_t st = h->stream;
-    CU(cudaMemcpyAsync(h->nodal[0], fx, nb, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(h->nodal[1], fy, nb, cudaMemcpyHostToDevice, st));
     int rc;
-    if ((rc = pfem2_advect(h, h->nodal[0], h->nodal[1], dt, substeps))) return rc;
-    if ((rc = pfem2_project(h, h->nodal[2], h->nodal[3]))) return rc;
+    const int K = host_pipe_chunks(h);
+    if (K <= 1 || substeps < 1) {
+        CU(cudaMemcpyAsync(h->nodal[0], fx, nb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->nodal[1], fy, nb, cudaMemcpyHostToDevice, st));
+        if ((rc = pfem2_advect(h, h->nodal[0], h->nodal[1], dt, substeps))) return rc;
+        if ((rc = pfem2_project(h, h->nodal[2], h->nodal[3]))) return rc;
+        if ((rc = pfem2_correct(h, h->nodal[0], h->nodal[1], h->nodal[2], h->nodal[3]))) return rc;
+        CU(cudaMemcpyAsync(wx, h->nodal[2], nb, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(wy, h->nodal[3], nb, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if ((rc = sync_counters(h))) return rc;
+        if (count_out) *count_out = h->host_count;
+        return PFEM2_OK;
+    }
+    // Pipelined form: upload slices on the copy stream -> chunked move pass; chunked projection -> download slices on the
+    // copy stream.  Same kernels, same arithmetic, same results as the three calls above.
+    if ((rc = plan_host_pipe(h, K, substeps))) return rc;
+    pfem2_handle::HostPipe &pp = h->pipe;
+    {   // the nodal buffers may still be read by work of the caller's stream (previous step): order the uploads behind it
+        CU(cudaEventRecord(pp.dn_ev[0], st));
+        CU(cudaStreamWaitEvent(pp.copy, pp.dn_ev[0], 0));
+    }
+    for (int s = 0; s < K; ++s) {
+        const size_t o = (size_t)pp.ns[s], len = (size_t)(pp.ns[s + 1] - pp.ns[s]) * sizeof(double);
+        if (len) {
+            CU(cudaMemcpyAsync(h->nodal[0] + o, fx + o, len, cudaMemcpyHostToDevice, pp.copy));
+            CU(cudaMemcpyAsync(h->nodal[1] + o, fy + o, len, cudaMemcpyHostToDevice, pp.copy));
+        }
+        CU(cudaEventRecord(pp.up_ev[s], pp.copy));
+    }
+    pp.packed_slices = 0;
+    pp.active = true;
+    rc = pfem2_advect(h, h->nodal[0], h->nodal[1], dt, substeps); // the move pass runs chunk by chunk (launch_advect)
+    pp.active = false;
+    if (rc) return rc;
+    for (; pp.packed_slices < K; ++pp.packed_slices) CU(cudaStreamWaitEvent(st, pp.up_ev[pp.packed_slices], 0));
+    if ((rc = flush_correct(h))) return rc; // nothing pending after an advect; kept for symmetry with do_project
+    {
+        ParticleSoA p = h->soa[h->cur];
+        int done = 0; // nodes [0, done) are final and on their way to the host
+        for (int j = 0; j < K; ++j) {
+            {
+                PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
+                launch_project_cells(h, p, pp.cb[j], pp.cb[j + 1]);
+            }
+            const int ready = pp.dn_ready[j];
+            if (ready > done) {
+                {
+                    PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
+                    PFEM2_LAUNCH(k_project_nodes, grid_for(ready - done, kThreads, 1 << 30), kThreads, 0, st, done, ready, h->node_off,
+                                 (const int *)h->node_inc, h->partial, h->nodal[2], h->nodal[3], (double *const *)nullptr);
+                }
+                CU(cudaEventRecord(pp.dn_ev[j], st));
+                CU(cudaStreamWaitEvent(pp.copy, pp.dn_ev[j], 0));
+                const size_t len = (size_t)(ready - done) * sizeof(double);
+                CU(cudaMemcpyAsync(wx + done, h->nodal[2] + done, len, cudaMemcpyDeviceToHost, pp.copy));
+                CU(cudaMemcpyAsync(wy + done, h->nodal[3] + done, len, cudaMemcpyDeviceToHost, pp.copy));
+                done = ready;
+            }
+        }
+    }
+    CU(cudaGetLastError());
     if ((rc = pfem2_correct(h, h->nodal[0], h->nodal[1], h->nodal[2], h->nodal[3]))) return rc;
-    CU(cudaMemcpyAsync(wx, h->nodal[2], nb, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(wy, h->nodal[3], nb, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(pp.copy));
     CU(cudaStreamSynchronize(st));
     if ((rc = sync_counters(h))) return rc;
     if (count_out) *count_out = h->host_count;

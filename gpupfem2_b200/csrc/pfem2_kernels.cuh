@@ -365,8 +365,11 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
                     int substeps, int n_cells, int ppc, int level, double sub_step, Counters *ctr, unsigned *__restrict__ stay_bits,
                     int *__restrict__ warp_movers, int *__restrict__ stay, int *__restrict__ arrive,
                     unsigned long long *__restrict__ cell_mask, int do_count, const double2 *__restrict__ dV2, int own_lo, int own_hi,
-                    const int *__restrict__ rank_bounds, int n_ranks, int *__restrict__ rank_count, unsigned *__restrict__ emig_idx)
+                    const int *__restrict__ rank_bounds, int n_ranks, int *__restrict__ rank_count, unsigned *__restrict__ emig_idx,
+                    const int *__restrict__ chunk_start, int chunk_lo, int chunk_hi)
 {
+    // chunk_start != nullptr: only the particles of the cells [chunk_lo, chunk_hi) are moved (chunk_start = the segment table
+    // of the sorted array): pfem2_step_host launches the pass chunk by chunk while the nodal field is still arriving over PCIe.
     // Multi-GPU (emig_idx != nullptr): a particle whose new cell lies outside the owned range [own_lo, own_hi) is an
     // emigrant.  It is written back like everybody else (the pack kernel removes it), but it is kept out of the per-cell
     // statistics, its array index is appended to emig_idx and rank_count[destination] / rank_count[n_ranks] (total) are
@@ -386,9 +389,13 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
         fence_barrier_init();
     }
     __syncthreads();
-    const int n = ctr->count;
+    int p_lo = 0, n = ctr->count; // particle range [p_lo, n) of this launch
+    if (chunk_start) {
+        p_lo = min(__ldg(chunk_start + chunk_lo), n);
+        n = min(__ldg(chunk_start + chunk_hi), n);
+    }
     const int tiles = (n + 31) >> 5;
-    const int warp_global = blockIdx.x * warps_per_block + warp;
+    const int warp_global = (p_lo >> 5) + blockIdx.x * warps_per_block + warp;
     const int warps_total = gridDim.x * warps_per_block;
     // my record inside a tile: the 16-byte field f of row `lane` sits at  lane * 64 + ((f ^ sw) << 4)  =  my0 ^ (f << 4)
     const uint32_t my0 = (uint32_t)lane * 64 + ((((uint32_t)lane >> 1) & 3) << 4);
@@ -415,7 +422,7 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
         const uint32_t sa0 = buf + my0, sa1 = sa0 ^ 16u, sa2 = sa0 ^ 32u, sa3 = sa0 ^ 48u;
         const int base = tile << 5;
         const int i = base + lane;
-        const bool valid = i < n;
+        const bool valid = i >= p_lo && i < n;
         unsigned c0 = 0, c = 0;
         double L0 = 0, L1 = 0, L2 = 0;
         int moved = 0; // substeps in which the particle left its cell
@@ -509,12 +516,51 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
 }
 
 // nodal velocity, interleaved for the advect pass: V2[n] = (Vx[n], Vy[n])
-__global__ void __launch_bounds__(kThreads) k_pack_nodal(int n_nodes, NodalVel vel, double2 *__restrict__ V2)
+__global__ void __launch_bounds__(kThreads) k_pack_nodal(int node_lo, int node_hi, NodalVel vel, double2 *__restrict__ V2)
 {
     const double *Vx, *Vy;
     vel.resolve(Vx, Vy);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_nodes) V2[i] = make_double2(Vx[i], Vy[i]);
+    const int i = node_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < node_hi) V2[i] = make_double2(Vx[i], Vy[i]);
+}
+
+// ---- pfem2_step_host pipeline plan (once per handle): how far the cell numbering couples distant cells, and which
+// node ranges a chunk of cells depends on ----
+// band[0] = max |neighbour - cell| over the one-ring lists: a particle changes its cell index by at most that per substep
+__global__ void __launch_bounds__(kThreads) k_band_width(int n_cells, const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, int *band)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int w = 0;
+    if (c < n_cells)
+        for (int k = __ldg(nbr_off + c); k < __ldg(nbr_off + c + 1); ++k) w = max(w, abs(__ldg(nbr_idx + k) - c));
+    w = __reduce_max_sync(0xffffffffu, w);
+    if ((threadIdx.x & 31) == 0 && w > 0) atomicMax(band, w);
+}
+// For the K chunks [cb[j], cb[j+1]) of the cell range and a reach of `ext` cells (substeps x band width):
+//   up_need[j]  = 1 + the largest node id of any cell a particle of chunk j can visit (cells [cb[j]-ext, cb[j+1]+ext))
+//   dn_ready[j] = the smallest node id of any cell behind chunk j (cells >= cb[j+1]): nodes below it are complete once the
+//                 chunks 0..j have been projected
+__global__ void __launch_bounds__(kThreads)
+k_chunk_node_ranges(int n_cells, const CellGeom *__restrict__ geom, int K, const int *__restrict__ cb, int ext, int *__restrict__ up_need,
+                    int *__restrict__ dn_ready)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = c < n_cells;
+    int mn = 0x7fffffff, mx = -1;
+    if (valid) {
+        const uint4 nn = __ldg(reinterpret_cast<const uint4 *>(&geom[c].n0));
+        mn = (int)min(nn.x, min(nn.y, nn.z));
+        mx = (int)max(nn.x, max(nn.y, nn.z));
+    }
+    for (int j = 0; j < K; ++j) {
+        const long long lo = (long long)__ldg(cb + j) - ext, hi = (long long)__ldg(cb + j + 1) + ext;
+        const int a = __reduce_max_sync(0xffffffffu, (valid && c >= lo && c < hi) ? mx + 1 : 0);
+        const int b = __reduce_min_sync(0xffffffffu, (valid && c >= __ldg(cb + j + 1)) ? mn : 0x7fffffff);
+        if ((threadIdx.x & 31) == 0) {
+            if (a > 0) atomicMax(up_need + j, a);
+            if (b != 0x7fffffff) atomicMin(dn_ready + j, b);
+        }
+    }
 }
 
 // movers -> (new cell, array index) pairs in array order, at the positions the scan of warp_movers assigns
@@ -1145,12 +1191,13 @@ k_project_cells(int c_lo, int n_cells, ParticleSoA p, const int *__restrict__ ce
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_project_nodes(int n_nodes, const int *__restrict__ node_off, const int *__restrict__ node_inc,
+k_project_nodes(int node_lo, int n_nodes, const int *__restrict__ node_off, const int *__restrict__ node_inc,
                 const double *__restrict__ partial, double *vx_arg, double *vy_arg, double *const *table)
 {
+    // nodes [node_lo, n_nodes)
     double *Vx = table ? table[0] : vx_arg;
     double *Vy = table ? table[1] : vy_arg;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = node_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     double sx = 0.0, sy = 0.0, sw = 0.0;
     const int e = __ldg(node_off + i + 1);

@@ -1012,7 +1012,8 @@ int host_pipe_chunks(const pfem2_handle *h)
     if (h->opt.host_pipeline == 1 || !advect_tma_enabled(h) || h->opt.stable_order) return 1;
     if (h->own_lo != 0 || h->own_hi != h->mesh.n_cells) return 1; // multi-GPU strips exchange particles between the phases
     if (h->opt.host_pipeline > 1) return std::min(h->opt.host_pipeline, 16);
-    return h->mesh.n_cells < (1 << 18) ? 1 : 4; // small meshes are launch-bound: one chunk
+    return h->mesh.n_cells < (1 << 18) ? 1 : 8; // small meshes are launch-bound: one chunk (sweep on channel16m: 1 chunk 23.5 ms,
+                                                // 2: 20.3, 4: 19.3, 6: 18.9, 8: 18.8, 12: 18.7; device time alone 17.8)
 }
 
 int pfem2_step_host(pfem2_handle *h, const double *fx, const double *fy, double *wx, double *wy, double dt, int substeps,

@@ -201,15 +201,18 @@ def bench_main(args, rank, world, local):
     h = DistributedParticleHandler2D(dm, level, bounds, rank, world, max_division_level=8, capacity_factor=args.capacity_factor)
     h.seed_particles()
     h.init_particle_velocity(F)
+    sampler = bench.ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         h.step(F, W, dt, args.substeps)
     h.get_particle_count()
     torch.cuda.synchronize()
+    if sampler:
+        sampler.wait_first_sample()
+        sampler.mark()
     dist.barrier()
     h.h.set_profiling(True)
     h.h.phase_times(reset=True)
     launches0 = handler.kernel_launches()
-    sampler = bench.ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     counts, sent = [], 0
     torch.cuda.synchronize()

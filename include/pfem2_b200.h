@@ -69,7 +69,7 @@ typedef struct pfem2_options {
                                (cp.async.bulk.tensor, 64-byte swizzle) and the reorder scatter uses four lanes per record;
                                1: one lane per 64-byte record with 128-bit global loads / stores in both (the earlier kernels:
                                same results, bounded by L1 data-pipe wavefronts; kept for A/B measurements) */
-    int host_pipeline;      /* pfem2_step_host: 0 (default) = 4 chunks on meshes of >= 262144 cells: the upload of the nodal field
+    int host_pipeline;      /* pfem2_step_host: 0 (default) = 8 chunks on meshes of >= 262144 cells: the upload of the nodal field
                                overlaps the move pass and the download of the projected field overlaps the projection, chunk by
                                chunk of the cell range (dependencies derived from the mesh numbering); 1 = no pipelining; n > 1 =
                                n chunks */

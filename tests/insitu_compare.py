@@ -3,7 +3,7 @@ the UNMODIFIED reference case cases/PoiseuilleFlow2D/main.cu, once linked agains
 against the library whose ParticleHandler2D is the B200 drop-in.  Compares the per-step particle counts printed by
 advectParticles and the nodal fields of the exported solution files.
 
-    python tests/insitu_compare.py [steps_to_compare] -> gpurun_out/insitu_summary.json
+    python tests/insitu_compare.py [poiseuille|cylinder] -> gpurun_out/insitu_summary[_cylinder].json
 """
 import json
 import os
@@ -33,14 +33,17 @@ def parse_vtu(path):
 
 
 def main():
+    case = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1] in ("poiseuille", "cylinder") else "poiseuille"
+    fixture, datname, exename, suffix = {"poiseuille": ("mesh_channel.npz", "ChannelMesh.dat", "Poiseuille", ""),
+                                         "cylinder": ("mesh_cylinder3.npz", "CylinderMesh3.dat", "Cylinder", "_cylinder")}[case]
     work = tempfile.mkdtemp(prefix="insitu_")
-    d = np.load(os.path.join(ROOT, "tests", "golden", "mesh_channel.npz"))
-    write_dat(os.path.join(work, "ChannelMesh.dat"), HostMesh(d["vertices"], d["cells"]))
+    d = np.load(os.path.join(ROOT, "tests", "golden", fixture))
+    write_dat(os.path.join(work, datname), HostMesh(d["vertices"], d["cells"]))
     res = {}
     for tag in ("ref", "shim"):
         run = os.path.join(work, tag)
         os.makedirs(run)
-        exe = os.path.join(ROOT, "oracle", "_ref", f"Poiseuille_{tag}")
+        exe = os.path.join(ROOT, "oracle", "_ref", f"{exename}_{tag}")
         t0 = time.time()
         p = subprocess.run([exe], cwd=run, capture_output=True, text=True, timeout=3000)
         res[tag] = {"rc": p.returncode, "wall_s": time.time() - t0, "stdout": p.stdout, "stderr": p.stderr[-2000:], "dir": run}
@@ -60,7 +63,7 @@ def main():
     summary["max_count_rel_diff"] = float(max((abs(a - b) / a for a, b in zip(counts["ref"][:n], counts["shim"][:n])), default=0.0))
     summary["final_counts"] = [counts["ref"][n - 1] if n else None, counts["shim"][n - 1] if n else None]
     fields = {}
-    for k in (10, 100, 250, 490):
+    for k in (10, 100, 250, 490, 500):
         fa, fb = (os.path.join(res[t]["dir"], f"solution{k:04d}.vtu") for t in ("ref", "shim"))
         if not (os.path.exists(fa) and os.path.exists(fb)):
             cand = [f for f in os.listdir(res["ref"]["dir"]) if f.startswith("solution")]
@@ -71,9 +74,10 @@ def main():
                      for name in A if name in B and A[name].shape == B[name].shape and A[name].size}
     summary["field_rel_inf_diff"] = fields
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "insitu_summary.json"), "w") as f:
+    summary["case"] = case
+    with open(os.path.join(ROOT, "gpurun_out", f"insitu_summary{suffix}.json"), "w") as f:
         json.dump(summary, f, indent=1)
-    with open(os.path.join(ROOT, "gpurun_out", "insitu_counts.txt"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", f"insitu_counts{suffix}.txt"), "w") as f:
         for i in range(n):
             f.write(f"{i + 1} {counts['ref'][i]} {counts['shim'][i]}\n")
     print(json.dumps(summary, indent=1))

@@ -101,6 +101,16 @@ struct pfem2_handle {
     size_t aos_bytes = 0;
     double *nodal[4] = {nullptr, nullptr, nullptr, nullptr}; // F.x F.y W.x W.y for pfem2_step_host
 
+    // trailing projection (pfem2_options.fuse_project): the projection's cell pass runs concurrently with the re-sort
+    // scatter inside advectParticles and leaves the per-cell sums in `partial`
+    int last_substeps = 1;             // substeps of the move pass in flight (reach of a particle = band x substeps)
+    int band = -1;                     // max |neighbour - cell| over the one-ring lists (-1: not computed yet)
+    bool partials_valid = false;       // `partial` holds the nine sums of the current particle state
+    cudaStream_t trail_stream = nullptr;
+    cudaEvent_t trail_ev[2] = {nullptr, nullptr};
+    int *trail_prog = nullptr;         // per producer block: slabs done; [n] = the consumer's chunk counter
+    int trail_prog_n = 0;
+
     // pfem2_step_host pipeline: the step runs in K chunks of the cell range so that the host <-> device copies of the nodal
     // fields overlap the move pass (upload) and the projection (download)
     struct HostPipe {
@@ -297,6 +307,29 @@ NodalVel nodal(const double *x, const double *y, double *const *table)
 // Re-establish the cell-sorted order in the other buffer: stayers keep their relative order, the movers listed in
 // keys[0]/vals[0] (n = ctr->n_movers, array order) are radix-sorted by new cell and appended behind the stayers of
 // their cell, lost particles are dropped and (optionally) every empty sub-cell is re-seeded.
+// band width of the cell numbering (one-time): a particle's cell index changes by at most this much per substep
+int mesh_band(pfem2_handle *h)
+{
+    if (h->band >= 0) return PFEM2_OK;
+    int *dev = nullptr;
+    CU(cudaMalloc((void **)&dev, sizeof(int)));
+    CU(cudaMemsetAsync(dev, 0, sizeof(int), h->stream));
+    const int C = h->mesh.n_cells;
+    PFEM2_LAUNCH(k_band_width, grid_for(C, kThreads, 1 << 30), kThreads, 0, h->stream, C, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, dev);
+    int band = 0;
+    CU(cudaMemcpyAsync(&band, dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(dev);
+    h->band = band;
+    return PFEM2_OK;
+}
+
+bool trailing_projection_enabled(const pfem2_handle *h, bool reseed, bool stable)
+{
+    return h->opt.fuse_project == 1 && reseed && !stable && h->opt.lane_per_record == 0 && !h->opt.scatter_tma && h->own_lo == 0 &&
+           h->own_hi == h->mesh.n_cells && h->band >= 0;
+}
+
 int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalVel vel)
 {
     cudaStream_t st = h->stream;
@@ -333,6 +366,49 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
             PFEM2_LAUNCH(k_scatter_all_tma<kStages>, grid_for(h->capacity, kThreads, g_num_sms * 4), kThreads, smem, st, src, dst,
                          &h->ctr->n_old, h->cursor, h->ctr);
         } else {
+            if (trailing_projection_enabled(h, reseed, stable)) {
+                // scatter (this stream) and re-seed + projection cell pass (side stream) run concurrently; the consumer trails the
+                // producer by the reach of a particle (band width x substeps) and so reads the new records from L2
+                constexpr int kU = 12, kSlab = (kThreads / 32) * 8 * kU;
+                const int producers = std::max(1, std::min(g_num_sms * 2, (int)(((long long)h->capacity + kSlab - 1) / kSlab)));
+                if (!h->trail_stream) {
+                    CU(cudaStreamCreateWithFlags(&h->trail_stream, cudaStreamNonBlocking));
+                    CU(cudaEventCreateWithFlags(&h->trail_ev[0], cudaEventDisableTiming));
+                    CU(cudaEventCreateWithFlags(&h->trail_ev[1], cudaEventDisableTiming));
+                }
+                // [0] completed producer iterations, [1 .. iters] per-iteration block counters, [last] the consumer's chunk counter
+                const int iters_max = (int)(((long long)h->capacity + kSlab - 1) / kSlab / producers) + 2;
+                if (h->trail_prog_n < iters_max + 2) {
+                    cudaFree(h->trail_prog);
+                    h->trail_prog = nullptr;
+                    CU(cudaMalloc((void **)&h->trail_prog, sizeof(int) * (size_t)(iters_max + 2)));
+                    h->trail_prog_n = iters_max + 2;
+                }
+                CU(cudaMemsetAsync(h->trail_prog, 0, sizeof(int) * (size_t)h->trail_prog_n, st));
+                CU(cudaEventRecord(h->trail_ev[0], st));
+                CU(cudaStreamWaitEvent(h->trail_stream, h->trail_ev[0], 0));
+                PFEM2_LAUNCH((k_scatter_quads_ordered<kU, 2>), producers, kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr,
+                             h->trail_prog);
+                const int consumers = g_num_sms; // one 256-thread block per SM next to the two producer blocks
+                const int reach = (int)std::min<long long>((long long)h->band * std::max(h->last_substeps, 1), C);
+#define PFEM2_TRAIL(G)                                                                                                               \
+    PFEM2_LAUNCH((k_reseed_project_trailing<G>), consumers, kThreads, 0, h->trail_stream, C, h->ppc, reach, kSlab, producers,          \
+                 (const int *)h->trail_prog, h->trail_prog + h->trail_prog_n - 1, (const int *)h->cell_start[h->cs],                   \
+                 (const double2 *)h->mesh.d_vertices, h->geom, h->centers, vel, h->cell_mask, h->stay, h->arrive, h->packed, dst,      \
+                 h->cell_start[h->cs ^ 1], h->partial, h->ctr)
+                if (h->ppc <= 4) PFEM2_TRAIL(2);
+                else if (h->ppc <= 16) PFEM2_TRAIL(4);
+                else if (h->ppc <= 36) PFEM2_TRAIL(8);
+                else PFEM2_TRAIL(16);
+#undef PFEM2_TRAIL
+                CU(cudaEventRecord(h->trail_ev[1], h->trail_stream));
+                CU(cudaStreamWaitEvent(st, h->trail_ev[1], 0));
+                h->cur ^= 1;
+                h->cs ^= 1;
+                h->partials_valid = true;
+                CU(cudaGetLastError());
+                return PFEM2_OK;
+            }
             if (h->opt.lane_per_record == 0)
                 // 12 eight-record groups in flight per warp, 2 blocks per SM (measured on channel16m: U x blocks = 8x3 6.40 ms,
                 // 12x2 6.16, 16x2 6.40, 20x2 7.4, 24x1 7.3, 8x4 6.7, 4x6 6.7 for the whole reorder phase)
@@ -466,6 +542,9 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     }
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells;
+    h->partials_valid = false;
+    h->last_substeps = substeps;
+    if (h->opt.fuse_project == 1 && h->band < 0 && !mg_move && (rc = mesh_band(h))) return rc;
     const double hsub = dt / substeps; // particle_handler_2d.cu:330, host double
     {   // per-cell scratch of the owned range (+ a few cells for the tolerance-band spill of the occupancy bits)
         const size_t lo = (size_t)h->own_lo, len = (size_t)std::min(C, h->own_hi + 4) - lo + 1;
@@ -595,9 +674,10 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
     ParticleSoA p = h->soa[h->cur];
     // lanes per cell: enough to cover the typical segment in one or two strides
     const int ppc = h->ppc;
-    {
-    PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
-    launch_project_cells(h, p);
+    if (!h->partials_valid) { // (the trailing projection of the last advect already left the per-cell sums in `partial`)
+        PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
+        launch_project_cells(h, p);
+        h->partials_valid = true;
     }
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
     PFEM2_LAUNCH(k_project_nodes, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, 0, N, h->node_off, (const int *)h->node_inc, h->partial,
@@ -608,6 +688,7 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
 
 int apply_correct_now(pfem2_handle *h, NodalVel v, NodalVel vold, bool has_old)
 {
+    if (h) h->partials_valid = false; // particle velocities change
     ParticleSoA p = h->soa[h->cur];
     const int grid = grid_for(h->capacity);
     PhaseScope ps(h, PFEM2_PHASE_CORRECT);
@@ -843,6 +924,9 @@ int pfem2_destroy(pfem2_handle *h)
     cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count); cudaFree(h->own_len_dev); cudaFree(h->node_list);
     cudaFree(h->dv[0]); cudaFree(h->dv[1]);
     cudaFree(h->dv2); cudaFree(h->v2);
+    if (h->trail_stream) cudaStreamDestroy(h->trail_stream);
+    for (cudaEvent_t e : h->trail_ev) if (e) cudaEventDestroy(e);
+    cudaFree(h->trail_prog);
     if (h->pipe.copy) cudaStreamDestroy(h->pipe.copy);
     for (cudaEvent_t e : h->pipe.up_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->pipe.dn_ev) cudaEventDestroy(e);
@@ -857,6 +941,7 @@ int pfem2_destroy(pfem2_handle *h)
 
 int pfem2_seed(pfem2_handle *h)
 {
+    if (h) h->partials_valid = false;
     if (!h) return PFEM2_EINVAL;
     CU(cudaSetDevice(h->device));
     const int C = h->mesh.n_cells;
@@ -1068,7 +1153,7 @@ int pfem2_step_host(pfem2_handle *h, const double *fx, const double *fy, double 
         ParticleSoA p = h->soa[h->cur];
         int done = 0; // nodes [0, done) are final and on their way to the host
         for (int j = 0; j < K; ++j) {
-            {
+            if (!h->partials_valid) {
                 PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
                 launch_project_cells(h, p, pp.cb[j], pp.cb[j + 1]);
             }
@@ -1127,6 +1212,7 @@ int pfem2_download(pfem2_handle *h, double *x, double *y, double *l0, double *l1
 int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const double *l0, const double *l1, const double *l2,
                  const double *vx, const double *vy, const unsigned *cell, const unsigned *id)
 {
+    if (h) h->partials_valid = false;
     if (!h || n < 0 || !x || !y || !l0 || !l1 || !l2 || !vx || !vy || !cell) return PFEM2_EINVAL;
     CU(cudaSetDevice(h->device));
     int rc;
@@ -1295,6 +1381,7 @@ int pfem2_emigrants_count(pfem2_handle *h, const int *h_bounds, int n_ranks, int
 
 int pfem2_emigrants_pack(pfem2_handle *h, void *d_records, long long capacity_records)
 {
+    if (h) h->partials_valid = false;
     if (!h || !d_records) return PFEM2_EINVAL;
     if (!h->move_pending || h->mg_ranks == 0) return fail(h, PFEM2_ESTATE, "emigrants_pack before emigrants_count");
     CU(cudaSetDevice(h->device));
@@ -1316,6 +1403,7 @@ int pfem2_emigrants_pack(pfem2_handle *h, void *d_records, long long capacity_re
 
 int pfem2_immigrants_append(pfem2_handle *h, const void *d_records, int n)
 {
+    if (h) h->partials_valid = false;
     if (!h || n < 0 || (n > 0 && !d_records)) return PFEM2_EINVAL;
     if (!h->move_pending) return fail(h, PFEM2_ESTATE, "immigrants_append outside advect_move / advect_finish");
     if (n == 0) return PFEM2_OK;

@@ -785,6 +785,211 @@ k_scatter_all_quads(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Trailing projection (pfem2_options.fuse_project = 1, EXPERIMENTAL, off by default): the re-sort scatter and the projection's cell pass run
+// CONCURRENTLY, the second one trailing the first so closely that it reads the freshly written records from L2 instead
+// of HBM (-64 B per particle-step of DRAM traffic).
+//   producer  k_scatter_quads_ordered   the quad scatter with a block-contiguous schedule: in its k-th iteration block b
+//             moves the records of "slab" k * gridDim + b (8 warps x U groups x 8 records) and counts in; the block that
+//             completes iteration k raises prog[0] to k + 1 (release): all slabs below prog[0] * gridDim are done.
+//   consumer  k_reseed_project_trailing  persistent blocks claim chunks of kTrailCells cells in ascending order, wait
+//             until every source record that can still land in the chunk has been moved (a particle's cell index changes by
+//             at most `reach` = band width of the one-ring lists x substeps, so the records of the old cells below
+//             chunk_end + reach suffice), then re-seed the chunk's cells and reduce their segments to the nine sums.
+// Neither kernel waits for the other's blocks to be scheduled: the producer never waits at all and its grid is sized to
+// be fully resident, so the consumer's spin always ends; a watchdog turns a would-be hang into an error flag.
+// Measured on channel16m (profiles/r01b_summary.md §8): producer 7.6 ms + consumer tail 1.3 ms = 9.1 ms against 6.1 + 2.8 ms for
+// the separate passes -- break-even, because the ordered producer pays for its publish fence (6.5 vs 5.5 ms alone), is slowed
+// further by the co-resident consumer, and the consumer (one 256-thread block per SM next to two producer blocks) cannot quite
+// keep up.  Kept opt-in as the starting point for the persistent fused kernel of DESIGN.md §10.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTrailCells = 256; // cells per consumer chunk (one thread per cell in the re-seed part)
+
+template <int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_scatter_quads_ordered(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_old_ptr, int *__restrict__ cursor, const Counters *ctr,
+                        int *prog)
+{
+    if (ctr->overflow) return;
+    const int n = *n_old_ptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = lane & 3, q = lane >> 2;
+    const unsigned lt = (1u << lane) - 1;
+    constexpr int kSlab = (kThreads / 32) * 8 * U; // records per block iteration
+    const int4 *__restrict__ in = reinterpret_cast<const int4 *>(src.records());
+    int4 *__restrict__ out = reinterpret_cast<int4 *>(dst.records());
+    // every block runs the same number of iterations (possibly with an empty last slab) so that "iteration k complete" is
+    // simply "gridDim blocks have counted in"
+    const long long n_slabs = ((long long)n + kSlab - 1) / kSlab;
+    const int iters = (int)((n_slabs + gridDim.x - 1) / gridDim.x);
+    int *iter_cnt = prog + 1; // prog[0] = completed iterations (monotone), prog[1 + k] = blocks that finished iteration k
+    for (int k = 0; k < iters; ++k) {
+        const long long slab = (long long)k * gridDim.x + blockIdx.x;
+        const long long base = slab * kSlab + (long long)warp * (8 * U);
+        int4 v[U];
+        unsigned peers[U];
+        int run[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long r = base + u * 8 + q;
+            v[u] = make_int4(0, 0, (int)kLostCell, 0);
+            if (r < n) v[u] = __ldcs(in + r * 4 + f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned c = (unsigned)__shfl_sync(0xffffffffu, v[u].z, (lane & ~3) | 2);
+            peers[u] = __match_any_sync(0xffffffffu, c);
+            run[u] = 0;
+            if (c == kLostCell) peers[u] = 0;
+            else if ((peers[u] & lt) == 0) run[u] = atomicAdd(cursor + c, __popc(peers[u]) >> 2);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int r0 = __shfl_sync(0xffffffffu, run[u], peers[u] ? __ffs(peers[u]) - 1 : 0);
+            if (peers[u] == 0) continue;
+            const long long d = r0 + (__popc(peers[u] & lt) >> 2);
+            out[d * 4 + f] = v[u];
+        }
+        // publish: the barrier orders the block's stores before thread 0's fence (cumulativity), one fence per slab.
+        // (Measured alternatives: a fence in every thread 10.6 ms; per-warp counting with the fence deferred to the next
+        // iteration 7.8 ms; this form 6.5 ms; the unordered k_scatter_all_quads 5.5 ms.)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(iter_cnt + k, 1) == (int)gridDim.x - 1) atomicMax(prog, k + 1);
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads, 4)
+k_reseed_project_trailing(int n_cells, int ppc, int reach, int slab_records, int n_producers, const int *prog, int *next_chunk,
+                          const int *__restrict__ old_start, const double2 *__restrict__ vertices, const CellGeom *__restrict__ geom,
+                          const double *__restrict__ centers, NodalVel vel, const unsigned long long *__restrict__ cell_mask,
+                          const int *__restrict__ stay, const int *__restrict__ arrive, const unsigned long long *__restrict__ packed_start,
+                          ParticleSoA dst, int *__restrict__ cell_start, double *__restrict__ partial, Counters *ctr)
+{
+    __shared__ int s_chunk;
+    const double *Vx, *Vy;
+    vel.resolve(Vx, Vy);
+    const int n_chunks = (n_cells + kTrailCells - 1) / kTrailCells;
+    const bool dead = ctr->overflow != 0; // the plan did not fit: only the segment table is written
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(next_chunk, 1);
+        __syncthreads();
+        const int chunk = s_chunk;
+        if (chunk >= n_chunks) break;
+        const int c0 = chunk * kTrailCells, c1 = min(c0 + kTrailCells, n_cells);
+        if (!dead) {
+            // wait until all source records of the old cells [0, c1 + reach) have been moved
+            const long long need_rec = __ldg(old_start + min((long long)c1 + reach, (long long)n_cells));
+            const long long need_slab = (need_rec + slab_records - 1) / slab_records; // slabs [0, need_slab) must be done
+            const int need_iter = (int)((need_slab + n_producers - 1) / n_producers);  // producer iterations that cover them
+            if (threadIdx.x == 0) {
+                const long long t0 = clock64();
+                for (;;) {
+                    int done;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(prog) : "memory");
+                    if (done >= need_iter) break;
+                    if (clock64() - t0 > (1ll << 32)) { // ~2 s without progress: fail loudly instead of hanging
+                        atomicExch(&ctr->overflow, 2);
+                        break;
+                    }
+                    __nanosleep(1000);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- re-seed (k_reseed) + segment table, one thread per cell ----
+        {
+            const int c = c0 + threadIdx.x;
+            if (c1 == n_cells && threadIdx.x == 0) cell_start[n_cells] = (int)(unsigned)(packed_start[n_cells] & 0xffffffffull);
+            if (c < c1) {
+                const int start = (int)(unsigned)(packed_start[c] & 0xffffffffull);
+                cell_start[c] = start;
+                if (!dead) {
+                    const int live = stay[c] + arrive[c];
+                    const int missing = (int)(unsigned)(packed_start[c + 1] & 0xffffffffull) - start - live;
+                    if (missing > 0) {
+                        const uint4 nn = __ldg(reinterpret_cast<const uint4 *>(&geom[c].n0));
+                        const double2 v0 = __ldg(&vertices[nn.x]), v1 = __ldg(&vertices[nn.y]), v2 = __ldg(&vertices[nn.z]);
+                        const double ax0 = __ldg(Vx + nn.x), ax1 = __ldg(Vx + nn.y), ax2 = __ldg(Vx + nn.z);
+                        const double ay0 = __ldg(Vy + nn.x), ay1 = __ldg(Vy + nn.y), ay2 = __ldg(Vy + nn.z);
+                        const unsigned long long mask = cell_mask[c];
+                        int d = start + live;
+                        for (int s = 0; s < ppc; ++s) {
+                            if ((mask >> s) & 1ull) continue;
+                            const double L0 = __ldg(&centers[3 * s]), L1 = __ldg(&centers[3 * s + 1]), L2 = __ldg(&centers[3 * s + 2]);
+                            dst.pos[d] = make_double2(to_global1(L0, L1, L2, v0.x, v1.x, v2.x), to_global1(L0, L1, L2, v0.y, v1.y, v2.y));
+                            dst.lab[d] = make_double2(L0, L1);
+                            st_tail(dst.tail + d, L2, (unsigned)c, (unsigned)d);
+                            dst.vel[d] = make_double2(interp3(L0, L1, L2, ax0, ax1, ax2), interp3(L0, L1, L2, ay0, ay1, ay2));
+                            ++d;
+                        }
+                    }
+                }
+            }
+        }
+        if (dead) continue;
+        __threadfence_block();
+        __syncthreads();
+        // ---- project (k_project_cells<G>): G lanes per cell, same summation order, records read through L2 (ld.cg) ----
+        const int lane = threadIdx.x & (G - 1);
+        for (int cw = c0 + (threadIdx.x / G); cw - (threadIdx.x / G) < c1; cw += kThreads / G) {
+            const int c = cw;
+            const bool valid = c < c1;
+            const int b = valid ? (int)(unsigned)(packed_start[c] & 0xffffffffull) : 0;
+            const int e = valid ? (int)(unsigned)(packed_start[c + 1] & 0xffffffffull) : 0;
+            double acc[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+            int i = b + lane;
+            for (; i + 3 * G < e; i += 4 * G) {
+                double2 l4[4], v4[4];
+                double z4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    l4[u] = __ldcg(&dst.lab[i + u * G]);
+                    v4[u] = __ldcg(&dst.vel[i + u * G]);
+                    z4[u] = __ldcg(&dst.tail[i + u * G].l2);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double Lu[3] = {l4[u].x, l4[u].y, z4[u]};
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        acc[3 * k + 0] = __dadd_rn(acc[3 * k + 0], __dmul_rn(Lu[k], v4[u].x));
+                        acc[3 * k + 1] = __dadd_rn(acc[3 * k + 1], __dmul_rn(Lu[k], v4[u].y));
+                        acc[3 * k + 2] = __dadd_rn(acc[3 * k + 2], Lu[k]);
+                    }
+                }
+            }
+            for (; i < e; i += G) {
+                const double2 la = __ldcg(&dst.lab[i]);
+                const double2 va = __ldcg(&dst.vel[i]);
+                const double La[3] = {la.x, la.y, __ldcg(&dst.tail[i].l2)};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    acc[3 * k + 0] = __dadd_rn(acc[3 * k + 0], __dmul_rn(La[k], va.x));
+                    acc[3 * k + 1] = __dadd_rn(acc[3 * k + 1], __dmul_rn(La[k], va.y));
+                    acc[3 * k + 2] = __dadd_rn(acc[3 * k + 2], La[k]);
+                }
+            }
+#pragma unroll
+            for (int d = G / 2; d > 0; d >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc[k] = __dadd_rn(acc[k], __shfl_xor_sync(0xffffffffu, acc[k], d, G));
+            }
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    if (lane == (k % G)) partial[9 * (size_t)c + k] = acc[k];
+            }
+        }
+    }
+}
+
 // One warp-tile of 32 particle records staged in shared memory by the copy engine (one bulk copy of 2 KB).
 struct __align__(128) ScatterStage {
     int4 rec[32][4]; // 32 whole particle records: [.][0] pos, [1] lab, [2] tail, [3] vel

@@ -73,6 +73,11 @@ typedef struct pfem2_options {
                                overlaps the move pass and the download of the projected field overlaps the projection, chunk by
                                chunk of the cell range (dependencies derived from the mesh numbering); 1 = no pipelining; n > 1 =
                                n chunks */
+    int fuse_project;       /* EXPERIMENTAL, 0 (default) = off.  1: on a single GPU in the fast order, advectParticles runs the
+                               projection's cell pass concurrently with its re-sort scatter, trailing it by the reach of a particle
+                               so that the freshly written records are read from L2 instead of HBM; projectVelocityOntoGrid then only
+                               gathers the per-cell sums (same arithmetic, same sums; any mutation in between recomputes them).
+                               Measured break-even on B200 (see pfem2_kernels.cuh), hence opt-in */
 } pfem2_options;
 
 /* counters of the last pfem2_advect call (device-resident, read back on demand) */

@@ -433,3 +433,26 @@ def test_pipelined_step_host_equals_the_three_calls(gpu, oracle, name, chunks):
         assert (sa["lost"], sa["added"], sa["movers"]) == (sb["lost"], sb["added"], sb["movers"]), f"step {s}"
         assert rel_inf(w[0].cpu().numpy(), hwx.numpy()) <= REL_TOL and rel_inf(w[1].cpu().numpy(), hwy.numpy()) <= REL_TOL
     assert_states_equal(ha.download(), hb.download(), name)
+
+
+@pytest.mark.parametrize("name", ["cyl3_l2", "channel_fast"])
+def test_trailing_projection_matches_oracle(gpu, oracle, name):
+    """pfem2_options.fuse_project (experimental): the projection's cell pass runs concurrently with the re-sort scatter
+    (producer / consumer kernels on two streams, progress counter, re-seeding inside the consumer) and
+    projectVelocityOntoGrid only gathers; particle set, counters and projected field must equal the oracle's, also when a
+    second projection or an eager correction follows."""
+    c = cases.build_case(name)
+    h, o = run_both(gpu, oracle, c.mesh, c.fx, c.fy, c.level, c.substeps, c.dt, 8, check_every=2, fuse_project=True)
+    f, w = dev_field(c)
+    w2 = (torch.zeros_like(f[0]), torch.zeros_like(f[0]))
+    h.project_velocity_onto_grid(w)
+    h.project_velocity_onto_grid(w2)  # partial sums are still valid: same bits
+    assert np.array_equal(w[0].cpu().numpy(), w2[0].cpu().numpy())
+    h.correct_particle_velocity(f, w)
+    h.get_particles()                  # forces the deferred correction: the sums must be recomputed
+    h.project_velocity_onto_grid(w2)
+    wx, wy = np.zeros_like(c.fx), np.zeros_like(c.fx)
+    o.project_velocity_onto_grid(wx, wy)
+    o.correct_particle_velocity(c.fx, c.fy, wx, wy)
+    o.project_velocity_onto_grid(wx, wy)
+    assert rel_inf(w2[0].cpu().numpy(), wx) <= REL_TOL and rel_inf(w2[1].cpu().numpy(), wy) <= REL_TOL

@@ -1257,6 +1257,11 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
 int pfem2_device_records(pfem2_handle *h, const void **d_records)
 {
     if (!h || !d_records) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    {   // the records expose the particle velocities: a deferred correction is applied first
+        const int rc = flush_correct(h);
+        if (rc) return rc;
+    }
     *d_records = h->soa[h->cur].records();
     return PFEM2_OK;
 }

@@ -1,0 +1,166 @@
+"""Parity at BASELINE.json's FULL sizes through size-independent properties (the oracle finishes only small cases in
+seconds): configs[2] = 1M triangles x 16/cell (16M particles) and configs[3] = 16M triangles x 16/cell (256M particles,
+one B200).  Everything is checked ON THE DEVICE through zero-copy views of the sorted record array, so no multi-GB
+download is needed:
+
+  * sortedness and segment-table consistency, every particle inside its cell (barycentrics in the +-2e-6 band, sum 1),
+  * conservation: count_after = count_before - lost + added at every step,
+  * idempotence: a step with a zero nodal field changes no position, moves and loses nobody, re-seeds nobody,
+  * partition of unity: projecting a uniform particle velocity gives back the constant at every node (<= 1e-12 relative),
+  * linearity of the projection in the particle velocities,
+  * a checksum of checksums: the order-independent column checksums of positions and local coordinates are identical
+    between the TMA-tile / quad kernels, the one-lane-per-record kernels, the stable order and the exact one-ring search
+    after the same steps (same particle SET bit for bit).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+SIZES = {"config3_channel1m": (1000, 500, 10.0, 5.0), "config4_channel16m": (4000, 2000, 20.0, 10.0)}
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required for -m gpu tests")
+    from gpupfem2_b200 import handler
+
+    return handler
+
+
+def columns(h):
+    from gpupfem2_b200 import io as pio
+
+    return pio.device_columns(h)
+
+
+def checksums(h):
+    """Order-independent checksum per 8-byte column of the record array (wrapping int64 sums) + the count."""
+    from gpupfem2_b200 import io as pio
+    import ctypes as C
+    from gpupfem2_b200.handler import _wrap_device
+
+    n = h.get_particle_count()
+    p = C.c_void_p()
+    h._check(h._L.pfem2_device_records(h._h, C.byref(p)), "device_records")
+    rec = _wrap_device(p.value, (n, 8), "<f8", h.mesh.device)
+    return [n] + [int(v) for v in rec.view(torch.int64).sum(dim=0).tolist()]
+
+
+def check_sorted_and_inside(h, dm):
+    c = columns(h)
+    cell = c["cell"].to(torch.int64)
+    n = cell.shape[0]
+    assert bool((cell[1:] >= cell[:-1]).all()), "records are not sorted by cell"
+    assert int(cell.min()) >= 0 and int(cell.max()) < dm.n_cells
+    start = h.cell_starts().to(torch.int64)
+    assert int(start[0]) == 0 and int(start[-1]) == n
+    counts = torch.bincount(cell, minlength=dm.n_cells)
+    assert torch.equal(counts, start[1:] - start[:-1]), "segment table does not match the records"
+    L0, L1, L2 = c["lab"][:, 0], c["lab"][:, 1], c["l2"]
+    lo, hi = -2e-6, 1.0 + 2e-6
+    for L in (L0, L1, L2):
+        assert bool(((L >= lo) & (L <= hi)).all()), "a particle sits outside the tolerance band of its cell"
+    assert float((L0 + L1 + L2 - 1.0).abs().max()) <= 4e-16 * 4
+    # the stored local position reproduces the stored global position (x = sum L_i x_i) to rounding
+    tri = dm.cells.to(torch.int64)[cell]
+    vx = dm.vertices[:, 0]
+    x = L0 * vx[tri[:, 0]] + L1 * vx[tri[:, 1]] + L2 * vx[tri[:, 2]]
+    assert float((x - c["pos"][:, 0]).abs().max()) <= 1e-9
+    return n
+
+
+@pytest.mark.parametrize("size", list(SIZES))
+def test_full_size_properties(gpu, size):
+    nx, ny, lx, ly = SIZES[size]
+    dm = gpu.device_structured_channel(nx, ny, lx, ly, colmajor=True)
+    y = dm.vertices[:, 1].contiguous()
+    F = ((4.0 * y * (ly - y) / (ly * ly)).contiguous(), torch.zeros_like(y))
+    Z = (torch.zeros_like(y), torch.zeros_like(y))
+    W = (torch.zeros_like(y), torch.zeros_like(y))
+    dt = 0.25 * (lx / nx) * 3
+    big = size.endswith("16m")
+    h = gpu.ParticleHandler2D(dm, 4, capacity_factor=1.2)
+    h.seed_particles()
+    assert h.get_particle_count() == 2 * nx * ny * 16
+    h.init_particle_velocity(F)
+    n = check_sorted_and_inside(h, dm)
+    for _ in range(3):  # conservation + invariants under real movement (outflow deletions, inflow re-seeding)
+        h.step(F, W, dt, 3)
+        st = h.stats()
+        assert st["count"] == n - st["lost"] + st["added"] and st["overflow"] == 0
+        n = st["count"]
+    assert check_sorted_and_inside(h, dm) == n
+    # a convex average of velocities in [0, 1], up to the +-2e-6 tolerance band of the barycentrics
+    assert bool(torch.isfinite(W[0]).all()) and float(W[0].max()) <= 1.0 + 1e-4 and float(W[0].min()) >= -1e-4
+
+    # idempotence: zero nodal field -> nobody moves, nothing is lost or added; positions, cells, ids and velocities keep
+    # their bits.  The local coordinates are re-derived from the position by the locate step (like kCheckParticleInCell),
+    # which changes the last bits of freshly seeded particles (their L came from the sub-cell centre table) -- once; a
+    # second zero step is then the identity on every column.
+    before = checksums(h)
+    h.correct_particle_velocity(F, F)  # zero increment (also exercises the deferred path)
+    h.advect_particles(Z, dt, 3)
+    st = h.stats()
+    assert (st["lost"], st["added"], st["movers"], st["count"]) == (0, 0, 0, n)
+    once = checksums(h)
+    keep = [0, 1, 2, 6, 7, 8]  # count, x, y, (cell, id), vx, vy
+    assert [once[k] for k in keep] == [before[k] for k in keep], "a zero-velocity step changed positions / cells / velocities"
+    h.advect_particles(Z, dt, 3)
+    assert checksums(h) == once, "the second zero-velocity step is not the identity"
+    check_sorted_and_inside(h, dm)
+
+    # partition of unity and linearity of the projection in the particle velocities.  initParticleVelocity ADDS the
+    # interpolated nodal field to every particle (kCorrectParticleVelocity with Vold = nullptr), so the properties are
+    # stated on increments: adding the constant (a, b) to every particle raises every projected nodal value by (a, b).
+    def projected():
+        h.project_velocity_onto_grid(W)
+        return W[0].clone(), W[1].clone()
+
+    a, b = 0.375, -1.25
+    P0 = projected()
+    h.init_particle_velocity((torch.full_like(y, a), torch.full_like(y, b)))
+    P1 = projected()
+    assert float((P1[0] - P0[0] - a).abs().max()) <= 4e-12 and float((P1[1] - P0[1] - b).abs().max()) <= 4e-12
+    if not big:
+        G = ((torch.sin(3.0 * dm.vertices[:, 0]) * 0.5).contiguous(), torch.cos(2.0 * y).contiguous())
+        h.init_particle_velocity(F)
+        P2 = projected()
+        h.init_particle_velocity(G)
+        P3 = projected()
+        h.init_particle_velocity((2.0 * F[0] - 3.0 * G[0], 2.0 * F[1] - 3.0 * G[1]))
+        P4 = projected()
+        for k in range(2):
+            lin = 2.0 * (P2[k] - P1[k]) - 3.0 * (P3[k] - P2[k])
+            assert float((P4[k] - P3[k] - lin).abs().max()) <= 2e-11
+    h.close()
+
+
+def test_checksum_of_checksums_between_kernel_variants(gpu):
+    """configs[2] size: the same three steps with the TMA-tile / quad kernels and with the one-lane-per-record kernels leave
+    the same particle SET bit for bit (order-independent column checksums of 16M records, computed on the device)."""
+    nx, ny, lx, ly = SIZES["config3_channel1m"]
+    dm = gpu.device_structured_channel(nx, ny, lx, ly, colmajor=True)
+    y = dm.vertices[:, 1].contiguous()
+    F = ((4.0 * y * (ly - y) / (ly * ly)).contiguous(), (0.05 * torch.sin(8.0 * dm.vertices[:, 0])).contiguous())
+    dt = 0.4 * (lx / nx) * 3
+    sums = []
+    for opts in ({}, {"lane_per_record": True}, {"stable_order": True}, {"exact_search": True}):
+        h = gpu.ParticleHandler2D(dm, 4, capacity_factor=1.2, **opts)
+        h.seed_particles()
+        h.init_particle_velocity(F)
+        W = (torch.zeros_like(y), torch.zeros_like(y))
+        for _ in range(3):
+            h.step(F, W, dt, 3)
+        cs = checksums(h)  # (pfem2_device_records applies the deferred correction first)
+        vsum = columns(h)["vel"].sum(dim=0).tolist()
+        # exact: count, x, y, L0, L1, L2 (the nodal field is frozen, so the trajectories do not depend on the slot order);
+        # column 5 holds (cell, id) and the ids of re-seeded particles are slot numbers; the velocities carry the projected
+        # field, whose last bits depend on the summation order inside a cell in the fast order -> compared to 1e-10
+        sums.append((cs[:6], h.stats()["lost"], h.stats()["added"], vsum))
+        h.close()
+    for s in sums[1:]:
+        assert s[:3] == sums[0][:3]
+        assert all(abs(a - b) <= 1e-10 * max(abs(a), 1.0) for a, b in zip(s[3], sums[0][3]))

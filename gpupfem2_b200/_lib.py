@@ -23,6 +23,7 @@ SYMBOLS = (
     "pfem2_mesh_inv_jacobi", "pfem2_mesh_one_ring", "pfem2_sort_pairs", "pfem2_kernel_launches", "pfem2_set_profiling",
     "pfem2_get_phase_times", "pfem2_set_owned_cells", "pfem2_advect_move", "pfem2_emigrants_count", "pfem2_emigrants_pack",
     "pfem2_immigrants_append", "pfem2_advect_finish", "pfem2_project_accumulate", "pfem2_project_finalize",
+    "pfem2_set_rank_bounds", "pfem2_emigrants_pack_neighbours", "pfem2_immigrants_append_device",
 )
 
 
@@ -90,6 +91,9 @@ def load():
     L.pfem2_emigrants_pack.argtypes = [vp, vp, C.c_longlong]
     L.pfem2_immigrants_append.argtypes = [vp, vp, i]
     L.pfem2_advect_finish.argtypes = [vp, vp, vp]
+    L.pfem2_set_rank_bounds.argtypes = [vp, C.POINTER(i), i]
+    L.pfem2_emigrants_pack_neighbours.argtypes = [vp, i, vp, vp, i]
+    L.pfem2_immigrants_append_device.argtypes = [vp, vp, i, i]
     L.pfem2_project_accumulate.argtypes = [vp, vp]
     L.pfem2_project_finalize.argtypes = [vp, vp, vp, vp]
     L.pfem2_set_profiling.argtypes = [vp, i]

@@ -282,6 +282,9 @@ int sync_counters(pfem2_handle *h)
         h->readback_pending = false;
         h->host_count = h->host_ctr->count;
         h->host_added = h->host_ctr->added;
+        if (h->host_ctr->overflow & kOverflowMigration)
+            return fail(h, PFEM2_ECAPACITY, "a migration buffer overflowed or a particle left for a non-adjacent strip (raise the migration "
+                                            "capacity / use wider strips); state is invalid");
         if (h->host_ctr->overflow) return fail(h, PFEM2_ECAPACITY, "particle capacity exceeded during advect; state is invalid");
     }
     return PFEM2_OK;
@@ -628,6 +631,22 @@ int advect_finish(pfem2_handle *h, NodalVel vel, int need_count)
         if ((rc = sync_counters(h))) return rc;
         printf("Particle handler contains %d particles\n", h->host_count); // particle_handler_2d.cu:341
     }
+    return PFEM2_OK;
+}
+
+// device + host copy of the strip bounds (cells [bounds[r], bounds[r + 1]) belong to rank r)
+int store_rank_bounds(pfem2_handle *h, const int *h_bounds, int n_ranks)
+{
+    if (h->mg_ranks != n_ranks) {
+        cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count);
+        h->mg_bounds = h->mg_rank_count = nullptr;
+        CU(cudaMalloc((void **)&h->mg_bounds, sizeof(int) * (n_ranks + 1)));
+        CU(cudaMalloc((void **)&h->mg_rank_count, sizeof(int) * (n_ranks + 1)));
+        h->mg_ranks = n_ranks;
+    }
+    h->mg_host_bounds.assign(h_bounds, h_bounds + n_ranks + 1);
+    // pageable host source: the copy is staged before the call returns, so the vector may change afterwards
+    CU(cudaMemcpyAsync(h->mg_bounds, h->mg_host_bounds.data(), sizeof(int) * (n_ranks + 1), cudaMemcpyHostToDevice, h->stream));
     return PFEM2_OK;
 }
 
@@ -1365,15 +1384,10 @@ int pfem2_emigrants_count(pfem2_handle *h, const int *h_bounds, int n_ranks, int
     if (h->mg_fused) { // different bounds than the move pass used: the statistics stand, the emigrants are searched the old way
         h->mg_fused_total = -1;
     }
-    if (h->mg_ranks != n_ranks) {
-        cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count);
-        h->mg_bounds = h->mg_rank_count = nullptr;
-        CU(cudaMalloc((void **)&h->mg_bounds, sizeof(int) * (n_ranks + 1)));
-        CU(cudaMalloc((void **)&h->mg_rank_count, sizeof(int) * (n_ranks + 1)));
-        h->mg_ranks = n_ranks;
+    {
+        const int rcb = store_rank_bounds(h, h_bounds, n_ranks);
+        if (rcb) return rcb;
     }
-    h->mg_host_bounds.assign(h_bounds, h_bounds + n_ranks + 1);
-    CU(cudaMemcpyAsync(h->mg_bounds, h_bounds, sizeof(int) * (n_ranks + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(h->mg_rank_count, 0, sizeof(int) * (n_ranks + 1), st));
     PFEM2_LAUNCH(k_emigrant_count, grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], h->ctr, h->own_lo, h->own_hi, h->mg_bounds,
                  n_ranks, h->mg_rank_count);
@@ -1427,6 +1441,64 @@ int pfem2_immigrants_append(pfem2_handle *h, const void *d_records, int n)
     }
     PFEM2_LAUNCH(k_add_count, 1, 1, 0, h->stream, h->ctr, n);
     h->host_count += n;
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int pfem2_set_rank_bounds(pfem2_handle *h, const int *h_bounds, int n_ranks)
+{
+    if (!h || !h_bounds || n_ranks < 1 || n_ranks > 64) return PFEM2_EINVAL;
+    if (h->move_pending) return fail(h, PFEM2_ESTATE, "set_rank_bounds between advect_move and advect_finish");
+    for (int r = 0; r < n_ranks; ++r)
+        if (h_bounds[r] > h_bounds[r + 1]) return fail(h, PFEM2_EINVAL, "rank bounds must be ascending");
+    CU(cudaSetDevice(h->device));
+    return store_rank_bounds(h, h_bounds, n_ranks);
+}
+
+int pfem2_emigrants_pack_neighbours(pfem2_handle *h, int rank, void *d_left, void *d_right, int capacity_records)
+{
+    if (h) h->partials_valid = false;
+    if (!h || capacity_records < 1 || rank < 0) return PFEM2_EINVAL;
+    if (!h->move_pending) return fail(h, PFEM2_ESTATE, "emigrants_pack_neighbours outside advect_move / advect_finish");
+    if (!h->mg_fused) // stable order, one-lane-per-record kernels or no rank bounds yet: use emigrants_count / emigrants_pack
+        return fail(h, PFEM2_ESTATE, "the move pass did not list its emigrants (call pfem2_set_rank_bounds before pfem2_advect_move; "
+                                     "fast order and TMA-tiled kernels only)");
+    if (rank >= h->mg_ranks) return fail(h, PFEM2_EINVAL, "rank outside the rank bounds");
+    if ((rank > 0 && !d_left) || (rank + 1 < h->mg_ranks && !d_right))
+        return fail(h, PFEM2_EINVAL, "a neighbour strip exists but its migration buffer is NULL");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (d_left) CU(cudaMemsetAsync(d_left, 0, sizeof(MigrationHeader), st));
+    if (d_right) CU(cudaMemsetAsync(d_right, 0, sizeof(MigrationHeader), st));
+    // the number of emigrants lives on the device (rank_count[n_ranks]): a fixed grid strides over the list
+    PFEM2_LAUNCH(k_emigrant_pack_nbr, grid_for(capacity_records, kThreads, g_num_sms * 2), kThreads, 0, st, h->soa[h->cur], h->keys[0],
+                 h->mg_rank_count, h->mg_ranks, h->mg_bounds, rank, (int4 *)d_left, (int4 *)d_right, capacity_records, h->ctr,
+                 h->cell_mask, h->own_hi, h->mesh.n_cells);
+    h->mg_fused_total = -1; // consumed
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int pfem2_immigrants_append_device(pfem2_handle *h, const void *d_buffer, int capacity_records, int from_left)
+{
+    if (h) h->partials_valid = false;
+    if (!h || !d_buffer || capacity_records < 1) return PFEM2_EINVAL;
+    if (!h->move_pending) return fail(h, PFEM2_ESTATE, "immigrants_append_device outside advect_move / advect_finish");
+    if (!h->mg_fused) return fail(h, PFEM2_ESTATE, "immigrants_append_device needs the fused move pass (see pfem2_emigrants_pack_neighbours)");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int4 *buf = (const int4 *)d_buffer;
+    const int grid = grid_for(capacity_records, kThreads, g_num_sms * 2);
+    PFEM2_LAUNCH(k_immigrant_append_dev, grid, kThreads, 0, st, h->soa[h->cur], h->ctr, buf, capacity_records);
+    const int C = h->mesh.n_cells;
+    const bool m64 = h->ppc > 32;
+#define PFEM2_CNTD(M, B)                                                                                                             \
+    PFEM2_LAUNCH((k_count_appended_dev<M, B>), grid, kThreads, 0, st, h->soa[h->cur], h->ctr, buf, capacity_records, C, h->ppc, h->level, \
+                 h->sub_step, h->stay, h->arrive, h->cell_mask)
+    if (h->opt.subcell_mode == 0) { if (m64) PFEM2_CNTD(0, true); else PFEM2_CNTD(0, false); }
+    else                          { if (m64) PFEM2_CNTD(1, true); else PFEM2_CNTD(1, false); }
+#undef PFEM2_CNTD
+    PFEM2_LAUNCH(k_add_count_dev, 1, 1, 0, st, h->ctr, buf, capacity_records, h->cell_mask, h->own_lo, h->own_hi, from_left ? 1 : 0);
     CU(cudaGetLastError());
     return PFEM2_OK;
 }

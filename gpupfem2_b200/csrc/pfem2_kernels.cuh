@@ -1271,6 +1271,126 @@ __global__ void k_add_count(Counters *ctr, int m)
     ctr->n_warps = (ctr->count + 31) >> 5;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Neighbour protocol of the strip partition: no host round trip between the move pass and the re-sort.
+// A migration buffer is  [64-byte header | cap 64-byte records]  of fixed capacity, so that the NCCL transfer needs no
+// size negotiation; the number of valid records travels in the header and is only ever read on the device.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) MigrationHeader {
+    int count;                   // records the sender wanted to pack (> cap: overflow, only cap of them are present)
+    int flags;                   // 1: the sender ran out of capacity; 2: an emigrant's destination was not an adjacent strip
+    int pad0[2];
+    unsigned long long spill[4]; // right-going only: occupancy words of the cells own_hi .. own_hi + 3 of the sender (SURVEY N4:
+                                 // the flat sub-cell index of a particle in the tolerance band lands in the next cell's word)
+    int pad1[4];
+};
+static_assert(sizeof(MigrationHeader) == sizeof(ParticleRec), "the header occupies exactly one record slot");
+constexpr int kOverflowMigration = 4; // Counters.overflow bit: migration buffer too small / non-adjacent destination
+
+// the move pass (k_advect_locate_tma) left the array indices of the emigrants in emig_idx and their number in
+// rank_count[n_ranks]; pack them for the left / right neighbour and remove them locally.  Headers are zeroed by the caller.
+__global__ void __launch_bounds__(kThreads)
+k_emigrant_pack_nbr(ParticleSoA p, const unsigned *__restrict__ emig_idx, const int *__restrict__ rank_count, int n_ranks,
+                    const int *__restrict__ bounds, int rank, int4 *out_left, int4 *out_right, int cap, Counters *ctr,
+                    const unsigned long long *__restrict__ cell_mask, int own_hi, int n_cells)
+{
+    const int n_emig = rank_count[n_ranks];
+    if (blockIdx.x == 0 && threadIdx.x < 4 && out_right) {
+        const int c = own_hi + (int)threadIdx.x;
+        reinterpret_cast<MigrationHeader *>(out_right)->spill[threadIdx.x] = c < n_cells ? cell_mask[c] : 0ull;
+    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_emig; j += gridDim.x * blockDim.x) {
+        const unsigned i = emig_idx[j];
+        const int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
+        const int dest = rank_of_cell((unsigned)t.z, bounds, n_ranks);
+        int4 *out = dest == rank - 1 ? out_left : (dest == rank + 1 ? out_right : nullptr);
+        st_cell(p.tail + i, kLostCell);
+        if (!out) { // more than one strip away in one step (or no such neighbour): the strips are too thin for this time step
+            atomicOr(&ctr->overflow, kOverflowMigration);
+            continue;
+        }
+        MigrationHeader *hd = reinterpret_cast<MigrationHeader *>(out);
+        const int slot = atomicAdd(&hd->count, 1);
+        if (slot >= cap) {
+            atomicOr(&hd->flags, 1);
+            atomicOr(&ctr->overflow, kOverflowMigration);
+            continue;
+        }
+        int4 *rec = out + 4 * ((size_t)slot + 1);
+        rec[0] = *reinterpret_cast<const int4 *>(p.pos + i);
+        rec[1] = *reinterpret_cast<const int4 *>(p.lab + i);
+        rec[2] = t;
+        rec[3] = *reinterpret_cast<const int4 *>(p.vel + i);
+    }
+}
+
+__device__ __forceinline__ int migration_count(const int4 *buf, int cap)
+{
+    return min(max(reinterpret_cast<const MigrationHeader *>(buf)->count, 0), cap);
+}
+
+// immigrants of one received migration buffer, appended behind the current array (count taken from the header)
+__global__ void __launch_bounds__(kThreads)
+k_immigrant_append_dev(ParticleSoA p, const Counters *ctr, const int4 *__restrict__ buf, int cap)
+{
+    const int m = migration_count(buf, cap), n = ctr->count;
+    if ((long long)n + m > ctr->capacity) return; // k_add_count_dev raises the overflow flag
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const int4 *rec = buf + 4 * ((size_t)j + 1);
+        *reinterpret_cast<int4 *>(p.pos + (n + j)) = rec[0];
+        *reinterpret_cast<int4 *>(p.lab + (n + j)) = rec[1];
+        *reinterpret_cast<int4 *>(p.tail + (n + j)) = rec[2];
+        *reinterpret_cast<int4 *>(p.vel + (n + j)) = rec[3];
+    }
+}
+
+// per-cell statistics of those records (all "arrived"), like k_count_appended
+template <int SUBCELL_MODE, bool MASK64>
+__global__ void __launch_bounds__(kThreads)
+k_count_appended_dev(ParticleSoA p, const Counters *ctr, const int4 *__restrict__ buf, int cap, int n_cells, int ppc, int level,
+                     double sub_step, int *__restrict__ stay, int *__restrict__ arrive, unsigned long long *__restrict__ cell_mask)
+{
+    const int m = migration_count(buf, cap), n0 = ctr->count;
+    if ((long long)n0 + m > ctr->capacity) return;
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < m; base += gridDim.x * blockDim.x) {
+        const int j = base + lane;
+        bool live = false;
+        unsigned c = 0;
+        double L0 = 0, L1 = 0, L2 = 0;
+        if (j < m) {
+            const ParticleTail tl = ld_tail(p.tail + (n0 + j));
+            c = tl.cell;
+            live = c != kLostCell;
+            const double2 lab = p.lab[n0 + j];
+            L0 = lab.x;
+            L1 = lab.y;
+            L2 = tl.l2;
+        }
+        const unsigned mb = __ballot_sync(0xffffffffu, live);
+        accumulate_cell_stats<SUBCELL_MODE, MASK64>(live, c, L0, L1, L2, 0u, mb, lane, n_cells, ppc, level, sub_step, stay, arrive, cell_mask);
+    }
+}
+
+// one thread: the array grows by the appended records; the left neighbour's spilled occupancy bits join this strip's first cells
+__global__ void k_add_count_dev(Counters *ctr, const int4 *__restrict__ buf, int cap, unsigned long long *__restrict__ cell_mask,
+                                int own_lo, int own_hi, int from_left)
+{
+    const MigrationHeader *hd = reinterpret_cast<const MigrationHeader *>(buf);
+    int m = migration_count(buf, cap);
+    if (hd->count > cap || hd->count < 0 || hd->flags) ctr->overflow |= kOverflowMigration;
+    if ((long long)ctr->count + m > ctr->capacity) {
+        ctr->overflow |= 1;
+        m = 0;
+    }
+    ctr->count += m;
+    ctr->n_old = ctr->count;
+    ctr->n_warps = (ctr->count + 31) >> 5;
+    if (from_left)
+        for (int k = 0; k < 4; ++k)
+            if (own_lo + k < own_hi && hd->spill[k]) cell_mask[own_lo + k] |= hd->spill[k];
+}
+
 // projection, multi-GPU flavour: per-node accumulators {sum L v_x, sum L v_y, sum L} without the division, so that the
 // contributions of the strips sharing an interface node can be added before kFinalizeVelocityProjection's division
 __global__ void __launch_bounds__(kThreads)

@@ -86,12 +86,40 @@ def exchange_records(send_buf: torch.Tensor, send_counts, group=None):
     return recv_buf, recv_counts
 
 
+def migration_capacity(n_interface_nodes: int, ppc: int, columns: int = 12, floor: int = 16384) -> int:
+    """Default record capacity of one migration buffer of the neighbour protocol: the nominal population of `columns`
+    cell layers along the interface (a layer has about n_interface_nodes cells), i.e. room for every particle within
+    several cells of the interface to leave in one step even after the density has grown."""
+    return max(int(floor), int(columns) * int(n_interface_nodes) * int(ppc))
+
+
+def exchange_neighbours(send_left, send_right, recv_left, recv_right, rank: int, world: int, group=None):
+    """Neighbour protocol: hand the fixed-size migration buffers ([header | capacity records], (cap + 1, 8) float64) to the
+    adjacent strips.  No sizes are negotiated and nothing is read on the host: the record count travels in the header.
+    On return the current stream waits for the receives (CUDA) / the receives are complete (CPU)."""
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, send_left, rank - 1, group=group))
+        ops.append(dist.P2POp(dist.irecv, recv_left, rank - 1, group=group))
+    if rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, send_right, rank + 1, group=group))
+        ops.append(dist.P2POp(dist.irecv, recv_right, rank + 1, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def header_count(buf: torch.Tensor) -> torch.Tensor:
+    """Record count in the header of a migration buffer (a 0-d int32 tensor on the buffer's device; no synchronisation)."""
+    return buf[0, :1].view(torch.int32)[0]
+
+
 def exchange_interface(acc3: torch.Tensor, iface: dict, group=None):
     """Add the neighbours' accumulators of the shared nodes into acc3 (N, 3), in place."""
     if not iface:
         return
     ops, recv = [], {}
-    send = {r: acc3[idx].contiguous() for r, idx in iface.items()}
+    send = {r: torch.index_select(acc3, 0, idx) for r, idx in iface.items()}
     for r in sorted(iface):
         recv[r] = torch.empty_like(send[r])
         ops.append(dist.P2POp(dist.isend, send[r], r, group=group))
@@ -99,7 +127,9 @@ def exchange_interface(acc3: torch.Tensor, iface: dict, group=None):
     for w in dist.batch_isend_irecv(ops):
         w.wait()
     for r in sorted(iface):
-        acc3[iface[r]] += recv[r]  # two contributions per shared node: a + b == b + a bit for bit
+        # the node ids of one interface are unique, so this is one plain addition per entry; two contributions per shared
+        # node: a + b == b + a bit for bit
+        acc3.index_add_(0, iface[r], recv[r])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -108,7 +138,7 @@ def exchange_interface(acc3: torch.Tensor, iface: dict, group=None):
 class DistributedParticleHandler2D:
     """ParticleHandler2D interface over a strip partition; same method names as handler.ParticleHandler2D."""
 
-    def __init__(self, mesh, cell_division_level, bounds, rank, world, group=None, **opts):
+    def __init__(self, mesh, cell_division_level, bounds, rank, world, group=None, migration="neighbour", migration_cap=0, **opts):
         from . import _lib, handler
 
         self._lib = _lib
@@ -120,8 +150,32 @@ class DistributedParticleHandler2D:
         self.h._check(self.L.pfem2_set_owned_cells(self.h._h, int(self.bounds[rank]), int(self.bounds[rank + 1])), "set_owned_cells")
         self.iface = interface_nodes(mesh.cells.view(torch.int32), self.bounds, rank)
         self.acc3 = torch.zeros((mesh.n_nodes, 3), dtype=torch.float64, device=mesh.device)
-        self.last_sent = 0
+        self._sent = 0
         self.last_received = 0
+        # neighbour protocol (default where the library supports it: fast order, TMA-tiled move pass): fixed-size migration
+        # buffers to / from the adjacent strips, counts stay on the device -> no host round trip inside advect_particles
+        self.protocol = os.environ.get("PFEM2_MG_PROTOCOL", migration)  # env: A/B measurements
+        if self.protocol not in ("neighbour", "exact"):
+            raise ValueError("migration must be 'neighbour' or 'exact'")
+        if opts.get("stable_order") or opts.get("lane_per_record") or os.environ.get("PFEM2_MG_FUSED") == "0":
+            self.protocol = "exact"  # the move pass lists its emigrants only in the default kernels
+        self._nbr = None
+        if self.protocol == "neighbour":
+            n_if = max([int(v.numel()) for v in self.iface.values()] or [1])
+            self.migration_cap = int(migration_cap) if migration_cap else migration_capacity(n_if, self.h.particles_per_cell)
+            shape = (self.migration_cap + 1, RECORD_DOUBLES)
+            mk = lambda: torch.zeros(shape, dtype=torch.float64, device=mesh.device)  # noqa: E731
+            self._nbr = {"sl": mk() if rank > 0 else None, "rl": mk() if rank > 0 else None,
+                         "sr": mk() if rank + 1 < world else None, "rr": mk() if rank + 1 < world else None}
+            self.h._check(self.L.pfem2_set_rank_bounds(self.h._h, self.bounds.ctypes.data_as(C.POINTER(C.c_int)), self.world),
+                          "set_rank_bounds")
+
+    @property
+    def last_sent(self):
+        """Particles this rank handed over in the last advect (neighbour protocol: read from the device on demand)."""
+        if self._nbr is not None and self._sent is None:
+            self._sent = sum(int(header_count(b).item()) for b in (self._nbr["sl"], self._nbr["sr"]) if b is not None)
+        return self._sent
 
     def seed_particles(self):
         self.h.seed_particles()
@@ -132,6 +186,20 @@ class DistributedParticleHandler2D:
     def advect_particles(self, vel, time_step, particle_substeps):
         h, L = self.h, self.L
         h._check(L.pfem2_advect_move(h._h, vel[0].data_ptr(), vel[1].data_ptr(), time_step, particle_substeps), "advect_move")
+        if self._nbr is not None:
+            # everything below is enqueued without waiting for the device: the library works on the legacy default stream, which
+            # is torch's current stream here, and torch orders the NCCL transfers against it (w.wait() is a stream-side wait)
+            b = self._nbr
+            ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+            h._check(L.pfem2_emigrants_pack_neighbours(h._h, self.rank, ptr(b["sl"]), ptr(b["sr"]), self.migration_cap), "emigrants_pack_neighbours")
+            exchange_neighbours(b["sl"], b["sr"], b["rl"], b["rr"], self.rank, self.world, self.group)
+            if b["rl"] is not None:
+                h._check(L.pfem2_immigrants_append_device(h._h, b["rl"].data_ptr(), self.migration_cap, 1), "immigrants_append_device")
+            if b["rr"] is not None:
+                h._check(L.pfem2_immigrants_append_device(h._h, b["rr"].data_ptr(), self.migration_cap, 0), "immigrants_append_device")
+            h._check(L.pfem2_advect_finish(h._h, vel[0].data_ptr(), vel[1].data_ptr()), "advect_finish")
+            self._sent = None  # read from the send headers on demand
+            return
         counts = (C.c_int * self.world)()
         h._check(L.pfem2_emigrants_count(h._h, self.bounds.ctypes.data_as(C.POINTER(C.c_int)), self.world, counts), "emigrants_count")
         send_counts = [int(c) for c in counts]
@@ -144,7 +212,7 @@ class DistributedParticleHandler2D:
             h._check(L.pfem2_immigrants_append(h._h, recv_buf.data_ptr(), recv_buf.shape[0]), "immigrants_append")
         h._check(L.pfem2_advect_finish(h._h, vel[0].data_ptr(), vel[1].data_ptr()), "advect_finish")
         self._keep = (send_buf, recv_buf)
-        self.last_sent, self.last_received = sum(send_counts), sum(recv_counts)
+        self._sent, self.last_received = sum(send_counts), sum(recv_counts)
 
     def project_velocity_onto_grid(self, vel):
         h, L = self.h, self.L
@@ -221,11 +289,11 @@ def bench_main(args, rank, world, local):
     for _ in range(args.steps):
         h.step(F, W, dt, args.substeps)
         counts.append(h.get_particle_count())
-        sent += h.last_sent
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
     ms = e0.elapsed_time(e1)
+    sent = h.last_sent * args.steps  # the last step's hand-over (read outside the timed region), steady state
     clocks = sampler.stop() if sampler else None
     phases = h.h.phase_times(reset=True)
     launches = handler.kernel_launches() - launches0
@@ -252,7 +320,11 @@ def bench_main(args, rank, world, local):
                        "particles_mean": psteps / args.steps, "cells": dm.n_cells, "nodes": dm.n_nodes, "substeps": args.substeps, "dt": dt,
                        "l2": "inputs larger than L2", "timing": "CUDA events on rank-local default stream, max over ranks, barrier on both sides",
                        "migrated_particles_per_step": float(tsum[2]) / args.steps,
-                       "collectives": "all_to_all_single (counts, 64-byte particle records) + pairwise isend/irecv of interface-node accumulators (NCCL)"},
+                       "migration_protocol": h.protocol,
+                       "collectives": ("fixed-size migration buffers [header | records] to / from the adjacent strips (ncclSend / ncclRecv, counts stay "
+                                       "on the device: no host round trip)" if h.protocol == "neighbour" else
+                                       "all_to_all_single (counts, 64-byte particle records)") +
+                                      " + pairwise isend/irecv of interface-node accumulators (NCCL)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "alg_bytes_per_particle": bench.ALG_BYTES[dom], "note": "rank 0, per GPU",
                          "step": {"achieved": bench.ALG_BYTES_STEP * value / 1e9 / world, "frac": bench.ALG_BYTES_STEP * value / 1e9 / world / peak,
@@ -260,7 +332,7 @@ def bench_main(args, rank, world, local):
                          "phases": {k: {"ms_per_step": v[0] / args.steps} for k, v in phases.items()}},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * world,
                     "note": "multi-GPU steps run through the public DistributedParticleHandler2D API; per step each rank reads back its "
-                            "emigrant counts and particle count (host sync), nodal fields stay device-resident"},
+                            "particle count (one host sync), nodal fields stay device-resident"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out))

@@ -158,6 +158,22 @@ int pfem2_emigrants_count(pfem2_handle *h, const int *h_bounds, int n_ranks, int
 int pfem2_emigrants_pack(pfem2_handle *h, void *d_records, long long capacity_records);
 int pfem2_immigrants_append(pfem2_handle *h, const void *d_records, int n);
 int pfem2_advect_finish(pfem2_handle *h, const double *d_vx, const double *d_vy);
+/* Neighbour protocol: the same exchange without any host round trip (strips only exchange with adjacent strips).
+ * A migration buffer is  [64-byte header | capacity_records 64-byte records]  in device memory, of a capacity both sides
+ * agree on, so that the transfer (ncclSend / ncclRecv of the whole buffer) needs no size negotiation; the number of valid
+ * records travels in the header and is only read on the device.  Header: { int count; int flags; int pad[2];
+ * unsigned long long spill[4]; int pad[4]; } -- `spill` carries the sub-cell occupancy bits that particles in the tolerance band
+ * of this strip's last cells put into the next strip's first cells, so re-seeding decisions match a single GPU.
+ *   set_rank_bounds (once, before the first advect_move) ; advect_move ; emigrants_pack_neighbours ; <send / recv the buffers> ;
+ *   immigrants_append_device (per received buffer) ; advect_finish
+ * Requires the default kernels (fast order, TMA-tiled move pass): otherwise emigrants_pack_neighbours returns PFEM2_ESTATE and
+ * the caller uses emigrants_count / emigrants_pack.  An overflowing buffer or an emigrant bound for a non-adjacent strip sets
+ * the sticky overflow flag: the next call that synchronises the counters fails with PFEM2_ECAPACITY. */
+int pfem2_set_rank_bounds(pfem2_handle *h, const int *h_bounds, int n_ranks);
+/* d_left / d_right: migration buffers for rank - 1 / rank + 1 (NULL where there is no such strip) */
+int pfem2_emigrants_pack_neighbours(pfem2_handle *h, int rank, void *d_left, void *d_right, int capacity_records);
+/* from_left != 0: the buffer came from rank - 1 (its spill words are OR-ed into this strip's first cells) */
+int pfem2_immigrants_append_device(pfem2_handle *h, const void *d_buffer, int capacity_records, int from_left);
 /* d_acc3: n_nodes x {sum L v_x, sum L v_y, sum L} of the particles this handle holds (no division) */
 int pfem2_project_accumulate(pfem2_handle *h, double *d_acc3);
 int pfem2_project_finalize(pfem2_handle *h, const double *d_acc3, double *d_vx, double *d_vy);

@@ -31,10 +31,13 @@ def main():
     fy = (-0.3 * torch.cos(k * x) * torch.sin(k * y)).contiguous()
     dt = 0.25 * (6.0 / nx) * S
     F = (fx, fy)
-    for stable in (False, True):
+    # fast order with the neighbour protocol (default: fixed-size buffers, no host round trip), fast order with the exact-size
+    # protocol, deterministic order (exact-size protocol)
+    for stable, protocol in ((False, "neighbour"), (False, "exact"), (True, "exact")):
         W = (torch.zeros_like(fx), torch.zeros_like(fx))
         bounds = multi_gpu.strip_bounds(dm.n_cells, world, align=2 * ny)
-        h = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world, stable_order=stable)
+        h = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world, migration=protocol, stable_order=stable)
+        assert h.protocol == protocol, (h.protocol, protocol)
         h.seed_particles()
         h.init_particle_velocity(F)
         moved = 0
@@ -58,12 +61,12 @@ def main():
             for g in gathered[1:]:
                 merged = {kk: np.concatenate([merged[kk], g[0][kk]]) for kk in merged}
             assert merged["x"].shape[0] == total == ref.get_particle_count(), (merged["x"].shape[0], total, ref.get_particle_count())
-            assert_states_equal(merged, ref.download(), f"{world} GPUs vs 1 GPU (stable={stable})")
+            assert_states_equal(merged, ref.download(), f"{world} GPUs vs 1 GPU (stable={stable}, {protocol})")
             assert sum(g[4] for g in gathered) > 0
             rwx, rwy = RW[0].cpu().numpy(), RW[1].cpu().numpy()
             for (_, wx, wy, m, _) in gathered:
                 assert rel_inf(wx[m], rwx[m]) <= REL_TOL and rel_inf(wy[m], rwy[m]) <= REL_TOL
-            print(f"MG_OK world={world} stable={stable} particles={total} migrated={sum(g[4] for g in gathered)}")
+            print(f"MG_OK world={world} stable={stable} protocol={protocol} particles={total} migrated={sum(g[4] for g in gathered)}")
             ref.close()
         h.close()
         dist.barrier()

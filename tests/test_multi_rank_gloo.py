@@ -1,4 +1,4 @@
-"""world_size-2 CPU tests (gloo) of the multi-GPU host logic in gpupfem2_b200/multi_gpu.py: strip partition,
+"""world_size-2 and -3 CPU tests (gloo) of the multi-GPU host logic in gpupfem2_b200/multi_gpu.py: strip partition,
 interface node lists, particle migration (all_to_all of 64-byte records) and the projection halo sum.  The compute on
 each rank is the CPU oracle; the result must equal the single-rank oracle on the same global problem:
 owner cells / positions / local coordinates bit-exact, velocities and nodal field within 1e-12."""
@@ -50,7 +50,16 @@ def problem():
     return m, fx, fy, 3, 3, 0.2, 12
 
 
-def worker(rank, world, port, out):
+def pack_neighbour_buffer(buf, rec):
+    """[64-byte header | cap records]: count in the first 32-bit word of the header (the layout of csrc MigrationHeader)."""
+    buf.zero_()
+    buf[0, :1].view(torch.int32)[0] = rec.shape[0]
+    assert rec.shape[0] <= buf.shape[0] - 1, "migration buffer too small for the test"
+    if rec.shape[0]:
+        buf[1:1 + rec.shape[0]] = torch.from_numpy(rec)
+
+
+def worker(rank, world, port, out, protocol="exact"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -79,11 +88,26 @@ def worker(rank, world, port, out):
             idx = np.nonzero(owner == r)[0] if r != rank else np.empty(0, dtype=np.int64)
             send_counts.append(idx.size)
             parts.append(to_records(s, idx))
-        send = torch.from_numpy(np.concatenate(parts) if parts else np.empty((0, 8)))
-        recv, recv_counts = multi_gpu.exchange_records(send, send_counts)
         migrated += sum(send_counts)
+        if protocol == "exact":
+            send = torch.from_numpy(np.concatenate(parts) if parts else np.empty((0, 8)))
+            recv, recv_counts = multi_gpu.exchange_records(send, send_counts)
+            arrived = recv.numpy()
+        else:  # neighbour protocol: fixed-size buffers to / from the adjacent strips, the count travels in the header
+            assert all(n == 0 for r, n in enumerate(send_counts) if abs(r - rank) != 1), "emigrant bound for a non-adjacent strip"
+            cap = multi_gpu.migration_capacity(max(int(v.numel()) for v in iface.values()), level * level, floor=64)
+            mk = lambda: torch.zeros((cap + 1, multi_gpu.RECORD_DOUBLES), dtype=torch.float64)  # noqa: E731
+            sl, rl = (mk(), mk()) if rank > 0 else (None, None)
+            sr, rr = (mk(), mk()) if rank + 1 < world else (None, None)
+            if sl is not None:
+                pack_neighbour_buffer(sl, parts[rank - 1])
+            if sr is not None:
+                pack_neighbour_buffer(sr, parts[rank + 1])
+            multi_gpu.exchange_neighbours(sl, sr, rl, rr, rank, world)
+            got = [b[1:1 + int(multi_gpu.header_count(b))].numpy() for b in (rl, rr) if b is not None]
+            arrived = np.concatenate(got) if got else np.empty((0, 8))
         local = {k: v[stay] for k, v in s.items()}
-        o.upload(concat(local, from_records(recv.numpy())))
+        o.upload(concat(local, from_records(arrived)))
         o.check_distribution(fx, fy, lo, hi)
         acc = torch.from_numpy(o.project_accumulate())
         multi_gpu.exchange_interface(acc, iface)
@@ -123,14 +147,20 @@ def test_interface_nodes_are_the_shared_column():
             assert nodes.tolist() == [col * 7 + j for j in range(7)]
 
 
-def test_two_rank_step_equals_single_rank(tmp_path, oracle):
+def test_migration_capacity_default():
+    assert multi_gpu.migration_capacity(2001, 16) == 12 * 2001 * 16  # channel16m: 24.6 MB per direction
+    assert multi_gpu.migration_capacity(7, 4) == 16384  # floor for small meshes
+
+
+@pytest.mark.parametrize("world,protocol", [(2, "exact"), (2, "neighbour"), (3, "neighbour")])
+def test_multi_rank_step_equals_single_rank(tmp_path, oracle, world, protocol):
     import socket
 
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
     out = str(tmp_path / "gathered.pt")
-    mp.spawn(worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(worker, args=(world, port, out, protocol), nprocs=world, join=True)
     gathered = torch.load(out, weights_only=False)
 
     from helpers import REL_TOL, assert_states_equal, rel_inf
@@ -145,7 +175,7 @@ def test_two_rank_step_equals_single_rank(tmp_path, oracle):
     merged = gathered[0][0]
     for g in gathered[1:]:
         merged = concat(merged, g[0])
-    assert_states_equal(merged, ref.download(), "2 ranks vs 1 rank")
+    assert_states_equal(merged, ref.download(), f"{world} ranks vs 1 rank ({protocol})")
     assert sum(g[4] for g in gathered) > 0, "no particle crossed the interface: the test would prove nothing"
     for (_, wx, wy, mine, _) in gathered:
         assert rel_inf(wx[mine], rwx[mine]) <= REL_TOL and rel_inf(wy[mine], rwy[mine]) <= REL_TOL

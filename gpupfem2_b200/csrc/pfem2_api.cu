@@ -48,6 +48,9 @@ struct pfem2_handle {
     int *own_len_dev = nullptr;              // device int: own_hi - own_lo (scan length)
     int *node_list = nullptr;                // nodes of the owned cells (nullptr = all nodes), multi-GPU
     int n_node_list = 0;
+    int own_node_lo = 0, own_node_hi = 0;    // node id range of the owned cells: what a deferred correction can touch
+    int v2_node_lo = 0, v2_node_hi = 0;      // node id range of the cells a particle of the owned range can reach in one advect call
+    int v2_range_substeps = -1;              // ... computed for this many substeps (-1: not yet)
     int *mg_bounds = nullptr;                // device copy of the rank cell bounds (n_ranks + 1)
     int *mg_rank_count = nullptr;            // device, per destination rank
     int mg_ranks = 0;
@@ -327,6 +330,47 @@ int mesh_band(pfem2_handle *h)
     return PFEM2_OK;
 }
 
+// node id range [lo, hi) of the cells [cell_lo, cell_hi) (one small kernel + an 8-byte read-back; multi-GPU set-up only)
+int node_range_of_cells(pfem2_handle *h, int cell_lo, int cell_hi, int &lo, int &hi)
+{
+    lo = hi = 0;
+    if (cell_hi <= cell_lo) return PFEM2_OK;
+    int *dev = nullptr;
+    const int init[2] = {0x7fffffff, -1};
+    int out[2] = {0, 0};
+    CU(cudaMalloc((void **)&dev, 2 * sizeof(int)));
+    CU(cudaMemcpyAsync(dev, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    PFEM2_LAUNCH(k_node_minmax, grid_for(cell_hi - cell_lo, kThreads, 1 << 30), kThreads, 0, h->stream, cell_lo, cell_hi, h->geom, dev);
+    CU(cudaMemcpyAsync(out, dev, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(dev);
+    if (out[1] >= out[0]) {
+        lo = out[0];
+        hi = out[1] + 1;
+    }
+    return PFEM2_OK;
+}
+
+// Multi-GPU: the nodal arrays the move pass gathers from (interleaved velocity v2) only need the nodes of the cells a particle
+// of the owned range can reach in one call: its cell index changes by at most the band width of the one-ring lists per substep.
+int ensure_v2_node_range(pfem2_handle *h, int substeps)
+{
+    const int C = h->mesh.n_cells;
+    if (h->own_lo == 0 && h->own_hi == C) {
+        h->v2_node_lo = 0;
+        h->v2_node_hi = h->mesh.n_nodes;
+        return PFEM2_OK;
+    }
+    if (h->v2_range_substeps == substeps) return PFEM2_OK;
+    int rc;
+    if ((rc = mesh_band(h))) return rc;
+    const long long reach = (long long)h->band * substeps;
+    const int c0 = (int)std::max<long long>(0, h->own_lo - reach), c1 = (int)std::min<long long>(C, h->own_hi + reach);
+    if ((rc = node_range_of_cells(h, c0, c1, h->v2_node_lo, h->v2_node_hi))) return rc;
+    h->v2_range_substeps = substeps;
+    return PFEM2_OK;
+}
+
 bool trailing_projection_enabled(const pfem2_handle *h, bool reseed, bool stable)
 {
     return h->opt.fuse_project == 1 && reseed && !stable && h->opt.lane_per_record == 0 && !h->opt.scatter_tma && h->own_lo == 0 &&
@@ -480,7 +524,9 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
                  h->warp_movers, h->stay, h->opt.stable_order ? h->arrive : (int *)nullptr, h->cell_mask, do_count, h->dv_pending ? h->dv2 : nullptr, h->own_lo, h->own_hi,          \
                  h->mg_bounds, h->mg_ranks, h->mg_rank_count, h->mg_fused ? h->keys[0] : (unsigned *)nullptr, cstart, c_lo, c_hi)
         if (!h->pipe.active) {
-            PFEM2_LAUNCH(k_pack_nodal, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, 0, N, vel, h->v2);
+            (void)N;
+            const int n0 = h->v2_node_lo, n1 = h->v2_node_hi; // all nodes on a single GPU; a strip's reach otherwise
+            if (n1 > n0) PFEM2_LAUNCH(k_pack_nodal, grid_for(n1 - n0, kThreads, 1 << 30), kThreads, 0, h->stream, n0, n1, vel, h->v2);
             const int grid = grid_for(h->capacity, kThreads, g_num_sms * 4); // persistent: 4 resident blocks per SM
             if (substeps == 3)
                 PFEM2_ADV_TMA(3);
@@ -568,6 +614,7 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     if (advect_tma_enabled(h)) {
         if ((rc = record_tensor_map(h, h->cur))) return rc;
         if (!h->v2) CU(cudaMalloc((void **)&h->v2, sizeof(double2) * (size_t)h->mesh.n_nodes));
+        if ((rc = ensure_v2_node_range(h, substeps))) return rc;
     }
     {
         PhaseScope ps(h, PFEM2_PHASE_ADVECT);
@@ -740,8 +787,11 @@ int do_correct(pfem2_handle *h, NodalVel v, NodalVel vold, bool has_old)
         if (!d) CU(cudaMalloc((void **)&d, sizeof(double) * (size_t)N));
     if (!h->dv2) CU(cudaMalloc((void **)&h->dv2, sizeof(double2) * (size_t)N));
     PhaseScope ps(h, PFEM2_PHASE_CORRECT);
-    PFEM2_LAUNCH(k_snapshot_dv, grid_for(N, kThreads, 1 << 30), kThreads, 0, h->stream, N, v, vold, has_old ? 1 : 0, h->dv[0], h->dv[1],
-                 h->dv2);
+    // the increment is only ever read at the nodes of owned cells (the particles this handle holds at the next move pass)
+    const int n0 = h->own_node_lo, n1 = h->own_node_hi;
+    if (n1 > n0)
+        PFEM2_LAUNCH(k_snapshot_dv, grid_for(n1 - n0, kThreads, 1 << 30), kThreads, 0, h->stream, n0, n1, v, vold, has_old ? 1 : 0, h->dv[0],
+                     h->dv[1], h->dv2);
     CU(cudaGetLastError());
     h->dv_pending = true;
     return PFEM2_OK;
@@ -838,6 +888,8 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
     while ((1ll << h->key_bits) <= C) ++h->key_bits; // keys 0..C (C = lost)
     h->own_lo = 0;
     h->own_hi = C;
+    h->own_node_lo = h->v2_node_lo = 0;
+    h->own_node_hi = h->v2_node_hi = mesh->n_nodes;
 
     // sub-cell centres (:248-274), host arithmetic without contraction
     std::vector<double> cen(3 * (size_t)h->ppc);
@@ -1356,6 +1408,14 @@ int pfem2_set_owned_cells(pfem2_handle *h, int cell_lo, int cell_hi)
     }
     cudaFree(flag); cudaFree(pos); cudaFree(scratch); cudaFree(n_dev);
     CU(cudaGetLastError());
+    h->v2_range_substeps = -1;
+    if (own_n < h->mesh.n_cells) {
+        const int rcn = node_range_of_cells(h, cell_lo, cell_hi, h->own_node_lo, h->own_node_hi);
+        if (rcn) return rcn;
+    } else {
+        h->own_node_lo = 0;
+        h->own_node_hi = N;
+    }
     return PFEM2_OK;
 }
 

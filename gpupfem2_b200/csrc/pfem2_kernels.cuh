@@ -524,6 +524,24 @@ __global__ void __launch_bounds__(kThreads) k_pack_nodal(int node_lo, int node_h
     if (i < node_hi) V2[i] = make_double2(Vx[i], Vy[i]);
 }
 
+// smallest / largest node id of the cells [cell_lo, cell_hi): out[0] = min (start INT_MAX), out[1] = max (start -1)
+__global__ void __launch_bounds__(kThreads) k_node_minmax(int cell_lo, int cell_hi, const CellGeom *__restrict__ geom, int *out)
+{
+    const int c = cell_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    int lo = 0x7fffffff, hi = -1;
+    if (c < cell_hi) {
+        const unsigned a = geom[c].n0, b = geom[c].n1, d = geom[c].n2;
+        lo = (int)min(a, min(b, d));
+        hi = (int)max(a, max(b, d));
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0 && hi >= 0) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+
 // ---- pfem2_step_host pipeline plan (once per handle): how far the cell numbering couples distant cells, and which
 // node ranges a chunk of cells depends on ----
 // band[0] = max |neighbour - cell| over the one-ring lists: a particle changes its cell index by at most that per substep
@@ -1585,14 +1603,15 @@ k_correct(ParticleSoA p, const CellGeom *__restrict__ geom, NodalVel vel, NodalV
 // is evaluated with the particle's cell and local position at the time of the correct call (nothing moves between
 // the two), so the bits are those of the eager kernel.  Any reader of particle velocities flushes first.
 __global__ void __launch_bounds__(kThreads)
-k_snapshot_dv(int n_nodes, NodalVel vel, NodalVel vel_old, int has_old, double *__restrict__ dvx, double *__restrict__ dvy,
+k_snapshot_dv(int node_lo, int node_hi, NodalVel vel, NodalVel vel_old, int has_old, double *__restrict__ dvx, double *__restrict__ dvy,
               double2 *__restrict__ dv2)
 {
+    // [node_lo, node_hi): the nodes of the owned cells (multi-GPU: a strip's share of the mesh; otherwise all nodes)
     const double *Vx, *Vy, *Ox = nullptr, *Oy = nullptr;
     vel.resolve(Vx, Vy);
     if (has_old) vel_old.resolve(Ox, Oy);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
+    const int i = node_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= node_hi) return;
     const double dx = has_old ? __dsub_rn(Vx[i], Ox[i]) : Vx[i];
     const double dy = has_old ? __dsub_rn(Vy[i], Oy[i]) : Vy[i];
     dvx[i] = dx;

@@ -14,6 +14,46 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
+def spill_case(handler, multi_gpu, rank, world, dev):
+    """SURVEY N4 across a strip boundary.  A particle in the tolerance band of the LAST cell of rank 0 (second barycentric
+    in [-2e-6, 0)) gets a flat sub-cell index that lands in the occupancy word of the next cell, i.e. the FIRST cell of
+    rank 1; there it suppresses the re-seeding of that sub-cell.  The neighbour protocol carries those bits in the
+    migration header, so the strip-partitioned run re-seeds exactly like a single GPU.  Returns (single, multi) counts."""
+    nx, ny, level = 8, 4, 2
+    ppc = level * level
+    dm = handler.device_structured_channel(nx, ny, 2.0, 1.0, colmajor=True, device=dev)
+    zero = torch.zeros(dm.n_nodes, dtype=torch.float64, device=dev)
+    F, W = (zero, zero.clone()), (zero.clone(), zero.clone())
+    bounds = multi_gpu.strip_bounds(dm.n_cells, world, align=2 * ny)
+    ref = handler.ParticleHandler2D(dm, level)
+    ref.seed_particles()
+    ref.init_particle_velocity(F)
+    s = ref.download()  # seeded order: particle of (cell, sub-cell) at cell * ppc + sub-cell
+    c = int(bounds[1]) - 1  # last cell of rank 0
+    tri = dm.cells[c].cpu().numpy().view(np.uint32)
+    v = dm.vertices.cpu().numpy()[tri.astype(np.int64)]
+    L = np.array([0.3, -1.0e-6, 0.7 + 1.0e-6])  # inside the +-2e-6 band, just across the edge opposite vertex 1
+    pos = L[0] * v[0] + L[1] * v[1] + L[2] * v[2]
+    keep = np.ones(s["x"].shape[0], dtype=bool)
+    keep[(c + 1) * ppc + 0] = keep[(c + 1) * ppc + 1] = False  # empty the two sub-cells of cell c + 1 the spill can reach (4 + 2j, +1)
+    st = {k: a[keep] for k, a in s.items()}
+    add = {"x": pos[0], "y": pos[1], "l0": L[0], "l1": L[1], "l2": L[2], "vx": 0.0, "vy": 0.0, "cell": c, "id": 0}
+    st = {k: np.concatenate([a, np.asarray([add[k]], dtype=a.dtype)]) for k, a in st.items()}
+    ref.upload(st)
+    ref.step(F, W, 0.01, 3)
+    single = (ref.get_particle_count(), ref.stats()["added"])
+    ref.close()
+    h = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world)
+    h.seed_particles()
+    h.init_particle_velocity(F)
+    own = (st["cell"] >= int(bounds[rank])) & (st["cell"] < int(bounds[rank + 1]))
+    h.h.upload({k: a[own] for k, a in st.items()})
+    h.step(F, W, 0.01, 3)
+    multi = h.global_particle_count()
+    h.close()
+    return single, multi, h.protocol
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -70,6 +110,13 @@ def main():
             ref.close()
         h.close()
         dist.barrier()
+    # tolerance-band spill of the occupancy bits across the strip boundary: carried by the neighbour protocol
+    single, multi, protocol = spill_case(handler, multi_gpu, rank, world, dev)
+    if rank == 0:
+        assert single[1] == 1, f"the crafted state does not exercise the spill: single GPU re-seeded {single[1]} sub-cells, expected 1"
+        assert multi == single[0], f"{world} GPUs hold {multi} particles, one GPU {single[0]}: spill bits lost at the strip boundary"
+        print(f"MG_SPILL_OK world={world} protocol={protocol} single_gpu(count, added)={single} multi_gpu_count={multi}")
+    dist.barrier()
     dist.destroy_process_group()
 
 

@@ -26,13 +26,22 @@ L, hh = h.L, h.h
 n = 10
 for _ in range(n):
     timed("move", lambda: hh._check(L.pfem2_advect_move(hh._h, F[0].data_ptr(), F[1].data_ptr(), dt, 3), "m"))
-    counts = (C.c_int * world)()
-    timed("emig_count", lambda: hh._check(L.pfem2_emigrants_count(hh._h, h.bounds.ctypes.data_as(C.POINTER(C.c_int)), world, counts), "c"))
-    sc = [int(c) for c in counts]
-    sb = torch.empty((sum(sc), 8), dtype=torch.float64, device=dev)
-    if sb.numel(): timed("emig_pack", lambda: hh._check(L.pfem2_emigrants_pack(hh._h, sb.data_ptr(), sb.shape[0]), "p"))
-    rb, rc = timed("exchange", lambda: mg.exchange_records(sb, sc, None))
-    if rb.shape[0]: timed("append", lambda: hh._check(L.pfem2_immigrants_append(hh._h, rb.data_ptr(), rb.shape[0]), "a"))
+    if h.protocol == "neighbour":
+        b = h._nbr
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        timed("emig_pack", lambda: hh._check(L.pfem2_emigrants_pack_neighbours(hh._h, rank, ptr(b["sl"]), ptr(b["sr"]), h.migration_cap), "p"))
+        timed("exchange", lambda: mg.exchange_neighbours(b["sl"], b["sr"], b["rl"], b["rr"], rank, world, None))
+        for key, left in (("rl", 1), ("rr", 0)):
+            if b[key] is not None:
+                timed("append", lambda: hh._check(L.pfem2_immigrants_append_device(hh._h, b[key].data_ptr(), h.migration_cap, left), "a"))
+    else:
+        counts = (C.c_int * world)()
+        timed("emig_count", lambda: hh._check(L.pfem2_emigrants_count(hh._h, h.bounds.ctypes.data_as(C.POINTER(C.c_int)), world, counts), "c"))
+        sc = [int(c) for c in counts]
+        sb = torch.empty((sum(sc), 8), dtype=torch.float64, device=dev)
+        if sb.numel(): timed("emig_pack", lambda: hh._check(L.pfem2_emigrants_pack(hh._h, sb.data_ptr(), sb.shape[0]), "p"))
+        rb, rc = timed("exchange", lambda: mg.exchange_records(sb, sc, None))
+        if rb.shape[0]: timed("append", lambda: hh._check(L.pfem2_immigrants_append(hh._h, rb.data_ptr(), rb.shape[0]), "a"))
     timed("finish", lambda: hh._check(L.pfem2_advect_finish(hh._h, F[0].data_ptr(), F[1].data_ptr()), "f"))
     timed("proj_acc", lambda: hh._check(L.pfem2_project_accumulate(hh._h, h.acc3.data_ptr()), "pa"))
     timed("halo", lambda: mg.exchange_interface(h.acc3, h.iface, None))
@@ -40,7 +49,7 @@ for _ in range(n):
     timed("correct", lambda: h.correct_particle_velocity(F, W))
     timed("count", lambda: h.get_particle_count())
 if rank == 0:
-    print("world", world, {k: round(v / n, 3) for k, v in acc.items()}, "sum", round(sum(acc.values()) / n, 3))
+    print("world", world, h.protocol, "cap", getattr(h, "migration_cap", None), {k: round(v / n, 3) for k, v in acc.items()}, "sum", round(sum(acc.values()) / n, 3))
 torch.cuda.synchronize(); t = time.perf_counter()
 for _ in range(n):
     h.step(F, W, dt, 3); h.get_particle_count()

@@ -24,6 +24,8 @@ SYMBOLS = (
     "pfem2_get_phase_times", "pfem2_set_owned_cells", "pfem2_advect_move", "pfem2_emigrants_count", "pfem2_emigrants_pack",
     "pfem2_immigrants_append", "pfem2_advect_finish", "pfem2_project_accumulate", "pfem2_project_finalize",
     "pfem2_set_rank_bounds", "pfem2_emigrants_pack_neighbours", "pfem2_immigrants_append_device",
+    "pfem2_p2p_inbox_create", "pfem2_p2p_connect", "pfem2_emigrants_send_p2p", "pfem2_immigrants_recv_p2p",
+    "pfem2_project_halo_p2p", "pfem2_p2p_last_sent",
 )
 
 
@@ -94,6 +96,12 @@ def load():
     L.pfem2_set_rank_bounds.argtypes = [vp, C.POINTER(i), i]
     L.pfem2_emigrants_pack_neighbours.argtypes = [vp, i, vp, vp, i]
     L.pfem2_immigrants_append_device.argtypes = [vp, vp, i, i]
+    L.pfem2_p2p_inbox_create.argtypes = [vp, i, i, i, C.POINTER(i), vp]
+    L.pfem2_p2p_connect.argtypes = [vp, i, vp]
+    L.pfem2_emigrants_send_p2p.argtypes = [vp, i]
+    L.pfem2_immigrants_recv_p2p.argtypes = [vp]
+    L.pfem2_project_halo_p2p.argtypes = [vp, vp]
+    L.pfem2_p2p_last_sent.argtypes = [vp, C.POINTER(i)]
     L.pfem2_project_accumulate.argtypes = [vp, vp]
     L.pfem2_project_finalize.argtypes = [vp, vp, vp, vp]
     L.pfem2_set_profiling.argtypes = [vp, i]

@@ -127,6 +127,18 @@ struct pfem2_handle {
         int packed_slices = 0;            // upload slices already interleaved into v2
     } pipe;
 
+    // P2P transport of the neighbour protocol (multi-GPU): inboxes in this GPU's memory the neighbours store into, and the
+    // neighbours' inboxes mapped through CUDA IPC.  side 0 = left neighbour (rank - 1), side 1 = right neighbour (rank + 1)
+    struct P2P {
+        int cap = 0;                            // records per migration block (the same on every strip)
+        void *inbox[2] = {nullptr, nullptr};    // mine: written by neighbour `side`
+        void *peer[2] = {nullptr, nullptr};     // theirs: the inbox neighbour `side` keeps for me (IPC mapping)
+        int *idx[2] = {nullptr, nullptr};       // interface node ids shared with neighbour `side` (ascending), device
+        int n_idx[2] = {0, 0};
+        int *cursors = nullptr;                 // device: [0], [1] pack cursors per side, [2] records handed over by the last send
+        unsigned mig_seq = 0, halo_seq = 0;     // deliveries made so far (block parity = seq & 1)
+    } p2p;
+
     // optional per-phase CUDA-event timing (pfem2_set_profiling)
     bool profiling = false;
     struct PhaseRec { int phase; cudaEvent_t a, b; };
@@ -285,6 +297,8 @@ int sync_counters(pfem2_handle *h)
         h->readback_pending = false;
         h->host_count = h->host_ctr->count;
         h->host_added = h->host_ctr->added;
+        if (h->host_ctr->overflow & kOverflowP2PTimeout)
+            return fail(h, PFEM2_ECUDA, "a neighbour strip's P2P delivery did not arrive within the watchdog time; state is invalid");
         if (h->host_ctr->overflow & kOverflowMigration)
             return fail(h, PFEM2_ECAPACITY, "a migration buffer overflowed or a particle left for a non-adjacent strip (raise the migration "
                                             "capacity / use wider strips); state is invalid");
@@ -697,6 +711,25 @@ int store_rank_bounds(pfem2_handle *h, const int *h_bounds, int n_ranks)
     return PFEM2_OK;
 }
 
+// shared tail of immigrants_append_device / immigrants_recv_p2p: append one [header | records] block, count it, grow the array
+int append_migration_block(pfem2_handle *h, const int4 *buf, int capacity_records, int from_left)
+{
+    cudaStream_t st = h->stream;
+    const int grid = grid_for(capacity_records, kThreads, g_num_sms * 2);
+    PFEM2_LAUNCH(k_immigrant_append_dev, grid, kThreads, 0, st, h->soa[h->cur], h->ctr, buf, capacity_records);
+    const int C = h->mesh.n_cells;
+    const bool m64 = h->ppc > 32;
+#define PFEM2_CNTD(M, B)                                                                                                             \
+    PFEM2_LAUNCH((k_count_appended_dev<M, B>), grid, kThreads, 0, st, h->soa[h->cur], h->ctr, buf, capacity_records, C, h->ppc, h->level, \
+                 h->sub_step, h->stay, h->arrive, h->cell_mask)
+    if (h->opt.subcell_mode == 0) { if (m64) PFEM2_CNTD(0, true); else PFEM2_CNTD(0, false); }
+    else                          { if (m64) PFEM2_CNTD(1, true); else PFEM2_CNTD(1, false); }
+#undef PFEM2_CNTD
+    PFEM2_LAUNCH(k_add_count_dev, 1, 1, 0, st, h->ctr, buf, capacity_records, h->cell_mask, h->own_lo, h->own_hi, from_left ? 1 : 0);
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
 int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
 {
     int rc;
@@ -995,6 +1028,12 @@ int pfem2_destroy(pfem2_handle *h)
     cudaFree(h->mg_bounds); cudaFree(h->mg_rank_count); cudaFree(h->own_len_dev); cudaFree(h->node_list);
     cudaFree(h->dv[0]); cudaFree(h->dv[1]);
     cudaFree(h->dv2); cudaFree(h->v2);
+    for (int k = 0; k < 2; ++k) {
+        if (h->p2p.peer[k]) cudaIpcCloseMemHandle(h->p2p.peer[k]);
+        cudaFree(h->p2p.inbox[k]);
+        cudaFree(h->p2p.idx[k]);
+    }
+    cudaFree(h->p2p.cursors);
     if (h->trail_stream) cudaStreamDestroy(h->trail_stream);
     for (cudaEvent_t e : h->trail_ev) if (e) cudaEventDestroy(e);
     cudaFree(h->trail_prog);
@@ -1546,20 +1585,155 @@ int pfem2_immigrants_append_device(pfem2_handle *h, const void *d_buffer, int ca
     if (!h->move_pending) return fail(h, PFEM2_ESTATE, "immigrants_append_device outside advect_move / advect_finish");
     if (!h->mg_fused) return fail(h, PFEM2_ESTATE, "immigrants_append_device needs the fused move pass (see pfem2_emigrants_pack_neighbours)");
     CU(cudaSetDevice(h->device));
+    return append_migration_block(h, (const int4 *)d_buffer, capacity_records, from_left);
+}
+
+// ---- P2P transport (NVLink peer memory through CUDA IPC) ----
+int pfem2_p2p_inbox_create(pfem2_handle *h, int side, int capacity_records, int n_interface_nodes, const int *h_interface_nodes,
+                           void *ipc_handle_out)
+{
+    if (!h || side < 0 || side > 1 || capacity_records < 1 || n_interface_nodes < 0 || (n_interface_nodes && !h_interface_nodes) ||
+        !ipc_handle_out)
+        return PFEM2_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI passes IPC handles as 64 opaque bytes");
+    if (h->p2p.inbox[side]) return fail(h, PFEM2_ESTATE, "inbox already created for this side");
+    if (h->p2p.cap && h->p2p.cap != capacity_records) return fail(h, PFEM2_EINVAL, "both inboxes must have the same capacity");
+    CU(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
-    const int4 *buf = (const int4 *)d_buffer;
-    const int grid = grid_for(capacity_records, kThreads, g_num_sms * 2);
-    PFEM2_LAUNCH(k_immigrant_append_dev, grid, kThreads, 0, st, h->soa[h->cur], h->ctr, buf, capacity_records);
-    const int C = h->mesh.n_cells;
-    const bool m64 = h->ppc > 32;
-#define PFEM2_CNTD(M, B)                                                                                                             \
-    PFEM2_LAUNCH((k_count_appended_dev<M, B>), grid, kThreads, 0, st, h->soa[h->cur], h->ctr, buf, capacity_records, C, h->ppc, h->level, \
-                 h->sub_step, h->stay, h->arrive, h->cell_mask)
-    if (h->opt.subcell_mode == 0) { if (m64) PFEM2_CNTD(0, true); else PFEM2_CNTD(0, false); }
-    else                          { if (m64) PFEM2_CNTD(1, true); else PFEM2_CNTD(1, false); }
-#undef PFEM2_CNTD
-    PFEM2_LAUNCH(k_add_count_dev, 1, 1, 0, st, h->ctr, buf, capacity_records, h->cell_mask, h->own_lo, h->own_hi, from_left ? 1 : 0);
+    // a multiple of 2 MiB so that the block is an allocation of its own (an IPC handle names a whole allocation)
+    const size_t bytes = (p2p_inbox_bytes(capacity_records, n_interface_nodes) + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    CU(cudaMalloc(&h->p2p.inbox[side], bytes));
+    CU(cudaMemsetAsync(h->p2p.inbox[side], 0, bytes, st));
+    PFEM2_LAUNCH(k_p2p_init_head, 1, 1, 0, st, (P2PInboxHead *)h->p2p.inbox[side], capacity_records, n_interface_nodes);
+    CU(cudaMalloc((void **)&h->p2p.idx[side], sizeof(int) * (size_t)std::max(n_interface_nodes, 1)));
+    if (n_interface_nodes)
+        CU(cudaMemcpyAsync(h->p2p.idx[side], h_interface_nodes, sizeof(int) * (size_t)n_interface_nodes, cudaMemcpyHostToDevice, st));
+    if (!h->p2p.cursors) {
+        CU(cudaMalloc((void **)&h->p2p.cursors, 4 * sizeof(int)));
+        CU(cudaMemsetAsync(h->p2p.cursors, 0, 4 * sizeof(int), st));
+    }
+    CU(cudaStreamSynchronize(st)); // the head is initialised before anybody can map the inbox; the host index list may go away
+    h->p2p.cap = capacity_records;
+    h->p2p.n_idx[side] = n_interface_nodes;
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, h->p2p.inbox[side]));
+    memcpy(ipc_handle_out, &hd, sizeof hd);
+    return PFEM2_OK;
+}
+
+int pfem2_p2p_connect(pfem2_handle *h, int side, const void *ipc_handle)
+{
+    if (!h || side < 0 || side > 1 || !ipc_handle) return PFEM2_EINVAL;
+    if (!h->p2p.inbox[side]) return fail(h, PFEM2_ESTATE, "create this side's inbox before connecting to the neighbour's");
+    if (h->p2p.peer[side]) return fail(h, PFEM2_ESTATE, "already connected on this side");
+    CU(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle, sizeof hd);
+    void *peer = nullptr;
+    CU(cudaIpcOpenMemHandle(&peer, hd, cudaIpcMemLazyEnablePeerAccess));
+    P2PInboxHead head;
+    cudaError_t e = cudaMemcpy(&head, peer, sizeof head, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess || head.magic != kP2PMagic || head.capacity_records != h->p2p.cap || head.n_halo_nodes != h->p2p.n_idx[side]) {
+        cudaIpcCloseMemHandle(peer);
+        cudaGetLastError();
+        return fail(h, PFEM2_EINVAL, "the neighbour's inbox does not match (magic / capacity / interface size): cannot use the P2P transport");
+    }
+    h->p2p.peer[side] = peer;
+    return PFEM2_OK;
+}
+
+int pfem2_emigrants_send_p2p(pfem2_handle *h, int rank)
+{
+    if (h) h->partials_valid = false;
+    if (!h || rank < 0) return PFEM2_EINVAL;
+    if (!h->move_pending) return fail(h, PFEM2_ESTATE, "emigrants_send_p2p outside advect_move / advect_finish");
+    if (!h->mg_fused)
+        return fail(h, PFEM2_ESTATE, "the move pass did not list its emigrants (call pfem2_set_rank_bounds before pfem2_advect_move; "
+                                     "fast order and TMA-tiled kernels only)");
+    if (rank >= h->mg_ranks) return fail(h, PFEM2_EINVAL, "rank outside the rank bounds");
+    if ((rank > 0 && !h->p2p.peer[0]) || (rank + 1 < h->mg_ranks && !h->p2p.peer[1]))
+        return fail(h, PFEM2_ESTATE, "a neighbour strip exists but is not connected (pfem2_p2p_connect)");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int cap = h->p2p.cap;
+    const unsigned seq = ++h->p2p.mig_seq;
+    const int parity = (int)(seq & 1u);
+    unsigned char *pl = (unsigned char *)h->p2p.peer[0], *pr = (unsigned char *)h->p2p.peer[1];
+    MigrationHeader *hl = pl ? (MigrationHeader *)(pl + p2p_block_offset(cap, parity)) : nullptr;
+    MigrationHeader *hr = pr ? (MigrationHeader *)(pr + p2p_block_offset(cap, parity)) : nullptr;
+    PFEM2_LAUNCH(k_emigrant_pack_p2p, grid_for(cap, kThreads, g_num_sms * 2), kThreads, 0, st, h->soa[h->cur], h->keys[0], h->mg_rank_count,
+                 h->mg_ranks, h->mg_bounds, rank, hl ? (int4 *)(hl + 1) : nullptr, hr ? (int4 *)(hr + 1) : nullptr, cap, h->ctr,
+                 h->p2p.cursors);
+    PFEM2_LAUNCH(k_p2p_publish_migration, 1, 1, 0, st, hl, pl ? &((P2PInboxHead *)pl)->flag_mig : nullptr, hr,
+                 pr ? &((P2PInboxHead *)pr)->flag_mig : nullptr, h->p2p.cursors, cap, h->cell_mask, h->own_hi, h->mesh.n_cells, seq);
+    h->mg_fused_total = -1; // consumed
     CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int pfem2_immigrants_recv_p2p(pfem2_handle *h)
+{
+    if (h) h->partials_valid = false;
+    if (!h) return PFEM2_EINVAL;
+    if (!h->move_pending || !h->mg_fused) return fail(h, PFEM2_ESTATE, "immigrants_recv_p2p outside advect_move / advect_finish");
+    if (!h->p2p.mig_seq) return fail(h, PFEM2_ESTATE, "immigrants_recv_p2p before emigrants_send_p2p");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int cap = h->p2p.cap;
+    const unsigned seq = h->p2p.mig_seq;
+    const int parity = (int)(seq & 1u);
+    unsigned char *il = h->p2p.peer[0] ? (unsigned char *)h->p2p.inbox[0] : nullptr; // a neighbour delivers only if it is connected
+    unsigned char *ir = h->p2p.peer[1] ? (unsigned char *)h->p2p.inbox[1] : nullptr;
+    if (!il && !ir) return PFEM2_OK;
+    PFEM2_LAUNCH(k_p2p_wait, 1, 1, 0, st, il ? &((const P2PInboxHead *)il)->flag_mig : nullptr,
+                 ir ? &((const P2PInboxHead *)ir)->flag_mig : nullptr, seq, h->ctr, 20ull * 1000000000ull);
+    int rc;
+    if (il && (rc = append_migration_block(h, (const int4 *)(il + p2p_block_offset(cap, parity)), cap, 1))) return rc;
+    if (ir && (rc = append_migration_block(h, (const int4 *)(ir + p2p_block_offset(cap, parity)), cap, 0))) return rc;
+    return PFEM2_OK;
+}
+
+int pfem2_project_halo_p2p(pfem2_handle *h, double *d_acc3)
+{
+    if (!h || !d_acc3) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int cap = h->p2p.cap;
+    if (!h->p2p.peer[0] && !h->p2p.peer[1]) return PFEM2_OK;
+    const unsigned seq = ++h->p2p.halo_seq;
+    const int parity = (int)(seq & 1u);
+    unsigned *flags[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; ++k) {
+        if (!h->p2p.peer[k]) continue;
+        unsigned char *peer = (unsigned char *)h->p2p.peer[k];
+        const int n = h->p2p.n_idx[k];
+        if (n)
+            PFEM2_LAUNCH(k_halo_send, grid_for(n, kThreads, 1 << 30), kThreads, 0, st, d_acc3, h->p2p.idx[k], n,
+                         (double *)(peer + p2p_halo_offset(cap, n, parity)));
+        flags[k] = &((P2PInboxHead *)peer)->flag_halo;
+    }
+    PFEM2_LAUNCH(k_p2p_publish_flag, 1, 1, 0, st, flags[0], flags[1], seq);
+    PFEM2_LAUNCH(k_p2p_wait, 1, 1, 0, st, h->p2p.peer[0] ? &((const P2PInboxHead *)h->p2p.inbox[0])->flag_halo : nullptr,
+                 h->p2p.peer[1] ? &((const P2PInboxHead *)h->p2p.inbox[1])->flag_halo : nullptr, seq, h->ctr, 20ull * 1000000000ull);
+    for (int k = 0; k < 2; ++k) {
+        if (!h->p2p.peer[k]) continue;
+        const int n = h->p2p.n_idx[k];
+        if (n)
+            PFEM2_LAUNCH(k_halo_add, grid_for(n, kThreads, 1 << 30), kThreads, 0, st, d_acc3, h->p2p.idx[k], n,
+                         (const double *)((unsigned char *)h->p2p.inbox[k] + p2p_halo_offset(cap, n, parity)));
+    }
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int pfem2_p2p_last_sent(pfem2_handle *h, int *out)
+{
+    if (!h || !out) return PFEM2_EINVAL;
+    *out = 0;
+    if (!h->p2p.cursors) return PFEM2_OK;
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(out, h->p2p.cursors + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return PFEM2_OK;
 }
 

@@ -1409,6 +1409,167 @@ __global__ void k_add_count_dev(Counters *ctr, const int4 *__restrict__ buf, int
             if (own_lo + k < own_hi && hd->spill[k]) cell_mask[own_lo + k] |= hd->spill[k];
 }
 
+// ---------------------------------------------------------------------------------------------
+// P2P transport of the neighbour protocol: NVLink peer memory instead of NCCL, nothing on the host in the loop.
+// Every strip allocates one INBOX per neighbour and hands its CUDA IPC handle to that neighbour, which maps it and
+// from then on stores into it directly:
+//     [ P2PInboxHead 64 B ][ parity 0: header | cap records ][ parity 1: header | cap records ][ halo 0 ][ halo 1 ]
+// The pack kernel of the sender writes the 64-byte records of its emigrants straight into the receiver's HBM (plain
+// 128-bit stores over NVLink), a one-thread publish kernel then writes the header (count, flags, spill words), fences
+// (system scope) and releases the sequence number into the head; the receiver's stream waits on that flag with a
+// one-thread acquire spin (bounded by a watchdog: a dead peer raises the overflow flag instead of hanging the GPU) and
+// appends from its own memory.  The projection halo uses the same inbox: interface-node accumulators are stored into
+// the neighbour's halo block and added there.  Blocks alternate with the parity of the sequence number: a sender can be
+// at most one delivery ahead of what the receiver has consumed (it waited for the receiver's delivery of the same step).
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned kP2PMagic = 0x50324232u;
+constexpr int kOverflowP2PTimeout = 8; // Counters.overflow bit: a neighbour's delivery did not arrive in time
+struct __align__(64) P2PInboxHead {
+    unsigned magic;
+    unsigned flag_mig;    // sequence number of the last complete migration delivery (written by the neighbour)
+    unsigned flag_halo;   // ... of the last complete halo delivery
+    int capacity_records;
+    int n_halo_nodes;
+    int pad[11];
+};
+static_assert(sizeof(P2PInboxHead) == 64, "inbox head is one record slot");
+__host__ __device__ inline size_t p2p_block_bytes(int cap) { return ((size_t)cap + 1) * sizeof(ParticleRec); }
+__host__ __device__ inline size_t p2p_block_offset(int cap, int parity) { return sizeof(P2PInboxHead) + (size_t)parity * p2p_block_bytes(cap); }
+__host__ __device__ inline size_t p2p_halo_offset(int cap, int n_nodes, int parity)
+{
+    return sizeof(P2PInboxHead) + 2 * p2p_block_bytes(cap) + (size_t)parity * (size_t)n_nodes * 3 * sizeof(double);
+}
+__host__ __device__ inline size_t p2p_inbox_bytes(int cap, int n_nodes) { return p2p_halo_offset(cap, n_nodes, 2); }
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// emigrants listed by the move pass -> records stored directly into the neighbours' inbox blocks (peer memory); slots come
+// from LOCAL cursors (no atomics over NVLink).  rec_left / rec_right point at the first record of the peer's block.
+__global__ void __launch_bounds__(kThreads)
+k_emigrant_pack_p2p(ParticleSoA p, const unsigned *__restrict__ emig_idx, const int *__restrict__ rank_count, int n_ranks,
+                    const int *__restrict__ bounds, int rank, int4 *rec_left, int4 *rec_right, int cap, Counters *ctr, int *cursors)
+{
+    const int n_emig = rank_count[n_ranks];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_emig; j += gridDim.x * blockDim.x) {
+        const unsigned i = emig_idx[j];
+        const int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
+        const int dest = rank_of_cell((unsigned)t.z, bounds, n_ranks);
+        const int side = dest == rank - 1 ? 0 : (dest == rank + 1 ? 1 : -1);
+        int4 *out = side == 0 ? rec_left : (side == 1 ? rec_right : nullptr);
+        st_cell(p.tail + i, kLostCell);
+        if (!out) {
+            atomicOr(&ctr->overflow, kOverflowMigration);
+            continue;
+        }
+        const int slot = atomicAdd(cursors + side, 1);
+        if (slot >= cap) {
+            atomicOr(&ctr->overflow, kOverflowMigration);
+            continue;
+        }
+        int4 *rec = out + 4 * (size_t)slot;
+        rec[0] = *reinterpret_cast<const int4 *>(p.pos + i);
+        rec[1] = *reinterpret_cast<const int4 *>(p.lab + i);
+        rec[2] = t;
+        rec[3] = *reinterpret_cast<const int4 *>(p.vel + i);
+    }
+}
+
+// one thread, after the pack kernel has completed (its peer stores are performed): headers, fence, then the flags
+__global__ void k_p2p_publish_migration(MigrationHeader *hdr_left, unsigned *flag_left, MigrationHeader *hdr_right, unsigned *flag_right,
+                                        int *cursors, int cap, const unsigned long long *__restrict__ cell_mask, int own_hi,
+                                        int n_cells, unsigned seq)
+{
+    if (hdr_left) {
+        const int n = cursors[0];
+        hdr_left->count = n;
+        hdr_left->flags = n > cap ? 1 : 0;
+        for (int k = 0; k < 4; ++k) hdr_left->spill[k] = 0ull;
+    }
+    if (hdr_right) {
+        const int n = cursors[1];
+        hdr_right->count = n;
+        hdr_right->flags = n > cap ? 1 : 0;
+        for (int k = 0; k < 4; ++k) hdr_right->spill[k] = own_hi + k < n_cells ? cell_mask[own_hi + k] : 0ull;
+    }
+    cursors[2] = cursors[0] + cursors[1]; // what this strip handed over (read back on demand)
+    cursors[0] = cursors[1] = 0;
+    __threadfence_system();
+    if (flag_left) st_release_sys(flag_left, seq);
+    if (flag_right) st_release_sys(flag_right, seq);
+}
+
+__global__ void k_p2p_publish_flag(unsigned *flag_left, unsigned *flag_right, unsigned seq)
+{
+    __threadfence_system();
+    if (flag_left) st_release_sys(flag_left, seq);
+    if (flag_right) st_release_sys(flag_right, seq);
+}
+
+// one thread: the stream continues once both neighbours have delivered sequence number `seq` (or the watchdog fires)
+__global__ void k_p2p_wait(const unsigned *flag_a, const unsigned *flag_b, unsigned seq, Counters *ctr, unsigned long long timeout_ns)
+{
+    const unsigned long long t0 = global_timer_ns();
+    const unsigned *flags[2] = {flag_a, flag_b};
+    for (int k = 0; k < 2; ++k) {
+        if (!flags[k]) continue;
+        while ((int)(ld_acquire_sys(flags[k]) - seq) < 0) {
+            if (global_timer_ns() - t0 > timeout_ns) {
+                atomicOr(&ctr->overflow, kOverflowP2PTimeout);
+                return;
+            }
+            __nanosleep(200);
+        }
+    }
+}
+
+// projection halo: my accumulators of the interface nodes -> the neighbour's halo block (peer memory)
+__global__ void __launch_bounds__(kThreads)
+k_halo_send(const double *__restrict__ acc3, const int *__restrict__ idx, int n, double *peer_halo)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *a = acc3 + 3 * (size_t)idx[i];
+    peer_halo[3 * (size_t)i] = a[0];
+    peer_halo[3 * (size_t)i + 1] = a[1];
+    peer_halo[3 * (size_t)i + 2] = a[2];
+}
+
+// ... and the neighbour's contribution added to mine (two contributions per shared node: a + b == b + a bit for bit)
+__global__ void __launch_bounds__(kThreads)
+k_halo_add(double *__restrict__ acc3, const int *__restrict__ idx, int n, const double *__restrict__ halo)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double *a = acc3 + 3 * (size_t)idx[i];
+    a[0] = __dadd_rn(a[0], halo[3 * (size_t)i]);
+    a[1] = __dadd_rn(a[1], halo[3 * (size_t)i + 1]);
+    a[2] = __dadd_rn(a[2], halo[3 * (size_t)i + 2]);
+}
+
+__global__ void k_p2p_init_head(P2PInboxHead *hd, int cap, int n_nodes)
+{
+    hd->magic = kP2PMagic;
+    hd->flag_mig = 0;
+    hd->flag_halo = 0;
+    hd->capacity_records = cap;
+    hd->n_halo_nodes = n_nodes;
+}
+
 // projection, multi-GPU flavour: per-node accumulators {sum L v_x, sum L v_y, sum L} without the division, so that the
 // contributions of the strips sharing an interface node can be added before kFinalizeVelocityProjection's division
 __global__ void __launch_bounds__(kThreads)

@@ -138,7 +138,7 @@ def exchange_interface(acc3: torch.Tensor, iface: dict, group=None):
 class DistributedParticleHandler2D:
     """ParticleHandler2D interface over a strip partition; same method names as handler.ParticleHandler2D."""
 
-    def __init__(self, mesh, cell_division_level, bounds, rank, world, group=None, migration="neighbour", migration_cap=0, **opts):
+    def __init__(self, mesh, cell_division_level, bounds, rank, world, group=None, migration="p2p", migration_cap=0, **opts):
         from . import _lib, handler
 
         self._lib = _lib
@@ -152,29 +152,73 @@ class DistributedParticleHandler2D:
         self.acc3 = torch.zeros((mesh.n_nodes, 3), dtype=torch.float64, device=mesh.device)
         self._sent = 0
         self.last_received = 0
-        # neighbour protocol (default where the library supports it: fast order, TMA-tiled move pass): fixed-size migration
-        # buffers to / from the adjacent strips, counts stay on the device -> no host round trip inside advect_particles
+        # Migration / halo transport:
+        #   "p2p"        NVLink peer memory: the pack kernel stores the emigrants' records straight into the neighbour's inbox,
+        #                sequence flags instead of collectives, nothing on the host in the loop (falls back to "neighbour" if the
+        #                CUDA IPC set-up fails on any rank);
+        #   "neighbour"  fixed-size [header | records] buffers to / from the adjacent strips over ncclSend / ncclRecv, counts stay
+        #                on the device (no host round trip inside advect_particles);
+        #   "exact"      counts first (host), then exactly sized payloads (all_to_all_single).
+        # "p2p" and "neighbour" need the default kernels (fast order, TMA-tiled move pass lists its emigrants).
         self.protocol = os.environ.get("PFEM2_MG_PROTOCOL", migration)  # env: A/B measurements
-        if self.protocol not in ("neighbour", "exact"):
-            raise ValueError("migration must be 'neighbour' or 'exact'")
+        if self.protocol not in ("p2p", "neighbour", "exact"):
+            raise ValueError("migration must be 'p2p', 'neighbour' or 'exact'")
         if opts.get("stable_order") or opts.get("lane_per_record") or os.environ.get("PFEM2_MG_FUSED") == "0":
-            self.protocol = "exact"  # the move pass lists its emigrants only in the default kernels
+            self.protocol = "exact"
         self._nbr = None
-        if self.protocol == "neighbour":
+        if self.protocol != "exact":
             n_if = max([int(v.numel()) for v in self.iface.values()] or [1])
             self.migration_cap = int(migration_cap) if migration_cap else migration_capacity(n_if, self.h.particles_per_cell)
+            self.h._check(self.L.pfem2_set_rank_bounds(self.h._h, self.bounds.ctypes.data_as(C.POINTER(C.c_int)), self.world),
+                          "set_rank_bounds")
+        if self.protocol == "p2p" and not self._setup_p2p():
+            self.protocol = "neighbour"
+        if self.protocol == "neighbour":
             shape = (self.migration_cap + 1, RECORD_DOUBLES)
             mk = lambda: torch.zeros(shape, dtype=torch.float64, device=mesh.device)  # noqa: E731
             self._nbr = {"sl": mk() if rank > 0 else None, "rl": mk() if rank > 0 else None,
                          "sr": mk() if rank + 1 < world else None, "rr": mk() if rank + 1 < world else None}
-            self.h._check(self.L.pfem2_set_rank_bounds(self.h._h, self.bounds.ctypes.data_as(C.POINTER(C.c_int)), self.world),
-                          "set_rank_bounds")
+
+    def _setup_p2p(self) -> bool:
+        """Create this strip's inboxes, swap CUDA IPC handles with the neighbours, map theirs.  Collective: every rank takes the
+        same decision (all ranks succeed or all fall back)."""
+        h, L, rank, world = self.h, self.L, self.rank, self.world
+        ok, handles = True, {}
+        if any(abs(r - rank) != 1 for r in self.iface):
+            ok = False  # not a strip partition: nodes shared with a non-adjacent rank
+        if ok:
+            for side, nb in ((0, rank - 1), (1, rank + 1)):
+                if not 0 <= nb < world:
+                    continue
+                idx = self.iface[nb].to(torch.int32).cpu().numpy() if nb in self.iface else np.empty(0, dtype=np.int32)
+                idx = np.ascontiguousarray(idx)
+                buf = C.create_string_buffer(64)
+                rc = L.pfem2_p2p_inbox_create(h._h, side, self.migration_cap, int(idx.size), idx.ctypes.data_as(C.POINTER(C.c_int)), buf)
+                if rc:
+                    ok = False
+                    break
+                handles[side] = buf.raw
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (ok, handles), group=self.group)
+        ok = all(g[0] for g in gathered)
+        if ok:
+            if rank > 0:
+                ok = ok and L.pfem2_p2p_connect(h._h, 0, gathered[rank - 1][1][1]) == 0
+            if rank + 1 < world:
+                ok = ok and L.pfem2_p2p_connect(h._h, 1, gathered[rank + 1][1][0]) == 0
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok), group=self.group)
+        return all(flags)
 
     @property
     def last_sent(self):
         """Particles this rank handed over in the last advect (neighbour protocol: read from the device on demand)."""
-        if self._nbr is not None and self._sent is None:
+        if self._sent is None and self._nbr is not None:
             self._sent = sum(int(header_count(b).item()) for b in (self._nbr["sl"], self._nbr["sr"]) if b is not None)
+        elif self._sent is None:
+            n = C.c_int(0)
+            self.h._check(self.L.pfem2_p2p_last_sent(self.h._h, C.byref(n)), "p2p_last_sent")
+            self._sent = n.value
         return self._sent
 
     def seed_particles(self):
@@ -186,6 +230,13 @@ class DistributedParticleHandler2D:
     def advect_particles(self, vel, time_step, particle_substeps):
         h, L = self.h, self.L
         h._check(L.pfem2_advect_move(h._h, vel[0].data_ptr(), vel[1].data_ptr(), time_step, particle_substeps), "advect_move")
+        if self.protocol == "p2p":
+            # three library calls, all enqueued on the handle's stream: records go straight into the neighbours' HBM over NVLink
+            h._check(L.pfem2_emigrants_send_p2p(h._h, self.rank), "emigrants_send_p2p")
+            h._check(L.pfem2_immigrants_recv_p2p(h._h), "immigrants_recv_p2p")
+            h._check(L.pfem2_advect_finish(h._h, vel[0].data_ptr(), vel[1].data_ptr()), "advect_finish")
+            self._sent = None  # read from the device on demand
+            return
         if self._nbr is not None:
             # everything below is enqueued without waiting for the device: the library works on the legacy default stream, which
             # is torch's current stream here, and torch orders the NCCL transfers against it (w.wait() is a stream-side wait)
@@ -219,7 +270,10 @@ class DistributedParticleHandler2D:
         # no host synchronisation: the library works on the legacy default stream, which is also torch's current stream here,
         # and torch orders the NCCL transfers against it (w.wait() makes the current stream wait for the receive)
         h._check(L.pfem2_project_accumulate(h._h, self.acc3.data_ptr()), "project_accumulate")
-        exchange_interface(self.acc3, self.iface, self.group)
+        if self.protocol == "p2p":
+            h._check(L.pfem2_project_halo_p2p(h._h, self.acc3.data_ptr()), "project_halo_p2p")
+        else:
+            exchange_interface(self.acc3, self.iface, self.group)
         h._check(L.pfem2_project_finalize(h._h, self.acc3.data_ptr(), vel[0].data_ptr(), vel[1].data_ptr()), "project_finalize")
 
     def correct_particle_velocity(self, vel, vel_old):
@@ -242,6 +296,9 @@ class DistributedParticleHandler2D:
         return self.h.download()
 
     def close(self):
+        if self.protocol == "p2p" and dist.is_initialized():
+            torch.cuda.synchronize(self.mesh.device)
+            dist.barrier(group=self.group)  # nobody unmaps / frees an inbox a neighbour may still be storing into
         self.h.close()
 
 
@@ -321,10 +378,13 @@ def bench_main(args, rank, world, local):
                        "l2": "inputs larger than L2", "timing": "CUDA events on rank-local default stream, max over ranks, barrier on both sides",
                        "migrated_particles_per_step": float(tsum[2]) / args.steps,
                        "migration_protocol": h.protocol,
-                       "collectives": ("fixed-size migration buffers [header | records] to / from the adjacent strips (ncclSend / ncclRecv, counts stay "
-                                       "on the device: no host round trip)" if h.protocol == "neighbour" else
-                                       "all_to_all_single (counts, 64-byte particle records)") +
-                                      " + pairwise isend/irecv of interface-node accumulators (NCCL)"},
+                       "collectives": {
+                           "p2p": "NVLink peer memory (CUDA IPC): emigrant records and interface-node accumulators stored straight into the "
+                                  "neighbour strip's HBM, device-side sequence flags; no NCCL and no host in the loop",
+                           "neighbour": "fixed-size migration buffers [header | records] to / from the adjacent strips (ncclSend / ncclRecv, "
+                                        "counts stay on the device) + pairwise isend/irecv of interface-node accumulators (NCCL)",
+                           "exact": "all_to_all_single (counts, 64-byte particle records) + pairwise isend/irecv of interface-node "
+                                    "accumulators (NCCL)"}[h.protocol]},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "alg_bytes_per_particle": bench.ALG_BYTES[dom], "note": "rank 0, per GPU",
                          "step": {"achieved": bench.ALG_BYTES_STEP * value / 1e9 / world, "frac": bench.ALG_BYTES_STEP * value / 1e9 / world / peak,

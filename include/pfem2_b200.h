@@ -174,6 +174,26 @@ int pfem2_set_rank_bounds(pfem2_handle *h, const int *h_bounds, int n_ranks);
 int pfem2_emigrants_pack_neighbours(pfem2_handle *h, int rank, void *d_left, void *d_right, int capacity_records);
 /* from_left != 0: the buffer came from rank - 1 (its spill words are OR-ed into this strip's first cells) */
 int pfem2_immigrants_append_device(pfem2_handle *h, const void *d_buffer, int capacity_records, int from_left);
+/* P2P transport of the neighbour protocol: NVLink peer memory instead of ncclSend / ncclRecv, no host in the loop.
+ * Every strip creates one inbox per neighbour in its own HBM (side 0: data from rank - 1, side 1: data from rank + 1) and
+ * hands the 64-byte CUDA IPC handle to that neighbour (any out-of-band channel: the Python layer uses all_gather_object);
+ * the neighbour maps it with pfem2_p2p_connect.  From then on
+ *   emigrants_send_p2p      the pack kernel stores the emigrants' records straight into the neighbours' inboxes, a publish
+ *                           kernel writes the header, fences (system scope) and releases a sequence number;
+ *   immigrants_recv_p2p     this strip's stream waits for both neighbours' sequence numbers (device-side acquire spin with a
+ *                           20 s watchdog: a dead peer raises an error instead of hanging the GPU) and appends from its own memory;
+ *   project_halo_p2p        between project_accumulate and project_finalize: interface-node accumulators are stored into the
+ *                           neighbours' inboxes, awaited and added (a + b == b + a: both strips get the same bits).
+ * h_interface_nodes: ascending ids of the nodes shared with that neighbour (both strips must pass the same list).  All
+ * strips use the same capacity_records.  Requirements as for emigrants_pack_neighbours. */
+int pfem2_p2p_inbox_create(pfem2_handle *h, int side, int capacity_records, int n_interface_nodes, const int *h_interface_nodes,
+                           void *ipc_handle_out /* 64 bytes */);
+/* side 0: ipc_handle = the inbox rank - 1 created with side 1;  side 1: the inbox rank + 1 created with side 0 */
+int pfem2_p2p_connect(pfem2_handle *h, int side, const void *ipc_handle);
+int pfem2_emigrants_send_p2p(pfem2_handle *h, int rank);
+int pfem2_immigrants_recv_p2p(pfem2_handle *h);
+int pfem2_project_halo_p2p(pfem2_handle *h, double *d_acc3);
+int pfem2_p2p_last_sent(pfem2_handle *h, int *out); /* records handed over by the last emigrants_send_p2p (synchronises) */
 /* d_acc3: n_nodes x {sum L v_x, sum L v_y, sum L} of the particles this handle holds (no division) */
 int pfem2_project_accumulate(pfem2_handle *h, double *d_acc3);
 int pfem2_project_finalize(pfem2_handle *h, const double *d_acc3, double *d_vx, double *d_vy);

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
-def spill_case(handler, multi_gpu, rank, world, dev):
+def spill_case(handler, multi_gpu, rank, world, dev, protocol):
     """SURVEY N4 across a strip boundary.  A particle in the tolerance band of the LAST cell of rank 0 (second barycentric
     in [-2e-6, 0)) gets a flat sub-cell index that lands in the occupancy word of the next cell, i.e. the FIRST cell of
     rank 1; there it suppresses the re-seeding of that sub-cell.  The neighbour protocol carries those bits in the
@@ -43,7 +43,7 @@ def spill_case(handler, multi_gpu, rank, world, dev):
     ref.step(F, W, 0.01, 3)
     single = (ref.get_particle_count(), ref.stats()["added"])
     ref.close()
-    h = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world)
+    h = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world, migration=protocol)
     h.seed_particles()
     h.init_particle_velocity(F)
     own = (st["cell"] >= int(bounds[rank])) & (st["cell"] < int(bounds[rank + 1]))
@@ -71,13 +71,15 @@ def main():
     fy = (-0.3 * torch.cos(k * x) * torch.sin(k * y)).contiguous()
     dt = 0.25 * (6.0 / nx) * S
     F = (fx, fy)
-    # fast order with the neighbour protocol (default: fixed-size buffers, no host round trip), fast order with the exact-size
-    # protocol, deterministic order (exact-size protocol)
-    for stable, protocol in ((False, "neighbour"), (False, "exact"), (True, "exact")):
+    # fast order over NVLink peer memory (P2P inboxes, no NCCL in the loop), fast order with the neighbour protocol over NCCL
+    # (fixed-size buffers, no host round trip), fast order with the exact-size protocol, deterministic order (exact-size protocol)
+    for stable, protocol in ((False, "p2p"), (False, "neighbour"), (False, "exact"), (True, "exact")):
         W = (torch.zeros_like(fx), torch.zeros_like(fx))
         bounds = multi_gpu.strip_bounds(dm.n_cells, world, align=2 * ny)
         h = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world, migration=protocol, stable_order=stable)
-        assert h.protocol == protocol, (h.protocol, protocol)
+        # "p2p" falls back to "neighbour" (on every rank alike) where CUDA IPC between the GPUs is not available
+        assert h.protocol == protocol or (protocol == "p2p" and h.protocol == "neighbour"), (h.protocol, protocol)
+        protocol = h.protocol if protocol != "p2p" else f"p2p->{h.protocol}"
         h.seed_particles()
         h.init_particle_velocity(F)
         moved = 0
@@ -110,12 +112,13 @@ def main():
             ref.close()
         h.close()
         dist.barrier()
-    # tolerance-band spill of the occupancy bits across the strip boundary: carried by the neighbour protocol
-    single, multi, protocol = spill_case(handler, multi_gpu, rank, world, dev)
-    if rank == 0:
-        assert single[1] == 1, f"the crafted state does not exercise the spill: single GPU re-seeded {single[1]} sub-cells, expected 1"
-        assert multi == single[0], f"{world} GPUs hold {multi} particles, one GPU {single[0]}: spill bits lost at the strip boundary"
-        print(f"MG_SPILL_OK world={world} protocol={protocol} single_gpu(count, added)={single} multi_gpu_count={multi}")
+    # tolerance-band spill of the occupancy bits across the strip boundary: carried by the migration header
+    for want in ("p2p", "neighbour"):
+        single, multi, protocol = spill_case(handler, multi_gpu, rank, world, dev, want)
+        if rank == 0:
+            assert single[1] == 1, f"the crafted state does not exercise the spill: single GPU re-seeded {single[1]} sub-cells, expected 1"
+            assert multi == single[0], f"{world} GPUs hold {multi} particles, one GPU {single[0]}: spill bits lost at the strip boundary"
+            print(f"MG_SPILL_OK world={world} protocol={want}->{protocol} single_gpu(count, added)={single} multi_gpu_count={multi}")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -19,4 +19,4 @@ def test_strip_partitioned_gpus_equal_single_gpu():
            "--master-port", "29561", os.path.join(ROOT, "tests", "mg_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("MG_OK") == 3 and r.stdout.count("MG_SPILL_OK") == 1, r.stdout[-2000:]
+    assert r.stdout.count("MG_OK") == 4 and r.stdout.count("MG_SPILL_OK") == 2, r.stdout[-2000:]

@@ -26,7 +26,10 @@ L, hh = h.L, h.h
 n = 10
 for _ in range(n):
     timed("move", lambda: hh._check(L.pfem2_advect_move(hh._h, F[0].data_ptr(), F[1].data_ptr(), dt, 3), "m"))
-    if h.protocol == "neighbour":
+    if h.protocol == "p2p":
+        timed("emig_send", lambda: hh._check(L.pfem2_emigrants_send_p2p(hh._h, rank), "s"))
+        timed("immig_recv", lambda: hh._check(L.pfem2_immigrants_recv_p2p(hh._h), "r"))
+    elif h.protocol == "neighbour":
         b = h._nbr
         ptr = lambda t: t.data_ptr() if t is not None else None
         timed("emig_pack", lambda: hh._check(L.pfem2_emigrants_pack_neighbours(hh._h, rank, ptr(b["sl"]), ptr(b["sr"]), h.migration_cap), "p"))
@@ -44,7 +47,10 @@ for _ in range(n):
         if rb.shape[0]: timed("append", lambda: hh._check(L.pfem2_immigrants_append(hh._h, rb.data_ptr(), rb.shape[0]), "a"))
     timed("finish", lambda: hh._check(L.pfem2_advect_finish(hh._h, F[0].data_ptr(), F[1].data_ptr()), "f"))
     timed("proj_acc", lambda: hh._check(L.pfem2_project_accumulate(hh._h, h.acc3.data_ptr()), "pa"))
-    timed("halo", lambda: mg.exchange_interface(h.acc3, h.iface, None))
+    if h.protocol == "p2p":
+        timed("halo", lambda: hh._check(L.pfem2_project_halo_p2p(hh._h, h.acc3.data_ptr()), "h"))
+    else:
+        timed("halo", lambda: mg.exchange_interface(h.acc3, h.iface, None))
     timed("proj_fin", lambda: hh._check(L.pfem2_project_finalize(hh._h, h.acc3.data_ptr(), W[0].data_ptr(), W[1].data_ptr()), "pf"))
     timed("correct", lambda: h.correct_particle_velocity(F, W))
     timed("count", lambda: h.get_particle_count())

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpfem2_b200.so")
+# PFEM2_LIB_PATH: A/B measurements of kernel variants built side by side (tools/); the product loads the in-tree library
+LIB_PATH = os.environ.get("PFEM2_LIB_PATH") or os.path.join(_HERE, "libpfem2_b200.so")
 
 PFEM2_OK, PFEM2_EINVAL, PFEM2_ECUDA, PFEM2_ECAPACITY, PFEM2_ESTATE = 0, 1, 2, 3, 4
 

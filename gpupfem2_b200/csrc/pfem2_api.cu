@@ -529,11 +529,11 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
     if (advect_tma_enabled(h)) { // default: particle tiles moved by the copy engine, nodal velocity interleaved
         unsigned *sb = h->opt.stable_order ? h->stay_bits : nullptr;
         const int N = h->mesh.n_nodes;
-        const size_t smem = advect_tma_smem_bytes(kThreads);
+        const size_t smem = advect_tma_smem_bytes(kAdvThreads);
         const int *cstart = nullptr;
         int c_lo = 0, c_hi = 0;
 #define PFEM2_ADV_TMA(NSUB)                                                                                                          \
-    PFEM2_LAUNCH((k_advect_locate_tma<MODE, WALK, MASK64, NSUB>), grid, kThreads, smem, h->stream, h->tmap[h->cur], h->geom, h->edge_nbr,   \
+    PFEM2_LAUNCH((k_advect_locate_tma<MODE, WALK, MASK64, NSUB>), grid, kAdvThreads, smem, h->stream, h->tmap[h->cur], h->geom, h->edge_nbr,   \
                  h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, hsub, substeps, C, h->ppc, h->level, h->sub_step, h->ctr, sb,         \
                  h->warp_movers, h->stay, h->opt.stable_order ? h->arrive : (int *)nullptr, h->cell_mask, do_count, h->dv_pending ? h->dv2 : nullptr, h->own_lo, h->own_hi,          \
                  h->mg_bounds, h->mg_ranks, h->mg_rank_count, h->mg_fused ? h->keys[0] : (unsigned *)nullptr, cstart, c_lo, c_hi)
@@ -541,7 +541,7 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
             (void)N;
             const int n0 = h->v2_node_lo, n1 = h->v2_node_hi; // all nodes on a single GPU; a strip's reach otherwise
             if (n1 > n0) PFEM2_LAUNCH(k_pack_nodal, grid_for(n1 - n0, kThreads, 1 << 30), kThreads, 0, h->stream, n0, n1, vel, h->v2);
-            const int grid = grid_for(h->capacity, kThreads, g_num_sms * 4); // persistent: 4 resident blocks per SM
+            const int grid = grid_for(h->capacity, kAdvThreads, g_num_sms * kAdvBlocksPerSM); // persistent: all resident blocks
             if (substeps == 3)
                 PFEM2_ADV_TMA(3);
             else
@@ -551,7 +551,7 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
             // landed (events recorded on the copy stream) and have been interleaved into v2
             pfem2_handle::HostPipe &pp = h->pipe;
             cstart = h->cell_start[h->cs];
-            const int grid = grid_for((long long)h->capacity / pp.K + 1, kThreads, g_num_sms * 4);
+            const int grid = grid_for((long long)h->capacity / pp.K + 1, kAdvThreads, g_num_sms * kAdvBlocksPerSM);
             for (int j = 0; j < pp.K; ++j) {
                 for (; pp.packed_slices <= pp.up_slice[j]; ++pp.packed_slices) {
                     const int s0 = pp.ns[pp.packed_slices], s1 = pp.ns[pp.packed_slices + 1];

@@ -358,8 +358,16 @@ __device__ __forceinline__ int rank_of_cell(unsigned c, const int *__restrict__ 
 constexpr int kAdvTileBytes = 32 * (int)sizeof(ParticleRec); // one warp tile
 constexpr size_t advect_tma_smem_bytes(int threads) { return (size_t)(threads / 32) * (2 * kAdvTileBytes + 2 * sizeof(uint64_t)) + 1024; }
 
+// Block size / resident blocks per SM of the TMA-tiled move pass, compile-time.  Swept on B200 (channel16m, ms per pass):
+// 256x4 8.42, 128x8 8.38, 64x16 8.45 (all 64 registers, 32 warps per SM); 192x5 8.67 (30 warps); 128x7 8.97 (72 registers, 28 warps);
+// 128x6 9.14 and 256x3 9.24 (80 registers, no spills, 24 warps): the pass is latency-bound, resident warps beat registers.
+#ifndef PFEM2_ADV_THREADS
+#define PFEM2_ADV_THREADS 256
+#define PFEM2_ADV_MINB 4
+#endif
+constexpr int kAdvThreads = PFEM2_ADV_THREADS, kAdvBlocksPerSM = PFEM2_ADV_MINB;
 template <int SUBCELL_MODE, bool WALK, bool MASK64, int NSUB>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kAdvThreads, kAdvBlocksPerSM)
 k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
                     const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, const double2 *__restrict__ V2, double h,
                     int substeps, int n_cells, int ppc, int level, double sub_step, Counters *ctr, unsigned *__restrict__ stay_bits,

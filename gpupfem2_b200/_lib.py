@@ -26,7 +26,7 @@ SYMBOLS = (
     "pfem2_immigrants_append", "pfem2_advect_finish", "pfem2_project_accumulate", "pfem2_project_finalize",
     "pfem2_set_rank_bounds", "pfem2_emigrants_pack_neighbours", "pfem2_immigrants_append_device",
     "pfem2_p2p_inbox_create", "pfem2_p2p_connect", "pfem2_emigrants_send_p2p", "pfem2_immigrants_recv_p2p",
-    "pfem2_project_halo_p2p", "pfem2_p2p_last_sent",
+    "pfem2_project_halo_p2p", "pfem2_p2p_last_sent", "pfem2_project_dual", "pfem2_project_dual_ptrs",
 )
 
 
@@ -74,6 +74,8 @@ def load():
     L.pfem2_advect_ptrs.argtypes = [vp, vp, d, i]
     L.pfem2_project.argtypes = [vp, vp, vp]
     L.pfem2_project_ptrs.argtypes = [vp, vp]
+    L.pfem2_project_dual.argtypes = [vp, vp, vp, vp, vp]
+    L.pfem2_project_dual_ptrs.argtypes = [vp, vp, vp]
     L.pfem2_correct.argtypes = [vp, vp, vp, vp, vp]
     L.pfem2_correct_ptrs.argtypes = [vp, vp, vp]
     L.pfem2_particle_count.argtypes = [vp, C.POINTER(i)]

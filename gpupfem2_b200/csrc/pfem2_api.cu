@@ -759,7 +759,8 @@ void launch_project_cells(pfem2_handle *h, const ParticleSoA &p, int c_lo = -1, 
         PFEM2_LAUNCH(k_project_cells<16>, grid_for(nc * 16), kThreads, 0, st, c_lo, c_hi, p, h->cell_start[h->cs], h->partial);
 }
 
-int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
+int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table, double *cx = nullptr, double *cy = nullptr,
+               double *const *table_copy = nullptr)
 {
     if (!h) return PFEM2_EINVAL;
     if (!h->seeded) return fail(h, PFEM2_ESTATE, "project before seed");
@@ -780,7 +781,7 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table)
     }
     PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
     PFEM2_LAUNCH(k_project_nodes, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, 0, N, h->node_off, (const int *)h->node_inc, h->partial,
-                 vx, vy, table);
+                 vx, vy, table, cx, cy, table_copy);
     CU(cudaGetLastError());
     return PFEM2_OK;
 }
@@ -1092,6 +1093,16 @@ int pfem2_advect_ptrs(pfem2_handle *h, double *const *t, double dt, int substeps
 }
 int pfem2_project(pfem2_handle *h, double *vx, double *vy) { return do_project(h, vx, vy, nullptr); }
 int pfem2_project_ptrs(pfem2_handle *h, double *const *t) { return do_project(h, nullptr, nullptr, t); }
+int pfem2_project_dual(pfem2_handle *h, double *vx, double *vy, double *cx, double *cy)
+{
+    if (!vx || !vy || !cx || !cy) return h ? fail(h, PFEM2_EINVAL, "project_dual: null nodal array") : PFEM2_EINVAL;
+    return do_project(h, vx, vy, nullptr, cx, cy, nullptr);
+}
+int pfem2_project_dual_ptrs(pfem2_handle *h, double *const *t, double *const *t_copy)
+{
+    if (!t || !t_copy) return h ? fail(h, PFEM2_EINVAL, "project_dual: null pointer table") : PFEM2_EINVAL;
+    return do_project(h, nullptr, nullptr, t, nullptr, nullptr, t_copy);
+}
 int pfem2_correct(pfem2_handle *h, const double *vx, const double *vy, const double *ox, const double *oy)
 {
     return do_correct(h, nodal(vx, vy, nullptr), nodal(ox, oy, nullptr), true);

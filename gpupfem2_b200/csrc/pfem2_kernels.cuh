@@ -1704,11 +1704,15 @@ k_project_cells(int c_lo, int n_cells, ParticleSoA p, const int *__restrict__ ce
 
 __global__ void __launch_bounds__(kThreads)
 k_project_nodes(int node_lo, int n_nodes, const int *__restrict__ node_off, const int *__restrict__ node_inc,
-                const double *__restrict__ partial, double *vx_arg, double *vy_arg, double *const *table)
+                const double *__restrict__ partial, double *vx_arg, double *vy_arg, double *const *table, double *cx_arg = nullptr,
+                double *cy_arg = nullptr, double *const *table_copy = nullptr)
 {
-    // nodes [node_lo, n_nodes)
+    // nodes [node_lo, n_nodes).  Optional second destination (pfem2_project_dual): the cases copy the projected field into their
+    // "old" solution right after the call (copy_d2d, cases/Cylinder2D/main.cu:804-805); written here it costs no extra pass
     double *Vx = table ? table[0] : vx_arg;
     double *Vy = table ? table[1] : vy_arg;
+    double *Cx = table_copy ? table_copy[0] : cx_arg;
+    double *Cy = table_copy ? table_copy[1] : cy_arg;
     const int i = node_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     double sx = 0.0, sy = 0.0, sw = 0.0;
@@ -1719,8 +1723,13 @@ k_project_nodes(int node_lo, int n_nodes, const int *__restrict__ node_off, cons
         sy = __dadd_rn(sy, a[1]);
         sw = __dadd_rn(sw, a[2]);
     }
-    Vx[i] = __ddiv_rn(sx, sw);
-    Vy[i] = __ddiv_rn(sy, sw);
+    const double qx = __ddiv_rn(sx, sw), qy = __ddiv_rn(sy, sw);
+    Vx[i] = qx;
+    Vy[i] = qy;
+    if (Cx) {
+        Cx[i] = qx;
+        Cy[i] = qy;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

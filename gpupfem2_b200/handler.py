@@ -176,6 +176,12 @@ class ParticleHandler2D:
         """Overwrites vel[0], vel[1] with the projected nodal velocity (like the reference)."""
         self._check(self._L.pfem2_project(self._h, vel[0].data_ptr(), vel[1].data_ptr()), "projectVelocityOntoGrid")
 
+    def project_velocity_onto_grid_dual(self, vel, vel_copy):
+        """Extension: projectVelocityOntoGrid(vel) that also writes the result into vel_copy (the cases' copy_d2d into the
+        "old" solution right after the call, cases/Cylinder2D/main.cu:804-805)."""
+        self._check(self._L.pfem2_project_dual(self._h, vel[0].data_ptr(), vel[1].data_ptr(), vel_copy[0].data_ptr(),
+                                               vel_copy[1].data_ptr()), "projectVelocityOntoGrid")
+
     def correct_particle_velocity(self, vel, vel_old):
         self._check(self._L.pfem2_correct(self._h, vel[0].data_ptr(), vel[1].data_ptr(), vel_old[0].data_ptr(),
                                           vel_old[1].data_ptr()), "correctParticleVelocity")
@@ -200,6 +206,9 @@ class ParticleHandler2D:
 
     def project_velocity_onto_grid_ptrs(self, table: torch.Tensor):
         self._check(self._L.pfem2_project_ptrs(self._h, table.data_ptr()), "projectVelocityOntoGrid")
+
+    def project_velocity_onto_grid_dual_ptrs(self, table: torch.Tensor, table_copy: torch.Tensor):
+        self._check(self._L.pfem2_project_dual_ptrs(self._h, table.data_ptr(), table_copy.data_ptr()), "projectVelocityOntoGrid")
 
     def correct_particle_velocity_ptrs(self, table: torch.Tensor, table_old: torch.Tensor):
         self._check(self._L.pfem2_correct_ptrs(self._h, table.data_ptr(), table_old.data_ptr()), "correctParticleVelocity")

@@ -67,6 +67,11 @@ void ParticleHandler2D::projectVelocityOntoGrid(deviceVector<double*> &velocity)
     check(pfem2_project_ptrs(handle, velocity.data), "projectVelocityOntoGrid");
 }
 
+void ParticleHandler2D::projectVelocityOntoGrid(deviceVector<double*> &velocity, deviceVector<double*> &velocityCopy)
+{
+    check(pfem2_project_dual_ptrs(handle, velocity.data, velocityCopy.data), "projectVelocityOntoGrid");
+}
+
 const Particle2D *ParticleHandler2D::getParticles() const
 {
     const void *aos = nullptr;

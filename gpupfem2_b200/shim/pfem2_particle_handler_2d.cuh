@@ -44,6 +44,8 @@ public:
 
     // writes the projected nodal velocity through the two pointers held in `velocity`
     void projectVelocityOntoGrid(deviceVector<double*> &velocity);
+    // extension: also writes the projected field into `velocityCopy` (replaces the copy_d2d pair that follows the call in the cases)
+    void projectVelocityOntoGrid(deviceVector<double*> &velocity, deviceVector<double*> &velocityCopy);
 
     // device pointer to 96-byte Particle2D records, materialised on demand from the library's SoA storage;
     // valid until the next mutating call

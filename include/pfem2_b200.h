@@ -112,6 +112,11 @@ int pfem2_advect_ptrs(pfem2_handle *h, double *const *d_vel2, double dt, int sub
 /* projectVelocityOntoGrid(velocity): WRITES the two nodal arrays   particle_handler_2d.cu:350-361 */
 int pfem2_project(pfem2_handle *h, double *d_vx, double *d_vy);
 int pfem2_project_ptrs(pfem2_handle *h, double *const *d_vel2);
+/* Extension: the same projection, additionally written into a second pair of nodal arrays.  The cases copy the
+ * projected field into their "old" solution right after the call (copy_d2d, cases/Cylinder2D/main.cu:804-805,
+ * cases/PoiseuilleFlow2D/main.cu:663-664); here the node pass of the projection writes both, so the two copies go away. */
+int pfem2_project_dual(pfem2_handle *h, double *d_vx, double *d_vy, double *d_vx_copy, double *d_vy_copy);
+int pfem2_project_dual_ptrs(pfem2_handle *h, double *const *d_vel2, double *const *d_vel_copy2);
 /* correctParticleVelocity(velocitySolution, velocitySolutionOld)   particle_handler_2d.cu:344-348 */
 int pfem2_correct(pfem2_handle *h, const double *d_vx, const double *d_vy, const double *d_vx_old, const double *d_vy_old);
 int pfem2_correct_ptrs(pfem2_handle *h, double *const *d_vel2, double *const *d_vel_old2);

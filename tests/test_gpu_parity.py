@@ -239,6 +239,35 @@ def test_pointer_table_flavour_and_step_host(gpu, oracle):
     assert np.array_equal(w[0].cpu().numpy(), w2[0].cpu().numpy()) and np.array_equal(w[0].cpu().numpy(), hwx)
 
 
+def test_project_dual_writes_both_destinations(gpu, oracle):
+    """Extension pfem2_project_dual(_ptrs): the projection plus the cases' copy into the "old" solution in one node pass."""
+    c = cases.build_case("tiny_l3")
+    oracle.complete_mesh(c.mesh)
+    dm = gpu.DeviceMesh(c.mesh)
+    ha, hb = gpu.ParticleHandler2D(dm, c.level, stable_order=True), gpu.ParticleHandler2D(dm, c.level, stable_order=True)
+    f, w = dev_field(c)
+    w2, old2 = (torch.zeros_like(f[0]), torch.zeros_like(f[0])), (torch.full_like(f[0], 7.0), torch.full_like(f[0], 7.0))
+    w3, old3 = (torch.zeros_like(f[0]), torch.zeros_like(f[0])), (torch.full_like(f[0], 7.0), torch.full_like(f[0], 7.0))
+    t3 = torch.tensor([w3[0].data_ptr(), w3[1].data_ptr()], dtype=torch.int64, device="cuda")
+    o3 = torch.tensor([old3[0].data_ptr(), old3[1].data_ptr()], dtype=torch.int64, device="cuda")
+    for h in (ha, hb):
+        h.seed_particles()
+        h.init_particle_velocity(f)
+    for _ in range(3):
+        ha.advect_particles(f, c.dt, c.substeps)
+        hb.advect_particles(f, c.dt, c.substeps)
+        ha.project_velocity_onto_grid(w)
+        hb.project_velocity_onto_grid_dual(w2, old2)
+        hb.project_velocity_onto_grid_dual_ptrs(t3, o3)
+        for k in range(2):
+            ref = w[k].cpu().numpy()
+            for other in (w2[k], old2[k], w3[k], old3[k]):
+                assert np.array_equal(ref, other.cpu().numpy(), equal_nan=True)
+        ha.correct_particle_velocity(f, w)
+        hb.correct_particle_velocity(f, old2)
+    assert_states_equal(ha.download(), hb.download(), "project_dual")
+
+
 def test_download_upload_roundtrip_and_resort(gpu, oracle):
     """Checkpoint/restart: a shuffled upload is re-sorted by cell and continues to the same state."""
     c = cases.build_case("tiny_l2")

@@ -114,7 +114,7 @@ int pfem2_project(pfem2_handle *h, double *d_vx, double *d_vy);
 int pfem2_project_ptrs(pfem2_handle *h, double *const *d_vel2);
 /* Extension: the same projection, additionally written into a second pair of nodal arrays.  The cases copy the
  * projected field into their "old" solution right after the call (copy_d2d, cases/Cylinder2D/main.cu:804-805,
- * cases/PoiseuilleFlow2D/main.cu:663-664); here the node pass of the projection writes both, so the two copies go away. */
+ * cases/PoiseuilleFlow2D/main.cu:664-665); here the node pass of the projection writes both, so the two copies go away. */
 int pfem2_project_dual(pfem2_handle *h, double *d_vx, double *d_vy, double *d_vx_copy, double *d_vy_copy);
 int pfem2_project_dual_ptrs(pfem2_handle *h, double *const *d_vel2, double *const *d_vel_copy2);
 /* correctParticleVelocity(velocitySolution, velocitySolutionOld)   particle_handler_2d.cu:344-348 */

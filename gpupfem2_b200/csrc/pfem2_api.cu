@@ -1600,6 +1600,16 @@ int pfem2_immigrants_append_device(pfem2_handle *h, const void *d_buffer, int ca
 }
 
 // ---- P2P transport (NVLink peer memory through CUDA IPC) ----
+// watchdog of the device-side waits: 20 s, PFEM2_P2P_TIMEOUT_S overrides (ranks that reach a step far apart in time)
+static unsigned long long p2p_timeout_ns()
+{
+    static const unsigned long long ns = [] {
+        const char *e = getenv("PFEM2_P2P_TIMEOUT_S");
+        const double s = e ? atof(e) : 20.0;
+        return (unsigned long long)((s > 0.0 ? s : 20.0) * 1e9);
+    }();
+    return ns;
+}
 int pfem2_p2p_inbox_create(pfem2_handle *h, int side, int capacity_records, int n_interface_nodes, const int *h_interface_nodes,
                            void *ipc_handle_out)
 {
@@ -1697,7 +1707,7 @@ int pfem2_immigrants_recv_p2p(pfem2_handle *h)
     unsigned char *ir = h->p2p.peer[1] ? (unsigned char *)h->p2p.inbox[1] : nullptr;
     if (!il && !ir) return PFEM2_OK;
     PFEM2_LAUNCH(k_p2p_wait, 1, 1, 0, st, il ? &((const P2PInboxHead *)il)->flag_mig : nullptr,
-                 ir ? &((const P2PInboxHead *)ir)->flag_mig : nullptr, seq, h->ctr, 20ull * 1000000000ull);
+                 ir ? &((const P2PInboxHead *)ir)->flag_mig : nullptr, seq, h->ctr, p2p_timeout_ns());
     int rc;
     if (il && (rc = append_migration_block(h, (const int4 *)(il + p2p_block_offset(cap, parity)), cap, 1))) return rc;
     if (ir && (rc = append_migration_block(h, (const int4 *)(ir + p2p_block_offset(cap, parity)), cap, 0))) return rc;
@@ -1725,7 +1735,7 @@ int pfem2_project_halo_p2p(pfem2_handle *h, double *d_acc3)
     }
     PFEM2_LAUNCH(k_p2p_publish_flag, 1, 1, 0, st, flags[0], flags[1], seq);
     PFEM2_LAUNCH(k_p2p_wait, 1, 1, 0, st, h->p2p.peer[0] ? &((const P2PInboxHead *)h->p2p.inbox[0])->flag_halo : nullptr,
-                 h->p2p.peer[1] ? &((const P2PInboxHead *)h->p2p.inbox[1])->flag_halo : nullptr, seq, h->ctr, 20ull * 1000000000ull);
+                 h->p2p.peer[1] ? &((const P2PInboxHead *)h->p2p.inbox[1])->flag_halo : nullptr, seq, h->ctr, p2p_timeout_ns());
     for (int k = 0; k < 2; ++k) {
         if (!h->p2p.peer[k]) continue;
         const int n = h->p2p.n_idx[k];

@@ -186,7 +186,7 @@ int pfem2_immigrants_append_device(pfem2_handle *h, const void *d_buffer, int ca
  *   emigrants_send_p2p      the pack kernel stores the emigrants' records straight into the neighbours' inboxes, a publish
  *                           kernel writes the header, fences (system scope) and releases a sequence number;
  *   immigrants_recv_p2p     this strip's stream waits for both neighbours' sequence numbers (device-side acquire spin with a
- *                           20 s watchdog: a dead peer raises an error instead of hanging the GPU) and appends from its own memory;
+ *                           20 s watchdog (PFEM2_P2P_TIMEOUT_S overrides): a dead peer raises an error instead of hanging the GPU) and appends from its own memory;
  *   project_halo_p2p        between project_accumulate and project_finalize: interface-node accumulators are stored into the
  *                           neighbours' inboxes, awaited and added (a + b == b + a: both strips get the same bits).
  * h_interface_nodes: ascending ids of the nodes shared with that neighbour (both strips must pass the same list).  All

@@ -179,3 +179,26 @@ def test_multi_rank_step_equals_single_rank(tmp_path, oracle, world, protocol):
     assert sum(g[4] for g in gathered) > 0, "no particle crossed the interface: the test would prove nothing"
     for (_, wx, wy, mine, _) in gathered:
         assert rel_inf(wx[mine], rwx[mine]) <= REL_TOL and rel_inf(wy[mine], rwy[mine]) <= REL_TOL
+
+
+def test_interface_lists_are_symmetric_and_ordered():
+    """Both strips of an interface must hold the SAME ascending node list: the P2P halo (k_halo_send / k_halo_add) and the NCCL
+    halo exchange pair entries by position.  Structured strips, and an unstructured mesh cut by cell index (where a strip
+    can touch non-adjacent strips: the P2P transport then declines and the NCCL path is used)."""
+    cyl = np.load(os.path.join(ROOT, "tests", "golden", "mesh_cylinder3.npz"))
+    cases_ = [(structured_channel(24, 8, 3.0, 1.0, colmajor=True).cells.astype(np.int64), 16, 4),
+              (cyl["cells"].astype(np.int64), 1, 3)]
+    for cells, align, world in cases_:
+        n = (cells.shape[0] // align) * align
+        bounds = multi_gpu.strip_bounds(n, world, align=align)
+        lists = [multi_gpu.interface_nodes(cells[:n], bounds, r) for r in range(world)]
+        for r in range(world):
+            for s, nodes in lists[r].items():
+                assert r in lists[s], (r, s)
+                assert torch.equal(nodes, lists[s][r])
+                assert torch.all(nodes[1:] > nodes[:-1])  # strictly ascending, no duplicates
+    # structured strips only ever touch their neighbours
+    cells = cases_[0][0]
+    bounds = multi_gpu.strip_bounds(cells.shape[0], 4, align=16)
+    for r in range(4):
+        assert all(abs(s - r) == 1 for s in multi_gpu.interface_nodes(cells, bounds, r))

@@ -177,6 +177,31 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_local_cpus(index):
+    """Run this process on the CPUs NVML reports as local to GPU `index` (same NUMA node / PCIe root), so that the pinned host
+    buffers of the e2e leg are allocated next to the GPU.  Returns the previous affinity mask (to restore) or None if nothing
+    was changed.  PFEM2_BENCH_AFFINITY=0 disables it."""
+    if os.environ.get("PFEM2_BENCH_AFFINITY", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+        dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(dev, (os.cpu_count() + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cur = os.sched_getaffinity(0)
+        want = local & cur  # never leave the cpuset the container grants
+        if want and want != cur:
+            os.sched_setaffinity(0, want)
+            return cur
+    except Exception:
+        pass
+    return None
+
+
 def channel_params(args, world=1):
     nx, ny, lx, ly, lvl = WORKLOADS[args.workload]
     if args.workload in WEAK:
@@ -321,6 +346,7 @@ def run_ours(args):
                 "phases": per_phase}
 
     # e2e: the same step through the C-ABI call with pinned HOST nodal buffers (H2D + D2H inside the timed region)
+    prev_affinity = bind_to_gpu_local_cpus(local)  # pinned buffers next to the GPU (NUMA); restored before the CPU baseline runs
     hF = [t.cpu().pin_memory() for t in F]
     hW = [torch.empty_like(t).pin_memory() for t in hF]
     e2e_counts = []
@@ -331,9 +357,12 @@ def run_ours(args):
         e2e_counts.append(h.step_host(hF[0], hF[1], hW[0], hW[1], dt, args.substeps))
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    if prev_affinity:
+        os.sched_setaffinity(0, prev_affinity)
     nodal_bytes = 2 * dm.n_nodes * 8
     e2e = {"value": float(sum(e2e_counts)) / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": nodal_bytes,
            "d2h_bytes_per_step": nodal_bytes + 32, "ms_per_step": t_e2e / args.steps * 1e3,
+           "host_cpus": ("bound to the GPU-local CPUs (NVML affinity)" if prev_affinity else "process default"),
            "api": "pfem2_step_host (C ABI), pinned host nodal buffers in, projected nodal field + count out; the call pipelines the "
                   "upload with the move pass and the projection with the download in chunks of the cell range (pfem2_options.host_pipeline)"}
 

@@ -55,3 +55,28 @@ def test_no_cpu_fallback_in_product_path():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "pfem2_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_header_is_plain_c99_and_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: include/pfem2_b200.h must compile as C99 (no C++ types), and a C program must link against the
+    library and call an entry point that needs no GPU."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    src = tmp_path / "cabi.c"
+    src.write_text('#include <stdio.h>\n#include "pfem2_b200.h"\n'
+                   "int main(void) { pfem2_options o; pfem2_default_options(&o);\n"
+                   '  printf("%d %d %s\\n", o.struct_size == (int)sizeof o, pfem2_create(0, 0, 2, 0), pfem2_version()); return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", f"-I{inc}", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "cabi"
+    r = subprocess.run(["gcc", "-std=c99", f"-I{inc}", str(src), "-o", str(exe), f"-L{libdir}", "-lpfem2_b200", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split()[:2] == ["1", str(_lib.PFEM2_EINVAL)] and "sm_100a" in r.stdout, (r.stdout, r.stderr)

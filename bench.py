@@ -281,7 +281,8 @@ def run_ours(args):
     h = handler.ParticleHandler2D(dm, level, max_division_level=8, capacity_factor=args.capacity_factor,
                                   scatter_tma=bool(int(os.environ.get("PFEM2_SCATTER_TMA", "0"))),
                                   lane_per_record=bool(int(os.environ.get("PFEM2_LANE_PER_RECORD", "0"))),
-                                  host_pipeline=int(os.environ.get("PFEM2_HOST_PIPELINE", "0")))
+                                  host_pipeline=int(os.environ.get("PFEM2_HOST_PIPELINE", "0")),
+                                  lazy_sort=bool(int(os.environ.get("PFEM2_LAZY_SORT", "0"))))  # experimental A/B switch, default off
     h.seed_particles()
     h.init_particle_velocity(F)
     torch.cuda.synchronize()
@@ -379,6 +380,8 @@ def run_ours(args):
                    "setup_s": t_setup},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
+    if int(os.environ.get("PFEM2_LAZY_SORT", "0")):
+        out["config"]["lazy_sort"] = True
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args)
     h.close()

@@ -4,6 +4,7 @@
 #include "../../include/pfem2_b200.h"
 
 #include "pfem2_kernels.cuh"
+#include "pfem2_lazy.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -127,6 +128,16 @@ struct pfem2_handle {
         int packed_slices = 0;            // upload slices already interleaved into v2
     } pipe;
 
+    // lazy re-sort (pfem2_options.lazy_sort): the current buffer is dense but in the order of the PREVIOUS step's cells; vals[perm_buf]
+    // maps sorted position -> record index (padded to a multiple of 32 with a valid row), keys[1] holds the new cells of the last move pass
+    bool permuted = false;
+    int perm_buf = 0;
+    int *tail_cursor = nullptr;              // device int: re-seeded records appended behind the dense array
+    bool lazy_swizzle = true;                // 64-byte swizzle of the lazy move pass's tiles (PFEM2_LAZY_SWIZZLE=0: linear tiles, the fallback)
+    CUtensorMap gmap[2], omap[2];            // lazy move pass: gather maps (box {16, 1}) and tile-store maps (box {16, 32}) of the two buffers
+    void *lzmap_base[2] = {nullptr, nullptr};
+    int lzmap_rows[2] = {0, 0};
+
     // P2P transport of the neighbour protocol (multi-GPU): inboxes in this GPU's memory the neighbours store into, and the
     // neighbours' inboxes mapped through CUDA IPC.  side 0 = left neighbour (rank - 1), side 1 = right neighbour (rank + 1)
     struct P2P {
@@ -244,8 +255,8 @@ int alloc_particle_scratch(pfem2_handle *h, int cap)
 {
     int rc;
     for (int k = 0; k < 2; ++k) {
-        if ((rc = dev_alloc(h, &h->keys[k], cap))) return rc;
-        if ((rc = dev_alloc(h, &h->vals[k], cap))) return rc;
+        if ((rc = dev_alloc(h, &h->keys[k], (size_t)cap + 32))) return rc; // + one tile: the lazy re-sort pads its index arrays to 32
+        if ((rc = dev_alloc(h, &h->vals[k], (size_t)cap + 32))) return rc;
     }
     if ((rc = dev_alloc(h, &h->rs_hist, rs_hist_elems(cap)))) return rc;
     if ((rc = dev_alloc(h, &h->rs_scan_scratch, rs_scan_scratch_elems(cap)))) return rc;
@@ -522,6 +533,49 @@ int record_tensor_map(pfem2_handle *h, int k)
 
 bool advect_tma_enabled(const pfem2_handle *h) { return h->opt.lane_per_record == 0; }
 
+// ---- lazy re-sort (pfem2_options.lazy_sort, EXPERIMENTAL; kernels in pfem2_lazy.cuh) ----
+bool lazy_enabled(const pfem2_handle *h)
+{
+    return h->opt.lazy_sort != 0 && h->own_lo == 0 && h->own_hi == h->mesh.n_cells; // (incompatible options are refused at create)
+}
+
+// maps of a record buffer for the lazy move pass: the same [rows x 64 B] tensor as record_tensor_map, once with box {16, 1} (tile::gather4
+// takes four row indices) and once with box {16, 32} (the dense tile store), both with the handle's swizzle mode
+int lazy_record_maps(pfem2_handle *h, int k)
+{
+    void *base = h->soa[k].records();
+    if (h->lzmap_base[k] == base && h->lzmap_rows[k] == h->capacity) return PFEM2_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, PFEM2_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {16, (cuuint64_t)h->capacity};
+    const cuuint64_t strides[1] = {sizeof(ParticleRec)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = h->lazy_swizzle ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    for (int which = 0; which < 2; ++which) {
+        const cuuint32_t box[2] = {16, which ? 32u : 1u};
+        const CUresult r = ((EncodeTiledFn)fn)(which ? &h->omap[k] : &h->gmap[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, base, dims, strides, box, estr,
+                                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(h, PFEM2_ECUDA, which ? "cuTensorMapEncodeTiled (lazy store map) failed" : "cuTensorMapEncodeTiled (gather map) failed");
+    }
+    h->lzmap_base[k] = base;
+    h->lzmap_rows[k] = h->capacity;
+    return PFEM2_OK;
+}
+
+// back to the ordinary state: the sorted order is made physical in the other buffer.  Every reader of the physical order calls this.
+int materialize(pfem2_handle *h)
+{
+    if (!h->permuted) return PFEM2_OK;
+    PFEM2_LAUNCH(k_materialize, grid_for(h->capacity), kThreads, 0, h->stream, h->soa[h->cur], h->soa[h->cur ^ 1],
+                 (const unsigned *)h->vals[h->perm_buf], h->ctr);
+    h->cur ^= 1;
+    h->permuted = false;
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
 template <int MODE, bool WALK, bool MASK64>
 void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int do_count)
 {
@@ -594,6 +648,7 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     CU(cudaSetDevice(h->device));
     int rc;
     if ((rc = sync_counters(h))) return rc;
+    if ((rc = materialize(h))) return rc;
     // capacity policy: keep room for the growth seen so far (re-seeding only ever adds)
     {
         const long long margin = std::max<long long>({(long long)h->host_count / 16, 4ll * h->host_added, 4096ll});
@@ -730,9 +785,106 @@ int append_migration_block(pfem2_handle *h, const int4 *buf, int capacity_record
     return PFEM2_OK;
 }
 
+// advectParticles in the lazy re-sort: gathered move pass -> plan -> rank pass -> appended re-seeds (pfem2_lazy.cuh)
+int advect_lazy(pfem2_handle *h, NodalVel vel, double dt, int substeps)
+{
+    if (!h->seeded) return fail(h, PFEM2_ESTATE, "advect before seed");
+    if (h->move_pending) return fail(h, PFEM2_ESTATE, "advect while a multi-GPU move is pending");
+    if (substeps < 1) return fail(h, PFEM2_EINVAL, "particleSubsteps must be >= 1");
+    CU(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = sync_counters(h))) return rc;
+    {   // the dense array holds the lost particles of the pass as well and the re-seeds are appended behind it: keep twice the margin
+        const long long margin = 2 * std::max<long long>({(long long)h->host_count / 16, 4ll * h->host_added, 4096ll});
+        if ((long long)h->host_count + margin > h->capacity) {
+            const long long want = std::max<long long>((long long)(1.25 * h->host_count), (long long)h->host_count + 2 * margin);
+            if (want > 2147483647ll - 1024) return fail(h, PFEM2_ECAPACITY, "particle count exceeds 32-bit indexing");
+            if ((rc = materialize(h))) return rc;
+            if ((rc = grow(h, (int)want))) return rc;
+        }
+    }
+    cudaStream_t st = h->stream;
+    const int C = h->mesh.n_cells, N = h->mesh.n_nodes;
+    h->partials_valid = false;
+    h->last_substeps = substeps;
+    const double hsub = dt / substeps;
+    {
+        const size_t len = (size_t)C + 1;
+        CU(cudaMemsetAsync(h->stay, 0, sizeof(int) * len, st));
+        CU(cudaMemsetAsync(h->arrive, 0, sizeof(int) * len, st));
+        CU(cudaMemsetAsync(h->cursor, 0, sizeof(int) * len, st));
+        CU(cudaMemsetAsync(h->cell_mask, 0, sizeof(unsigned long long) * len, st));
+    }
+    PFEM2_LAUNCH(k_begin_advect, 1, 1, 0, st, h->ctr, h->capacity);
+    if (!h->tail_cursor) CU(cudaMalloc((void **)&h->tail_cursor, sizeof(int)));
+    CU(cudaMemsetAsync(h->tail_cursor, 0, sizeof(int), st));
+    if (!h->permuted) { // physically sorted (seed, upload, materialize): the identity permutation
+        const int padded = (h->host_count + 31) & ~31;
+        PFEM2_LAUNCH(k_iota, grid_for(padded), kThreads, 0, st, h->vals[h->perm_buf], h->ctr, padded);
+    }
+    if (!h->v2) CU(cudaMalloc((void **)&h->v2, sizeof(double2) * (size_t)N));
+    if ((rc = lazy_record_maps(h, h->cur))) return rc;
+    if ((rc = lazy_record_maps(h, h->cur ^ 1))) return rc;
+    {
+        PhaseScope ps(h, PFEM2_PHASE_ADVECT);
+        PFEM2_LAUNCH(k_pack_nodal, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, 0, N, vel, h->v2);
+        const size_t smem = advect_tma_smem_bytes(kAdvThreads);
+        const int grid = grid_for(h->capacity, kAdvThreads, g_num_sms * kAdvBlocksPerSM);
+        const bool m64 = h->ppc > 32, walk = h->opt.exact_search == 0;
+        const int mode = h->opt.subcell_mode ? 1 : 0;
+#define PFEM2_LAZY_ADV(M, W, B, NSUB, SWZ)                                                                                                    \
+    PFEM2_LAUNCH((k_advect_locate_lazy<M, W, B, NSUB, SWZ>), grid, kAdvThreads, smem, st, h->gmap[h->cur], h->omap[h->cur ^ 1],                 \
+                 (const int4 *)h->vals[h->perm_buf], h->keys[1], h->geom, h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, hsub, \
+                 substeps, C, h->ppc, h->level, h->sub_step, h->ctr, h->stay, h->cell_mask, h->dv_pending ? h->dv2 : (const double2 *)nullptr)
+#define PFEM2_LAZY_ADV_N(M, W, B)                                                                                                             \
+    do {                                                                                                                                      \
+        if (!h->lazy_swizzle) PFEM2_LAZY_ADV(M, W, B, 0, false);                                                                              \
+        else if (substeps == 3) PFEM2_LAZY_ADV(M, W, B, 3, true);                                                                             \
+        else PFEM2_LAZY_ADV(M, W, B, 0, true);                                                                                                \
+    } while (0)
+        if (mode == 0) {
+            if (walk) { if (m64) PFEM2_LAZY_ADV_N(0, true, true); else PFEM2_LAZY_ADV_N(0, true, false); }
+            else      { if (m64) PFEM2_LAZY_ADV_N(0, false, true); else PFEM2_LAZY_ADV_N(0, false, false); }
+        } else {
+            if (walk) { if (m64) PFEM2_LAZY_ADV_N(1, true, true); else PFEM2_LAZY_ADV_N(1, true, false); }
+            else      { if (m64) PFEM2_LAZY_ADV_N(1, false, true); else PFEM2_LAZY_ADV_N(1, false, false); }
+        }
+#undef PFEM2_LAZY_ADV_N
+#undef PFEM2_LAZY_ADV
+    }
+    CU(cudaGetLastError());
+    h->dv_pending = false; // the move pass applied the deferred correction
+    h->cur ^= 1;           // the dense output is the current buffer now (order of the previous step's cells, lost particles included)
+    {
+        PhaseScope ps(h, PFEM2_PHASE_REORDER);
+        PFEM2_LAUNCH(k_plan_cells, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, C, 0, C, h->ppc, 1, h->stay, h->arrive, h->cell_mask, h->packed,
+                     h->ctr);
+        exclusive_scan_dev<unsigned long long>(h->packed, h->packed, h->own_len_dev, 1, 0, C, h->scan_scratch64, st);
+        PFEM2_LAUNCH(k_plan_finish, 1, 1, 0, st, C, h->packed, h->ctr);
+        PFEM2_LAUNCH(k_init_cursor, grid_for(C, kThreads, 1 << 30), kThreads, 0, st, 0, C, h->packed, h->cursor);
+        unsigned *src_new = h->vals[h->perm_buf ^ 1];
+        PFEM2_LAUNCH(k_rank, grid_for(h->capacity), kThreads, 0, st, (const unsigned *)h->keys[1], (const int *)&h->ctr->n_old, h->cursor, src_new,
+                     h->ctr);
+        PFEM2_LAUNCH(k_reseed_lazy, grid_for(C + 1, kThreads, 1 << 30), kThreads, 0, st, 0, C, h->ppc, (const double2 *)h->mesh.d_vertices, h->geom,
+                     h->centers, vel, h->cell_mask, h->stay, h->packed, h->soa[h->cur], (const int *)&h->ctr->n_old, h->tail_cursor, src_new,
+                     h->cell_start[h->cs ^ 1], h->ctr);
+        h->cs ^= 1;
+        h->perm_buf ^= 1;
+        h->permuted = true;
+    }
+    CU(cudaGetLastError());
+    if ((rc = queue_readback(h))) return rc;
+    if (h->opt.verbose) {
+        if ((rc = sync_counters(h))) return rc;
+        printf("Particle handler contains %d particles\n", h->host_count); // particle_handler_2d.cu:341
+    }
+    return PFEM2_OK;
+}
+
 int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
 {
     int rc;
+    if (h && lazy_enabled(h)) return advect_lazy(h, vel, dt, substeps);
     if ((rc = advect_move(h, vel, dt, substeps, 1))) return rc;
     return advect_finish(h, vel, 0);
 }
@@ -748,6 +900,18 @@ void launch_project_cells(pfem2_handle *h, const ParticleSoA &p, int c_lo = -1, 
         c_hi = h->own_hi;
     }
     const long long nc = c_hi - c_lo;
+    if (h->permuted) { // lazy re-sort: the segment [cell_start[c], cell_start[c + 1]) names its records through the permutation
+        const unsigned *src = h->vals[h->perm_buf];
+        if (ppc <= 4)
+            PFEM2_LAUNCH(k_project_cells_lazy<2>, grid_for(nc * 2), kThreads, 0, st, c_lo, c_hi, p, src, h->cell_start[h->cs], h->partial);
+        else if (ppc <= 16)
+            PFEM2_LAUNCH(k_project_cells_lazy<4>, grid_for(nc * 4), kThreads, 0, st, c_lo, c_hi, p, src, h->cell_start[h->cs], h->partial);
+        else if (ppc <= 36)
+            PFEM2_LAUNCH(k_project_cells_lazy<8>, grid_for(nc * 8), kThreads, 0, st, c_lo, c_hi, p, src, h->cell_start[h->cs], h->partial);
+        else
+            PFEM2_LAUNCH(k_project_cells_lazy<16>, grid_for(nc * 16), kThreads, 0, st, c_lo, c_hi, p, src, h->cell_start[h->cs], h->partial);
+        return;
+    }
     // lanes per cell: about a quarter of the nominal segment length, so each lane keeps several loads in flight
     if (ppc <= 4)
         PFEM2_LAUNCH(k_project_cells<2>, grid_for(nc * 2), kThreads, 0, st, c_lo, c_hi, p, h->cell_start[h->cs], h->partial);
@@ -789,6 +953,10 @@ int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table, do
 int apply_correct_now(pfem2_handle *h, NodalVel v, NodalVel vold, bool has_old)
 {
     if (h) h->partials_valid = false; // particle velocities change
+    {
+        const int rcm = materialize(h); // the eager kernel walks the physical order
+        if (rcm) return rcm;
+    }
     ParticleSoA p = h->soa[h->cur];
     const int grid = grid_for(h->capacity);
     PhaseScope ps(h, PFEM2_PHASE_CORRECT);
@@ -895,6 +1063,8 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
     if (opt.max_division_level <= 0) opt.max_division_level = 4;
     if (opt.max_division_level > kMaxLevel) return fail(nullptr, PFEM2_EINVAL, "max_division_level > 8");
     if (opt.capacity_factor < 1.05) opt.capacity_factor = 1.5;
+    if (opt.lazy_sort && (opt.stable_order || opt.lane_per_record || opt.fuse_project || opt.scatter_tma))
+        return fail(nullptr, PFEM2_EINVAL, "lazy_sort works with the default kernels only (no stable_order / lane_per_record / fuse_project / scatter_tma)");
 
     int dev = opt.device;
     if (dev < 0) CU(cudaGetDevice(&dev));
@@ -908,6 +1078,10 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
     h->opt = opt;
     h->stream = (cudaStream_t)opt.stream;
     h->mesh = *mesh;
+    {
+        const char *e = getenv("PFEM2_LAZY_SWIZZLE"); // env: hardware bring-up of the lazy move pass only
+        h->lazy_swizzle = !(e && atoi(e) == 0);
+    }
     // :241-243
     const int n = std::max(std::min(cell_division_level, opt.max_division_level), 1);
     h->level = n;
@@ -1035,6 +1209,7 @@ int pfem2_destroy(pfem2_handle *h)
         cudaFree(h->p2p.idx[k]);
     }
     cudaFree(h->p2p.cursors);
+    cudaFree(h->tail_cursor);
     if (h->trail_stream) cudaStreamDestroy(h->trail_stream);
     for (cudaEvent_t e : h->trail_ev) if (e) cudaEventDestroy(e);
     cudaFree(h->trail_prog);
@@ -1058,6 +1233,7 @@ int pfem2_seed(pfem2_handle *h)
     const int C = h->mesh.n_cells;
     h->cur = 0;
     h->cs = 0;
+    h->permuted = false;
     PFEM2_LAUNCH(k_set_counters, 1, 1, 0, h->stream, h->ctr, 0, h->capacity);
     PFEM2_LAUNCH(k_seed, grid_for(std::max<long long>((long long)(h->own_hi - h->own_lo) * h->ppc, C + 1)), kThreads, 0, h->stream, C,
                  h->own_lo, h->own_hi, h->ppc, (const double2 *)h->mesh.d_vertices, h->geom, h->centers, h->soa[0], h->cell_start[0],
@@ -1140,6 +1316,7 @@ int pfem2_export_aos(pfem2_handle *h, const void **d_particles96, int *count)
     CU(cudaSetDevice(h->device));
     int rc;
     if ((rc = sync_counters(h))) return rc;
+    if ((rc = materialize(h))) return rc;
     if ((rc = flush_correct(h))) return rc;
     const size_t need = (size_t)std::max(h->capacity, 1) * 96;
     if (h->aos_bytes < need) {
@@ -1215,7 +1392,7 @@ int plan_host_pipe(pfem2_handle *h, int K, int substeps)
 
 int host_pipe_chunks(const pfem2_handle *h)
 {
-    if (h->opt.host_pipeline == 1 || !advect_tma_enabled(h) || h->opt.stable_order) return 1;
+    if (h->opt.host_pipeline == 1 || !advect_tma_enabled(h) || h->opt.stable_order || lazy_enabled(h)) return 1;
     if (h->own_lo != 0 || h->own_hi != h->mesh.n_cells) return 1; // multi-GPU strips exchange particles between the phases
     if (h->opt.host_pipeline > 1) return std::min(h->opt.host_pipeline, 16);
     return h->mesh.n_cells < (1 << 18) ? 1 : 8; // small meshes are launch-bound: one chunk (sweep on channel16m: 1 chunk 23.5 ms,
@@ -1310,6 +1487,7 @@ int pfem2_download(pfem2_handle *h, double *x, double *y, double *l0, double *l1
     CU(cudaSetDevice(h->device));
     int rc;
     if ((rc = sync_counters(h))) return rc;
+    if ((rc = materialize(h))) return rc;
     if ((rc = flush_correct(h))) return rc;
     const size_t n = (size_t)h->host_count;
     const ParticleSoA &p = h->soa[h->cur];
@@ -1339,6 +1517,7 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
     int rc;
     if ((rc = sync_counters(h))) return rc;
     h->dv_pending = false; // the uploaded state replaces everything, including a correction not yet applied
+    h->permuted = false;   // ... and a permutation of the replaced state
     if (n > h->capacity) {
         h->host_count = 0;
         if ((rc = grow(h, (int)std::min<long long>(2147483000ll, (long long)(1.25 * n) + 4096)))) return rc;
@@ -1379,8 +1558,10 @@ int pfem2_device_records(pfem2_handle *h, const void **d_records)
 {
     if (!h || !d_records) return PFEM2_EINVAL;
     CU(cudaSetDevice(h->device));
-    {   // the records expose the particle velocities: a deferred correction is applied first
-        const int rc = flush_correct(h);
+    {   // the records expose the physical order and the particle velocities: a pending permutation (lazy re-sort) is made
+        // physical and a deferred correction is applied first
+        int rc = materialize(h);
+        if (!rc) rc = flush_correct(h);
         if (rc) return rc;
     }
     *d_records = h->soa[h->cur].records();
@@ -1429,6 +1610,8 @@ int pfem2_set_owned_cells(pfem2_handle *h, int cell_lo, int cell_hi)
     if (!h) return PFEM2_EINVAL;
     if (cell_lo < 0 || cell_hi > h->mesh.n_cells || cell_lo > cell_hi) return fail(h, PFEM2_EINVAL, "bad owned cell range");
     if (h->seeded) return fail(h, PFEM2_ESTATE, "set_owned_cells after seed");
+    if (h->opt.lazy_sort && (cell_lo != 0 || cell_hi != h->mesh.n_cells))
+        return fail(h, PFEM2_EINVAL, "lazy_sort is single-GPU only (the strip-partitioned calls work on the physical order)");
     h->own_lo = cell_lo;
     h->own_hi = cell_hi;
     CU(cudaSetDevice(h->device));

@@ -1,6 +1,7 @@
-// pfem2_lazy.cuh -- DRAFT kernels of the lazy re-sort.  NOT part of libpfem2_b200.so: nothing includes this file
-// except the compile check `make -C gpupfem2_b200/csrc lazy-check`; the kernels have been compiled for sm_100a but have NOT run on
-// hardware yet.  What is measured is the mechanism they rest on (profiles/r01d_summary.md §4: tile::gather4 moves 64-byte records
+// pfem2_lazy.cuh -- kernels of the lazy re-sort, pfem2_options.lazy_sort = 1 (EXPERIMENTAL, off by default).
+// Part of libpfem2_b200.so since the end of round 1, compiled for sm_100a, NOT yet run on hardware (the GPU budget of the round was
+// spent): the parity tests of the path are tests/test_gpu_lazy.py (opt-in: PFEM2_TEST_LAZY=1), the first thing to run in round 2
+// (tools/lazy_check.sh).  What IS measured is the mechanism (profiles/r01d_summary.md §4: tile::gather4 moves 64-byte records
 // from arbitrary rows into a warp's shared-memory tile at 31-38 G records/s with no LSU work) and the data-movement model of the
 // whole step (tools/micro/lazy_resort_model.cu: 12.75 ms against 14.27 ms of record / index traffic at channel16m scale).
 //
@@ -51,9 +52,12 @@ __global__ void __launch_bounds__(kThreads) k_iota(unsigned *__restrict__ src, c
 //   * n_sorted = number of sorted positions (live particles of the previous step) comes from ctr->count; src[] is padded with a valid
 //     row index up to a multiple of 32.
 // The swizzle of `gmap` must be the one of `tmap_out` (64-byte): TMA swizzling is a function of the shared-memory address, so the four
-// rows a gather4 drops at tile + 256 k land exactly where a 32-row tile load would have put rows 4 k .. 4 k + 3.   [to be verified on hardware]
+// rows a gather4 drops at tile + 256 k land exactly where a 32-row tile load would have put rows 4 k .. 4 k + 3.   [to be verified on hardware;
+// the micro-benchmark verified the linear layout only]
 // ---------------------------------------------------------------------------------------------
-template <int SUBCELL_MODE, bool WALK, bool MASK64, int NSUB>
+// SWZ = false (PFEM2_LAZY_SWIZZLE=0): both maps are encoded without swizzle and lane r reads its record at r * 64 (4-way bank conflicts on
+// the shared-memory side, correct by construction): the fallback should the hardware check above fail.
+template <int SUBCELL_MODE, bool WALK, bool MASK64, int NSUB, bool SWZ>
 __global__ void __launch_bounds__(kAdvThreads, kAdvBlocksPerSM)
 k_advect_locate_lazy(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap tmap_out, const int4 *__restrict__ src,
                      unsigned *__restrict__ keys, const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
@@ -78,7 +82,7 @@ k_advect_locate_lazy(const __grid_constant__ CUtensorMap gmap, const __grid_cons
     const int tiles = (n + 31) >> 5;
     const int warp_global = blockIdx.x * warps_per_block + warp;
     const int warps_total = gridDim.x * warps_per_block;
-    const uint32_t my0 = (uint32_t)lane * 64 + ((((uint32_t)lane >> 1) & 3) << 4);
+    const uint32_t my0 = (uint32_t)lane * 64 + (SWZ ? ((((uint32_t)lane >> 1) & 3) << 4) : 0u);
     auto fetch = [&](int tile, uint32_t buf, uint32_t bar) { // lane 0 only
         mbar_arrive_expect_tx(bar, kAdvTileBytes);
         const int4 *rows = src + (size_t)tile * 8;
@@ -236,6 +240,10 @@ k_reseed_lazy(int own_lo, int own_hi, int ppc, const double2 *__restrict__ verti
     const double ay0 = __ldg(Vy + nn.x), ay1 = __ldg(Vy + nn.y), ay2 = __ldg(Vy + nn.z);
     const unsigned long long mask = cell_mask[c];
     int d = *n_old_ptr + atomicAdd(tail_cursor, missing); // a block of `missing` records behind the array
+    if ((long long)d + missing > ctr->capacity) { // (the plan only checked the number of live particles; the dense array also holds the lost ones)
+        atomicExch(const_cast<int *>(&ctr->overflow), 1);
+        return;
+    }
     int j = start + live;
     for (int s = 0; s < ppc; ++s) {
         if ((mask >> s) & 1ull) continue;
@@ -269,7 +277,30 @@ k_project_cells_lazy(int c_lo, int n_cells, ParticleSoA p, const unsigned *__res
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc[k] = 0.0;
         int i = b + lane;
-        for (; i + G < e; i += 2 * G) { // two particles in flight per lane
+        for (; i + 3 * G < e; i += 4 * G) { // four (then two) particles in flight per lane, as in k_project_cells
+            long long r4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r4[u] = __ldg(src + i + u * G);
+            double2 l4[4], v4[4];
+            double z4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                l4[u] = p.lab[r4[u]];
+                v4[u] = p.vel[r4[u]];
+                z4[u] = p.tail[r4[u]].l2;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double Lu[3] = {l4[u].x, l4[u].y, z4[u]};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    acc[3 * k + 0] = __dadd_rn(acc[3 * k + 0], __dmul_rn(Lu[k], v4[u].x));
+                    acc[3 * k + 1] = __dadd_rn(acc[3 * k + 1], __dmul_rn(Lu[k], v4[u].y));
+                    acc[3 * k + 2] = __dadd_rn(acc[3 * k + 2], Lu[k]);
+                }
+            }
+        }
+        for (; i + G < e; i += 2 * G) {
             const long long ra = __ldg(src + i), rb = __ldg(src + i + G);
             const double2 la = p.lab[ra], lb = p.lab[rb];
             const double2 va = p.vel[ra], vb = p.vel[rb];

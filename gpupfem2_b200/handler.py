@@ -121,7 +121,7 @@ class ParticleHandler2D:
 
     def __init__(self, mesh: DeviceMesh, cell_division_level: int, *, subcell_mode=0, max_division_level=4,
                  capacity_factor=1.5, verbose=False, exact_search=False, stable_order=False, scatter_tma=False, defer_correct=True,
-                 lane_per_record=False, host_pipeline=0, fuse_project=False):
+                 lane_per_record=False, host_pipeline=0, fuse_project=False, lazy_sort=False):
         self._L = _lib.load()
         self.mesh = mesh  # borrowed for the handler's lifetime, like the reference's `const Mesh2D *`
         opt = _lib.Options()
@@ -138,6 +138,7 @@ class ParticleHandler2D:
         opt.lane_per_record = 1 if lane_per_record else 0
         opt.host_pipeline = int(host_pipeline)
         opt.fuse_project = 1 if fuse_project else 0
+        opt.lazy_sort = 1 if lazy_sort else 0
         self._h = C.c_void_p()
         view = mesh.view()
         rc = self._L.pfem2_create(C.byref(self._h), C.byref(view), cell_division_level, C.byref(opt))

@@ -78,6 +78,11 @@ typedef struct pfem2_options {
                                so that the freshly written records are read from L2 instead of HBM; projectVelocityOntoGrid then only
                                gathers the per-cell sums (same arithmetic, same sums; any mutation in between recomputes them).
                                Measured break-even on B200 (see pfem2_kernels.cuh), hence opt-in */
+    int lazy_sort;          /* EXPERIMENTAL, 0 (default) = off.  1: lazy re-sort (single GPU, fast order, default kernels): the records move
+                               once per step.  advectParticles gathers its tiles through the permutation left by the previous step's
+                               counting sort (cp.async.bulk.tensor tile::gather4), writes them dense and ends with a 4-byte rank pass
+                               instead of the 128-byte-per-particle scatter; the projection reads through the permutation; every other
+                               reader of the physical order materialises the sorted array first.  Same results as the default */
 } pfem2_options;
 
 /* counters of the last pfem2_advect call (device-resident, read back on demand) */

@@ -47,6 +47,25 @@ def test_create_rejects_bad_arguments_without_touching_the_gpu():
     assert L.pfem2_destroy(None) == _lib.PFEM2_OK
 
 
+def test_lazy_sort_is_off_by_default_and_refuses_incompatible_options_before_touching_the_gpu():
+    """pfem2_options.lazy_sort (experimental) only combines with the default kernels; the check precedes every CUDA call."""
+    L = _lib.load()
+    o = _lib.Options()
+    L.pfem2_default_options(ctypes.byref(o))
+    assert o.lazy_sort == 0
+    buf = (ctypes.c_double * 8)()
+    fake = ctypes.cast(buf, ctypes.c_void_p)  # never dereferenced: the option check fails first
+    view = _lib.MeshView(1, 3, fake, fake, fake, fake, fake)
+    h = ctypes.c_void_p()
+    for name in ("stable_order", "lane_per_record", "fuse_project", "scatter_tma"):
+        L.pfem2_default_options(ctypes.byref(o))
+        o.lazy_sort = 1
+        setattr(o, name, 1)
+        assert L.pfem2_create(ctypes.byref(h), ctypes.byref(view), 2, ctypes.byref(o)) == _lib.PFEM2_EINVAL, name
+        assert b"lazy_sort" in L.pfem2_last_error(None)
+        assert not h.value
+
+
 def test_no_cpu_fallback_in_product_path():
     """The product package must not import or reference the oracle (it is test infrastructure)."""
     pkg = os.path.join(ROOT, "gpupfem2_b200")

@@ -1,0 +1,30 @@
+#!/bin/bash
+# Hardware bring-up of the lazy re-sort (pfem2_options.lazy_sort): the first gpurun call of round 2.
+#   gpurun --timeout 1500 -- 'bash tools/lazy_check.sh'
+# 1. parity tests of the path in both tile layouts (each in its own process under `timeout`: a faulting kernel poisons the
+#    context and must not hang the box);  2. A/B bench default vs lazy (64-byte swizzled tiles, then linear tiles) on channel16m.
+# Everything lands in gpurun_out/lazy_*.
+mkdir -p gpurun_out
+export PFEM2_TEST_LAZY=1
+for k in "refuses" "reference_dumps and swizzle64" "reference_dumps and linear" "oracle and swizzle64" "oracle and linear" \
+         "cylinder or clamped or growth" "eager or step_host"; do
+  tag=$(echo "$k" | tr ' ' '_')
+  timeout 600 python -m pytest tests/test_gpu_lazy.py -x -q -k "$k" > gpurun_out/lazy_test_$tag.log 2>&1
+  echo "== $k: rc=$? $(tail -1 gpurun_out/lazy_test_$tag.log)"
+done
+run() { # tag ENV=VAL ...
+  tag=$1; shift
+  timeout 900 env "$@" python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/lazy_bench_$tag.json 2> gpurun_out/lazy_bench_$tag.err
+  python - <<PY
+import json
+try:
+    j = json.loads([l for l in open("gpurun_out/lazy_bench_$tag.json") if l.startswith("{")][-1])
+    print("$tag", round(j["ms_per_step"], 3), {k: round(v["ms_per_step"], 3) for k, v in j["roofline"]["phases"].items()},
+          "e2e", round(j["e2e"]["ms_per_step"], 2))
+except Exception as e:
+    print("$tag FAILED", e); print(open("gpurun_out/lazy_bench_$tag.err").read()[-800:])
+PY
+}
+run default PFEM2_LAZY_SORT=0
+run lazy_swizzle64 PFEM2_LAZY_SORT=1 PFEM2_LAZY_SWIZZLE=1
+run lazy_linear PFEM2_LAZY_SORT=1 PFEM2_LAZY_SWIZZLE=0

@@ -827,27 +827,51 @@ int advect_lazy(pfem2_handle *h, NodalVel vel, double dt, int substeps)
     if ((rc = lazy_record_maps(h, h->cur ^ 1))) return rc;
     {
         PhaseScope ps(h, PFEM2_PHASE_ADVECT);
-        PFEM2_LAUNCH(k_pack_nodal, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, 0, N, vel, h->v2);
         const size_t smem = advect_tma_smem_bytes(kAdvThreads);
-        const int grid = grid_for(h->capacity, kAdvThreads, g_num_sms * kAdvBlocksPerSM);
         const bool m64 = h->ppc > 32, walk = h->opt.exact_search == 0;
         const int mode = h->opt.subcell_mode ? 1 : 0;
+        const int *cstart = nullptr;
+        int c_lo = 0, c_hi = C, grid = 1;
 #define PFEM2_LAZY_ADV(M, W, B, NSUB, SWZ)                                                                                                    \
     PFEM2_LAUNCH((k_advect_locate_lazy<M, W, B, NSUB, SWZ>), grid, kAdvThreads, smem, st, h->gmap[h->cur], h->omap[h->cur ^ 1],                 \
                  (const int4 *)h->vals[h->perm_buf], h->keys[1], h->geom, h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, hsub, \
-                 substeps, C, h->ppc, h->level, h->sub_step, h->ctr, h->stay, h->cell_mask, h->dv_pending ? h->dv2 : (const double2 *)nullptr)
+                 substeps, C, h->ppc, h->level, h->sub_step, h->ctr, h->stay, h->cell_mask, h->dv_pending ? h->dv2 : (const double2 *)nullptr,  \
+                 cstart, c_lo, c_hi)
 #define PFEM2_LAZY_ADV_N(M, W, B)                                                                                                             \
     do {                                                                                                                                      \
         if (!h->lazy_swizzle) PFEM2_LAZY_ADV(M, W, B, 0, false);                                                                              \
         else if (substeps == 3) PFEM2_LAZY_ADV(M, W, B, 3, true);                                                                             \
         else PFEM2_LAZY_ADV(M, W, B, 0, true);                                                                                                \
     } while (0)
-        if (mode == 0) {
-            if (walk) { if (m64) PFEM2_LAZY_ADV_N(0, true, true); else PFEM2_LAZY_ADV_N(0, true, false); }
-            else      { if (m64) PFEM2_LAZY_ADV_N(0, false, true); else PFEM2_LAZY_ADV_N(0, false, false); }
+        auto launch = [&]() {
+            if (mode == 0) {
+                if (walk) { if (m64) PFEM2_LAZY_ADV_N(0, true, true); else PFEM2_LAZY_ADV_N(0, true, false); }
+                else      { if (m64) PFEM2_LAZY_ADV_N(0, false, true); else PFEM2_LAZY_ADV_N(0, false, false); }
+            } else {
+                if (walk) { if (m64) PFEM2_LAZY_ADV_N(1, true, true); else PFEM2_LAZY_ADV_N(1, true, false); }
+                else      { if (m64) PFEM2_LAZY_ADV_N(1, false, true); else PFEM2_LAZY_ADV_N(1, false, false); }
+            }
+        };
+        if (!h->pipe.active) {
+            PFEM2_LAUNCH(k_pack_nodal, grid_for(N, kThreads, 1 << 30), kThreads, 0, st, 0, N, vel, h->v2);
+            grid = grid_for(h->capacity, kAdvThreads, g_num_sms * kAdvBlocksPerSM);
+            launch();
         } else {
-            if (walk) { if (m64) PFEM2_LAZY_ADV_N(1, true, true); else PFEM2_LAZY_ADV_N(1, true, false); }
-            else      { if (m64) PFEM2_LAZY_ADV_N(1, false, true); else PFEM2_LAZY_ADV_N(1, false, false); }
+            // pfem2_step_host: chunk j of the cell range starts as soon as the slices of the nodal field it can touch have landed (events
+            // recorded on the copy stream) and have been interleaved into v2 -- the schedule of launch_advect, over whole tiles
+            pfem2_handle::HostPipe &pp = h->pipe;
+            cstart = h->cell_start[h->cs];
+            grid = grid_for((long long)h->capacity / pp.K + 1, kAdvThreads, g_num_sms * kAdvBlocksPerSM);
+            for (int j = 0; j < pp.K; ++j) {
+                for (; pp.packed_slices <= pp.up_slice[j]; ++pp.packed_slices) {
+                    const int s0 = pp.ns[pp.packed_slices], s1 = pp.ns[pp.packed_slices + 1];
+                    cudaStreamWaitEvent(st, pp.up_ev[pp.packed_slices], 0);
+                    if (s1 > s0) PFEM2_LAUNCH(k_pack_nodal, grid_for(s1 - s0, kThreads, 1 << 30), kThreads, 0, st, s0, s1, vel, h->v2);
+                }
+                c_lo = pp.cb[j];
+                c_hi = pp.cb[j + 1];
+                launch();
+            }
         }
 #undef PFEM2_LAZY_ADV_N
 #undef PFEM2_LAZY_ADV
@@ -1392,7 +1416,7 @@ int plan_host_pipe(pfem2_handle *h, int K, int substeps)
 
 int host_pipe_chunks(const pfem2_handle *h)
 {
-    if (h->opt.host_pipeline == 1 || !advect_tma_enabled(h) || h->opt.stable_order || lazy_enabled(h)) return 1;
+    if (h->opt.host_pipeline == 1 || !advect_tma_enabled(h) || h->opt.stable_order) return 1;
     if (h->own_lo != 0 || h->own_hi != h->mesh.n_cells) return 1; // multi-GPU strips exchange particles between the phases
     if (h->opt.host_pipeline > 1) return std::min(h->opt.host_pipeline, 16);
     return h->mesh.n_cells < (1 << 18) ? 1 : 8; // small meshes are launch-bound: one chunk (sweep on channel16m: 1 chunk 23.5 ms,

@@ -63,8 +63,14 @@ k_advect_locate_lazy(const __grid_constant__ CUtensorMap gmap, const __grid_cons
                      unsigned *__restrict__ keys, const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
                      const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, const double2 *__restrict__ V2, double h, int substeps,
                      int n_cells, int ppc, int level, double sub_step, Counters *ctr, int *__restrict__ stay,
-                     unsigned long long *__restrict__ cell_mask, const double2 *__restrict__ dV2)
+                     unsigned long long *__restrict__ cell_mask, const double2 *__restrict__ dV2, const int *__restrict__ chunk_start,
+                     int chunk_lo, int chunk_hi)
 {
+    // chunk_start != nullptr (pfem2_step_host, chunked): this launch moves the tiles whose FIRST sorted position lies in the segment range
+    // of the cells [chunk_lo, chunk_hi) -- whole tiles, because the pass is not in place (a tile shared by two launches would be written
+    // twice from the unmoved source).  Rounding the chunk's particle range down to tiles only moves work to an EARLIER chunk's neighbour on
+    // the low side and to the LATER chunk on the high side; the upload dependencies are node prefixes that grow with the chunk index, so
+    // they still hold.  The launches of one step partition the tiles exactly (the last chunk ends at the last, possibly partial, tile).
     extern __shared__ unsigned char adv_smem_raw[];
     __shared__ int s_mov, s_lost;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
@@ -79,8 +85,12 @@ k_advect_locate_lazy(const __grid_constant__ CUtensorMap gmap, const __grid_cons
     }
     __syncthreads();
     const int n = ctr->count; // sorted positions [0, n)
-    const int tiles = (n + 31) >> 5;
-    const int warp_global = blockIdx.x * warps_per_block + warp;
+    int tiles = (n + 31) >> 5, t_lo = 0;
+    if (chunk_start) {
+        t_lo = min(__ldg(chunk_start + chunk_lo), n) >> 5;
+        if (chunk_hi < n_cells) tiles = min(__ldg(chunk_start + chunk_hi), n) >> 5;
+    }
+    const int warp_global = t_lo + blockIdx.x * warps_per_block + warp;
     const int warps_total = gridDim.x * warps_per_block;
     const uint32_t my0 = (uint32_t)lane * 64 + (SWZ ? ((((uint32_t)lane >> 1) & 3) << 4) : 0u);
     auto fetch = [&](int tile, uint32_t buf, uint32_t bar) { // lane 0 only

@@ -174,6 +174,31 @@ def test_lazy_step_host_and_upload(gpu, oracle):
     assert_states_equal(ha.download(), hc.download(), "lazy after restart")
 
 
+@pytest.mark.parametrize("name,chunks", [("channel_fast", 3), ("cyl3_l2", 4), ("tiny_l4", 5)])
+def test_lazy_pipelined_step_host_equals_the_three_calls(gpu, oracle, name, chunks):
+    """The chunked pfem2_step_host under lazy_sort: the move pass runs chunk by chunk over WHOLE tiles of the sorted order (the
+    pass is not in place, so a tile must not be shared by two launches), the projection chunk by chunk through the permutation."""
+    c = cases.build_case(name)
+    oracle.complete_mesh(c.mesh)
+    dm = gpu.DeviceMesh(c.mesh)
+    ha = gpu.ParticleHandler2D(dm, c.level)
+    hb = gpu.ParticleHandler2D(dm, c.level, host_pipeline=chunks, lazy_sort=True)
+    f, w = dev_field(c)
+    for h in (ha, hb):
+        h.seed_particles()
+        h.init_particle_velocity(f)
+    hfx, hfy = torch.as_tensor(c.fx).pin_memory(), torch.as_tensor(c.fy).pin_memory()
+    hwx, hwy = torch.zeros_like(hfx).pin_memory(), torch.zeros_like(hfx).pin_memory()
+    for s in range(8):
+        ha.step(f, w, c.dt, c.substeps)
+        n = hb.step_host(hfx, hfy, hwx, hwy, c.dt, c.substeps)
+        assert n == ha.get_particle_count(), f"step {s}"
+        sa, sb = ha.stats(), hb.stats()
+        assert (sa["lost"], sa["added"], sa["movers"]) == (sb["lost"], sb["added"], sb["movers"]), f"step {s}"
+        assert rel_inf(w[0].cpu().numpy(), hwx.numpy()) <= REL_TOL and rel_inf(w[1].cpu().numpy(), hwy.numpy()) <= REL_TOL
+    assert_states_equal(ha.download(), hb.download(), name)
+
+
 def test_lazy_refuses_what_it_does_not_support(gpu, oracle):
     c = cases.build_case("tiny_l2")
     oracle.complete_mesh(c.mesh)

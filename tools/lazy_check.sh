@@ -7,7 +7,7 @@
 mkdir -p gpurun_out
 export PFEM2_TEST_LAZY=1
 for k in "refuses" "reference_dumps and swizzle64" "reference_dumps and linear" "oracle and swizzle64" "oracle and linear" \
-         "cylinder or clamped or growth" "eager or step_host"; do
+         "cylinder or clamped or growth" "eager or step_host_and_upload" "pipelined"; do
   tag=$(echo "$k" | tr ' ' '_')
   timeout 600 python -m pytest tests/test_gpu_lazy.py -x -q -k "$k" > gpurun_out/lazy_test_$tag.log 2>&1
   echo "== $k: rc=$? $(tail -1 gpurun_out/lazy_test_$tag.log)"

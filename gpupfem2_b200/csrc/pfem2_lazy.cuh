@@ -208,14 +208,28 @@ k_rank(const unsigned *__restrict__ keys, const int *__restrict__ n_old_ptr, int
     const int n = *n_old_ptr;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
-    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
-        const int i = base + lane;
-        const unsigned c = i < n ? __ldg(keys + i) : kLostCell;
-        const unsigned peers = __match_any_sync(0xffffffffu, c);
-        int run = 0;
-        if (c != kLostCell && (peers & lt) == 0) run = atomicAdd(cursor + c, __popc(peers));
-        run = __shfl_sync(0xffffffffu, run, __ffs(peers) - 1);
-        if (c != kLostCell) src_new[run + __popc(peers & lt)] = (unsigned)i;
+    constexpr int U = 4; // keys per lane and iteration: all loads, then all atomics, are in flight together (as in k_scatter_all_regs)
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp_global * (32 * U); base < n; base += warps_total * (32 * U)) {
+        unsigned c[U], peers[U];
+        int run[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = base + u * 32 + lane;
+            c[u] = i < n ? __ldg(keys + i) : kLostCell;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            peers[u] = __match_any_sync(0xffffffffu, c[u]);
+            run[u] = 0;
+            if (c[u] != kLostCell && (peers[u] & lt) == 0) run[u] = atomicAdd(cursor + c[u], __popc(peers[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int r = __shfl_sync(0xffffffffu, run[u], __ffs(peers[u]) - 1);
+            if (c[u] != kLostCell) src_new[r + __popc(peers[u] & lt)] = (unsigned)(base + u * 32 + lane);
+        }
     }
 }
 

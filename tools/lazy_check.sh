@@ -28,3 +28,12 @@ PY
 run default PFEM2_LAZY_SORT=0
 run lazy_swizzle64 PFEM2_LAZY_SORT=1 PFEM2_LAZY_SWIZZLE=1
 run lazy_linear PFEM2_LAZY_SORT=1 PFEM2_LAZY_SWIZZLE=0
+# 3. only if the lazy bench ran: launch list of one lazy step (shares) and one --set full capture of its three new kernels
+if grep -q '"value"' gpurun_out/lazy_bench_lazy_swizzle64.json 2>/dev/null; then
+  PFEM2_LAZY_SORT=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 60 --csv \
+    --log-file gpurun_out/lazy_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+  PFEM2_LAZY_SORT=1 timeout 1200 ncu --set full --clock-control none --import-source on \
+    -k regex:'k_advect_locate_lazy|k_rank|k_project_cells_lazy' -s 9 -c 3 -o gpurun_out/lazy_prof \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/lazy_prof.log 2>&1
+  ls -la gpurun_out/lazy_prof.ncu-rep gpurun_out/lazy_launches.csv
+fi

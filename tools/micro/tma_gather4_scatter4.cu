@@ -6,7 +6,10 @@
 //   mode 0  tile load (32 rows)  -> tile store (32 rows)            the dense reference
 //   mode 1  tile load            -> 8 x scatter4 to dest[]          move pass writing straight to the re-sorted positions
 //   mode 2  8 x gather4 by src[] -> tile store                      move pass reading through a permutation (lazy re-sort)
-// usage: tma_gather4_scatter4 <mode> <box_rows of the gather/scatter map: 1 or 4> <run length R> <log2 n>
+// usage: tma_gather4_scatter4 <mode> <box_rows of the gather/scatter map: 1 or 4> <run length R> <log2 n> [swizzle: 0 none (default), 1 = 64-byte]
+// swizzle 1 encodes ALL maps with CU_TENSOR_MAP_SWIZZLE_64B: mode 2 then answers the open question of the lazy re-sort in
+// isolation -- do the rows of a gather4 land where the 32-row tile store expects them?  ("wrong pieces 0" = yes)
+// build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/micro/_bin/tma_g4s4 tools/micro/tma_gather4_scatter4.cu
 // Every configuration runs in its own process (an invalid tensor map / instruction poisons the context).
 #include <cstdint>
 #include <cstdio>
@@ -139,6 +142,7 @@ int main(int argc, char **argv)
 {
     const int mode = argc > 1 ? atoi(argv[1]) : 0, box_rows = argc > 2 ? atoi(argv[2]) : 1, R = argc > 3 ? atoi(argv[3]) : 4;
     const int n = 1 << (argc > 4 ? atoi(argv[4]) : 26);
+    const CUtensorMapSwizzle swz = (argc > 5 && atoi(argv[5]) == 1) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
     int4 *src, *dst;
     int *perm;
     unsigned long long *bad;
@@ -160,7 +164,7 @@ int main(int argc, char **argv)
         const cuuint64_t strides[1] = {64};
         const cuuint32_t box[2] = {16, rows};
         const cuuint32_t es[2] = {1, 1};
-        return enc(m, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+        return enc(m, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
     CUtensorMap t_in, t_out, g_in, s_out;
@@ -187,7 +191,7 @@ int main(int argc, char **argv)
     k_check<<<148 * 8, 256>>>(dst, perm, n, mode, bad);
     unsigned long long hbad = 0;
     CK(cudaMemcpy(&hbad, bad, 8, cudaMemcpyDeviceToHost));
-    printf("mode %d box_rows %d run %d n %d : %.3f ms  %.2f G records/s  %.2f TB/s (in + out)  wrong pieces %llu\n", mode, box_rows, R, n, best, n / best * 1e-6,
+    printf("mode %d box_rows %d run %d n %d swizzle %s : %.3f ms  %.2f G records/s  %.2f TB/s (in + out)  wrong pieces %llu\n", mode, box_rows, R, n, swz == CU_TENSOR_MAP_SWIZZLE_64B ? "64B" : "none", best, n / best * 1e-6,
            2.0 * n * 64 / best * 1e-9, hbad);
     return 0;
 }

@@ -83,6 +83,7 @@ struct pfem2_handle {
     bool readback_pending = false;
     int host_count = 0; // last count known on the host
     int host_added = 0;
+    bool scatter_attr_set = false;           // scatter_tma: the kernel's dynamic shared-memory limit has been raised on this device
     unsigned *keys[2]{}, *vals[2]{};         // (new cell, array index) of the movers, ping-pong for the radix sort
     unsigned *stay_bits = nullptr;           // capacity / 32 + 2: ballot of particles that stayed in their cell
     int *warp_movers = nullptr;              // capacity / 32 + 2: movers per warp, scanned in place
@@ -429,11 +430,10 @@ int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable, NodalV
         PFEM2_LAUNCH(k_init_cursor, grid_for(own_n, kThreads, 1 << 30), kThreads, 0, st, lo, hi, h->packed, h->cursor);
         if (h->opt.scatter_tma) {
             constexpr int kStages = 3;
-            static bool attr_set = false;
             const size_t smem = scatter_smem_bytes<kStages>(kThreads);
-            if (!attr_set) {
+            if (!h->scatter_attr_set) { // a function attribute is per device: remembered per handle, not per process
                 CU(cudaFuncSetAttribute(k_scatter_all_tma<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
+                h->scatter_attr_set = true;
             }
             PFEM2_LAUNCH(k_scatter_all_tma<kStages>, grid_for(h->capacity, kThreads, g_num_sms * 4), kThreads, smem, st, src, dst,
                          &h->ctr->n_old, h->cursor, h->ctr);

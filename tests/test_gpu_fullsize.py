@@ -12,6 +12,8 @@ download is needed:
     between the TMA-tile / quad kernels, the one-lane-per-record kernels, the stable order and the exact one-ring search
     after the same steps (same particle SET bit for bit).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -72,8 +74,13 @@ def check_sorted_and_inside(h, dm):
     return n
 
 
+# the experimental lazy re-sort joins these tests only on request (PFEM2_TEST_LAZY=1, see tests/test_gpu_lazy.py)
+LAZY = [False, True] if os.environ.get("PFEM2_TEST_LAZY") == "1" else [False]
+
+
+@pytest.mark.parametrize("lazy", LAZY, ids=lambda v: "lazy_sort" if v else "default")
 @pytest.mark.parametrize("size", list(SIZES))
-def test_full_size_properties(gpu, size):
+def test_full_size_properties(gpu, size, lazy):
     nx, ny, lx, ly = SIZES[size]
     dm = gpu.device_structured_channel(nx, ny, lx, ly, colmajor=True)
     y = dm.vertices[:, 1].contiguous()
@@ -82,7 +89,7 @@ def test_full_size_properties(gpu, size):
     W = (torch.zeros_like(y), torch.zeros_like(y))
     dt = 0.25 * (lx / nx) * 3
     big = size.endswith("16m")
-    h = gpu.ParticleHandler2D(dm, 4, capacity_factor=1.2)
+    h = gpu.ParticleHandler2D(dm, 4, capacity_factor=1.2, lazy_sort=lazy)
     h.seed_particles()
     assert h.get_particle_count() == 2 * nx * ny * 16
     h.init_particle_velocity(F)
@@ -147,7 +154,8 @@ def test_checksum_of_checksums_between_kernel_variants(gpu):
     F = ((4.0 * y * (ly - y) / (ly * ly)).contiguous(), (0.05 * torch.sin(8.0 * dm.vertices[:, 0])).contiguous())
     dt = 0.4 * (lx / nx) * 3
     sums = []
-    for opts in ({}, {"lane_per_record": True}, {"stable_order": True}, {"exact_search": True}):
+    variants = [{}, {"lane_per_record": True}, {"stable_order": True}, {"exact_search": True}] + ([{"lazy_sort": True}] if LAZY[-1] else [])
+    for opts in variants:
         h = gpu.ParticleHandler2D(dm, 4, capacity_factor=1.2, **opts)
         h.seed_particles()
         h.init_particle_velocity(F)

@@ -15,6 +15,8 @@ for k in "refuses" "reference_dumps and swizzle64" "reference_dumps and linear" 
   timeout 600 python -m pytest tests/test_gpu_lazy.py -x -q -k "$k" > gpurun_out/lazy_test_$tag.log 2>&1
   echo "== $k: rc=$? $(tail -1 gpurun_out/lazy_test_$tag.log)"
 done
+timeout 900 python -m pytest tests/test_gpu_fullsize.py -x -q -k "lazy_sort or checksum" > gpurun_out/lazy_test_fullsize.log 2>&1
+echo "== full-size properties (16M and 256M particles) with lazy_sort: rc=$? $(tail -1 gpurun_out/lazy_test_fullsize.log)"
 run() { # tag ENV=VAL ...
   tag=$1; shift
   timeout 900 env "$@" python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/lazy_bench_$tag.json 2> gpurun_out/lazy_bench_$tag.err

@@ -135,6 +135,8 @@ struct pfem2_handle {
     int perm_buf = 0;
     int *tail_cursor = nullptr;              // device int: re-seeded records appended behind the dense array
     bool lazy_swizzle = true;                // 64-byte swizzle of the lazy move pass's tiles (PFEM2_LAZY_SWIZZLE=0: linear tiles, the fallback)
+    bool lazy_nsub3 = false;                 // PFEM2_LAZY_NSUB3=1: the S = 3 specialisation of the lazy move pass (ptxas: 20 / 68 spilled bytes
+                                             // against none for the runtime-S form, hence off until measured)
     CUtensorMap gmap[2], omap[2];            // lazy move pass: gather maps (box {16, 1}) and tile-store maps (box {16, 32}) of the two buffers
     void *lzmap_base[2] = {nullptr, nullptr};
     int lzmap_rows[2] = {0, 0};
@@ -587,7 +589,12 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
         const int *cstart = nullptr;
         int c_lo = 0, c_hi = 0;
 #define PFEM2_ADV_TMA(NSUB)                                                                                                          \
-    PFEM2_LAUNCH((k_advect_locate_tma<MODE, WALK, MASK64, NSUB>), grid, kAdvThreads, smem, h->stream, h->tmap[h->cur], h->geom, h->edge_nbr,   \
+    do {                                                                                                                             \
+        if (sb || !WALK) PFEM2_ADV_TMA_(NSUB, false); /* FAST is only a register-allocation matter: taken where ptxas spills less */ \
+        else PFEM2_ADV_TMA_(NSUB, true);                                                                                             \
+    } while (0)
+#define PFEM2_ADV_TMA_(NSUB, FAST)                                                                                                   \
+    PFEM2_LAUNCH((k_advect_locate_tma<MODE, WALK, MASK64, NSUB, FAST>), grid, kAdvThreads, smem, h->stream, h->tmap[h->cur], h->geom, h->edge_nbr,   \
                  h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, hsub, substeps, C, h->ppc, h->level, h->sub_step, h->ctr, sb,         \
                  h->warp_movers, h->stay, h->opt.stable_order ? h->arrive : (int *)nullptr, h->cell_mask, do_count, h->dv_pending ? h->dv2 : nullptr, h->own_lo, h->own_hi,          \
                  h->mg_bounds, h->mg_ranks, h->mg_rank_count, h->mg_fused ? h->keys[0] : (unsigned *)nullptr, cstart, c_lo, c_hi)
@@ -623,6 +630,7 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
                 cudaStreamWaitEvent(h->stream, pp.up_ev[pp.packed_slices], 0);
         }
 #undef PFEM2_ADV_TMA
+#undef PFEM2_ADV_TMA_
         return;
     }
     unsigned *sbits = h->opt.stable_order ? h->stay_bits : nullptr; // only the stable-order path consumes the ballots
@@ -840,7 +848,7 @@ int advect_lazy(pfem2_handle *h, NodalVel vel, double dt, int substeps)
 #define PFEM2_LAZY_ADV_N(M, W, B)                                                                                                             \
     do {                                                                                                                                      \
         if (!h->lazy_swizzle) PFEM2_LAZY_ADV(M, W, B, 0, false);                                                                              \
-        else if (substeps == 3) PFEM2_LAZY_ADV(M, W, B, 3, true);                                                                             \
+        else if (substeps == 3 && h->lazy_nsub3) PFEM2_LAZY_ADV(M, W, B, 3, true);                                                            \
         else PFEM2_LAZY_ADV(M, W, B, 0, true);                                                                                                \
     } while (0)
         auto launch = [&]() {
@@ -1105,6 +1113,8 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
     {
         const char *e = getenv("PFEM2_LAZY_SWIZZLE"); // env: hardware bring-up of the lazy move pass only
         h->lazy_swizzle = !(e && atoi(e) == 0);
+        e = getenv("PFEM2_LAZY_NSUB3");
+        h->lazy_nsub3 = e && atoi(e) == 1;
     }
     // :241-243
     const int n = std::max(std::min(cell_division_level, opt.max_division_level), 1);

@@ -366,7 +366,11 @@ constexpr size_t advect_tma_smem_bytes(int threads) { return (size_t)(threads / 
 #define PFEM2_ADV_MINB 4
 #endif
 constexpr int kAdvThreads = PFEM2_ADV_THREADS, kAdvBlocksPerSM = PFEM2_ADV_MINB;
-template <int SUBCELL_MODE, bool WALK, bool MASK64, int NSUB>
+// FAST (the fast order, i.e. not pfem2_options.stable_order): only the number of survivors per cell is needed (stayers + arrivals are
+// summed, accumulate_cell_stats with arrive == nullptr, and no stay bits are written), so the cell a particle started in is not carried
+// through the substep loop -- one register less at the 64-register cap: ptxas then allocates the S = 3 form without a single spill
+// (12 / 20 spilled bytes before; on this LSU-bound kernel 16 more spilled bytes had cost 0.47 ms, profiles/r01d_summary.md §3).
+template <int SUBCELL_MODE, bool WALK, bool MASK64, int NSUB, bool FAST>
 __global__ void __launch_bounds__(kAdvThreads, kAdvBlocksPerSM)
 k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
                     const int *__restrict__ nbr_off, const int *__restrict__ nbr_idx, const double2 *__restrict__ V2, double h,
@@ -437,7 +441,8 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
         bool lost = false;
         if (valid) {
             const int4 r0 = lds128(sa0), r1 = lds128(sa1), r2 = lds128(sa2);
-            c0 = c = (unsigned)r2.z;
+            c = (unsigned)r2.z;
+            if (!FAST) c0 = c;
             double x = __hiloint2double(r0.y, r0.x);
             double y = __hiloint2double(r0.w, r0.z);
             L0 = __hiloint2double(r1.y, r1.x);
@@ -498,7 +503,7 @@ k_advect_locate_tma(const __grid_constant__ CUtensorMap tmap, const CellGeom *__
             atomicAdd(rank_count + rank_of_cell(c, rank_bounds, n_ranks), 1);
             live = false;
         }
-        const bool stays = live && c == c0;
+        const bool stays = live && (FAST || c == c0);
         const unsigned sb = __ballot_sync(0xffffffffu, stays);
         const unsigned mb = __ballot_sync(0xffffffffu, live && !stays);
         const unsigned lb = __ballot_sync(0xffffffffu, lost);

@@ -73,7 +73,8 @@ k_advect_locate_lazy(const __grid_constant__ CUtensorMap gmap, const __grid_cons
     // they still hold.  The launches of one step partition the tiles exactly (the last chunk ends at the last, possibly partial, tile).
     extern __shared__ unsigned char adv_smem_raw[];
     __shared__ int s_mov, s_lost;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    constexpr int warps_per_block = kAdvThreads / 32; // (the launch uses kAdvThreads: compile-time, so the strides below fold)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t smem = (smem_u32(adv_smem_raw) + 1023u) & ~1023u;
     const uint32_t tile0 = smem + (uint32_t)warp * (2 * kAdvTileBytes);
     const uint32_t bar0 = smem + (uint32_t)warps_per_block * (2 * kAdvTileBytes) + (uint32_t)warp * 16;
@@ -84,44 +85,44 @@ k_advect_locate_lazy(const __grid_constant__ CUtensorMap gmap, const __grid_cons
         fence_barrier_init();
     }
     __syncthreads();
-    const int n = ctr->count; // sorted positions [0, n)
-    int tiles = (n + 31) >> 5, t_lo = 0;
+    // sorted positions [p_lo, n) of this launch, p_lo a multiple of 32; n = the live count, or the (tile-aligned) end of the chunk: one
+    // bound serves the loop and the validity of a lane
+    int n = ctr->count, p_lo = 0;
     if (chunk_start) {
-        t_lo = min(__ldg(chunk_start + chunk_lo), n) >> 5;
-        if (chunk_hi < n_cells) tiles = min(__ldg(chunk_start + chunk_hi), n) >> 5;
+        p_lo = min(__ldg(chunk_start + chunk_lo), n) & ~31;
+        if (chunk_hi < n_cells) n = min(__ldg(chunk_start + chunk_hi), n) & ~31;
     }
-    const int warp_global = t_lo + blockIdx.x * warps_per_block + warp;
-    const int warps_total = gridDim.x * warps_per_block;
+    const int first = p_lo + ((blockIdx.x * warps_per_block + warp) << 5);
+    const int stride = (int)gridDim.x * (warps_per_block * 32);
     const uint32_t my0 = (uint32_t)lane * 64 + (SWZ ? ((((uint32_t)lane >> 1) & 3) << 4) : 0u);
-    auto fetch = [&](int tile, uint32_t buf, uint32_t bar) { // lane 0 only
+    auto fetch = [&](int base, uint32_t buf, uint32_t bar) { // lane 0 only; base = first sorted position of the tile
         mbar_arrive_expect_tx(bar, kAdvTileBytes);
-        const int4 *rows = src + (size_t)tile * 8;
+        const int4 *rows = src + ((size_t)base >> 2);
 #pragma unroll
         for (int k = 0; k < 8; ++k) tma_gather4_rows(buf + (uint32_t)k * 256u, &gmap, __ldg(rows + k), bar);
     };
-    if (lane == 0 && warp_global < tiles) fetch(warp_global, tile0, bar0);
+    if (lane == 0 && first < n) fetch(first, tile0, bar0);
     uint32_t b = 0, par = 0;
-    for (int tile = warp_global; tile < tiles; tile += warps_total) {
+    for (int base = first; base < n; base += stride) {
         const uint32_t buf = tile0 + b * kAdvTileBytes;
         if (lane == 0) {
             bulk_wait_group_read<0>(); // the other buffer's store (previous iteration) has finished reading shared memory
-            const int nxt = tile + warps_total;
-            if (nxt < tiles) fetch(nxt, tile0 + (b ^ 1) * kAdvTileBytes, bar0 + (b ^ 1) * 8);
+            const int nxt = base + stride;
+            if (nxt < n) fetch(nxt, tile0 + (b ^ 1) * kAdvTileBytes, bar0 + (b ^ 1) * 8);
         }
         mbar_wait(bar0 + b * 8, par);
         par ^= b;
         b ^= 1;
         const uint32_t sa0 = buf + my0, sa1 = sa0 ^ 16u, sa2 = sa0 ^ 32u, sa3 = sa0 ^ 48u;
-        const int base = tile << 5;
         const int i = base + lane;
         const bool valid = i < n;
-        unsigned c0 = 0, c = 0;
+        unsigned c = 0;
         double L0 = 0, L1 = 0, L2 = 0;
         int moved = 0;
         bool lost = false;
         if (valid) {
             const int4 r0 = lds128(sa0), r1 = lds128(sa1), r2 = lds128(sa2);
-            c0 = c = (unsigned)r2.z;
+            c = (unsigned)r2.z;
             double x = __hiloint2double(r0.y, r0.x);
             double y = __hiloint2double(r0.w, r0.z);
             L0 = __hiloint2double(r1.y, r1.x);
@@ -174,9 +175,9 @@ k_advect_locate_lazy(const __grid_constant__ CUtensorMap gmap, const __grid_cons
             bulk_commit_group();
         }
         const bool live = valid && !lost;
-        const bool stays = live && c == c0;
-        const unsigned sb = __ballot_sync(0xffffffffu, stays);
-        const unsigned mb = __ballot_sync(0xffffffffu, live && !stays);
+        // the fast order only needs the number of survivors per cell (stayers + arrivals, accumulate_cell_stats with arrive == nullptr),
+        // so the cell the particle started in is not carried through the substep loop
+        const unsigned sb = __ballot_sync(0xffffffffu, live), mb = 0u;
         const unsigned lb = __ballot_sync(0xffffffffu, lost);
         const int wm = __reduce_add_sync(0xffffffffu, moved);
         if (lane == 0) {

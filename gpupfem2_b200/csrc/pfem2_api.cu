@@ -135,8 +135,8 @@ struct pfem2_handle {
     int perm_buf = 0;
     int *tail_cursor = nullptr;              // device int: re-seeded records appended behind the dense array
     bool lazy_swizzle = true;                // 64-byte swizzle of the lazy move pass's tiles (PFEM2_LAZY_SWIZZLE=0: linear tiles, the fallback)
-    bool lazy_nsub3 = false;                 // PFEM2_LAZY_NSUB3=1: the S = 3 specialisation of the lazy move pass (ptxas: 20 / 68 spilled bytes
-                                             // against none for the runtime-S form, hence off until measured)
+    bool lazy_nsub3 = true;                  // PFEM2_LAZY_NSUB3=0: runtime-S form of the lazy move pass also for S = 3 (A/B; ptxas allocates the
+                                             // S = 3 specialisation without spills, the runtime-S form with 4 / 8 bytes)
     CUtensorMap gmap[2], omap[2];            // lazy move pass: gather maps (box {16, 1}) and tile-store maps (box {16, 32}) of the two buffers
     void *lzmap_base[2] = {nullptr, nullptr};
     int lzmap_rows[2] = {0, 0};
@@ -1114,7 +1114,7 @@ int pfem2_create(pfem2_handle **out, const pfem2_mesh_view *mesh, int cell_divis
         const char *e = getenv("PFEM2_LAZY_SWIZZLE"); // env: hardware bring-up of the lazy move pass only
         h->lazy_swizzle = !(e && atoi(e) == 0);
         e = getenv("PFEM2_LAZY_NSUB3");
-        h->lazy_nsub3 = e && atoi(e) == 1;
+        h->lazy_nsub3 = !(e && atoi(e) == 0);
     }
     // :241-243
     const int n = std::max(std::min(cell_division_level, opt.max_division_level), 1);

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kThreads) k_iota(unsigned *__restrict__ src, c
 
 // ---------------------------------------------------------------------------------------------
 // move pass of the lazy re-sort.  Same arithmetic, same statistics as k_advect_locate_tma (pfem2_kernels.cuh); differences:
-//   * input tile = rows src[32 t .. 32 t + 31] of `gmap` (the current buffer), fetched with 8 gather4 operations by lane 0;
+//   * input tile = rows src[32 t .. 32 t + 31] of `gmap` (the current buffer), fetched with 8 gather4 operations (lanes 0..7, one each);
 //   * output tile = rows 32 t .. of `tmap_out` (the OTHER buffer): the pass is not in place;
 //   * keys[32 t + lane] = new cell (kLostCell for lost and padding lanes): what k_rank consumes;
 //   * n_sorted = number of sorted positions (live particles of the previous step) comes from ctr->count; src[] is padded with a valid
@@ -95,21 +95,36 @@ k_advect_locate_lazy(const __grid_constant__ CUtensorMap gmap, const __grid_cons
     const int first = p_lo + ((blockIdx.x * warps_per_block + warp) << 5);
     const int stride = (int)gridDim.x * (warps_per_block * 32);
     const uint32_t my0 = (uint32_t)lane * 64 + (SWZ ? ((((uint32_t)lane >> 1) & 3) << 4) : 0u);
-    auto fetch = [&](int base, uint32_t buf, uint32_t bar) { // lane 0 only; base = first sorted position of the tile
-        mbar_arrive_expect_tx(bar, kAdvTileBytes);
-        const int4 *rows = src + ((size_t)base >> 2);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) tma_gather4_rows(buf + (uint32_t)k * 256u, &gmap, __ldg(rows + k), bar);
+    // Fetch of a tile = 8 gather4 operations.  The eight lanes 0..7 each hold the four row indices of "their" quarter-kilobyte and issue
+    // one gather4 (the hardware instruction is warp-uniform: ptxas wraps a divergent issue in an elect / R2UR loop over the active lanes,
+    // so this costs the same 8 UTMALDG as one lane issuing all eight), but the indices arrive with ONE coalesced 128-byte load per tile
+    // that is issued an iteration ahead -- in the one-lane form each 16-byte index load sat right in front of the gather4 that consumed it
+    // (the asm statements are memory barriers to the compiler): eight DRAM latencies in a row on the warp's critical path.
+    auto load_rows = [&](int base) { // indices of the tile at sorted position `base` (lanes 0..7), zeros otherwise
+        int4 r = make_int4(0, 0, 0, 0);
+        if (lane < 8 && base < n) r = __ldg(src + ((size_t)base >> 2) + lane);
+        return r;
     };
-    if (lane == 0 && first < n) fetch(first, tile0, bar0);
+    auto issue = [&](int4 r, uint32_t buf, uint32_t bar) { // all lanes call; expect_tx was armed by lane 0 before the __syncwarp
+        if (lane < 8) tma_gather4_rows(buf + (uint32_t)lane * 256u, &gmap, r, bar);
+    };
+    int4 rows = load_rows(first);
+    if (first < n) {
+        if (lane == 0) mbar_arrive_expect_tx(bar0, kAdvTileBytes);
+        __syncwarp();
+        issue(rows, tile0, bar0);
+    }
+    rows = load_rows(first + stride); // for the fetch at the top of the first iteration
     uint32_t b = 0, par = 0;
     for (int base = first; base < n; base += stride) {
         const uint32_t buf = tile0 + b * kAdvTileBytes;
+        const int nxt = base + stride;
         if (lane == 0) {
             bulk_wait_group_read<0>(); // the other buffer's store (previous iteration) has finished reading shared memory
-            const int nxt = base + stride;
-            if (nxt < n) fetch(nxt, tile0 + (b ^ 1) * kAdvTileBytes, bar0 + (b ^ 1) * 8);
+            if (nxt < n) mbar_arrive_expect_tx(bar0 + (b ^ 1) * 8, kAdvTileBytes);
         }
+        __syncwarp(); // lanes 1..7 write into that buffer too: behind lane 0's wait
+        if (nxt < n) issue(rows, tile0 + (b ^ 1) * kAdvTileBytes, bar0 + (b ^ 1) * 8);
         mbar_wait(bar0 + b * 8, par);
         par ^= b;
         b ^= 1;
@@ -174,6 +189,7 @@ k_advect_locate_lazy(const __grid_constant__ CUtensorMap gmap, const __grid_cons
             tma_store_tile_2d(&tmap_out, 0, base, buf);
             bulk_commit_group();
         }
+        rows = load_rows(nxt + stride); // indices of the tile after the next: in flight during the statistics, consumed at the next loop top
         const bool live = valid && !lost;
         // the fast order only needs the number of survivors per cell (stayers + arrivals, accumulate_cell_stats with arrive == nullptr),
         // so the cell the particle started in is not carried through the substep loop

@@ -7,7 +7,7 @@
 mkdir -p gpurun_out
 # 0. the open hardware question in isolation: gather4 through 64-byte-swizzled maps -> tile store ("wrong pieces 0" = the rows land
 #    where the 32-row tile expects them); linear maps as the control
-for sw in 0 1; do timeout 120 tools/micro/_bin/tma_g4s4 2 1 4 24 $sw | tee -a gpurun_out/lazy_gather4_swizzle.log; done
+for m in 2 3; do for sw in 0 1; do timeout 120 tools/micro/_bin/tma_g4s4 $m 1 4 24 $sw | tee -a gpurun_out/lazy_gather4_swizzle.log; done; done
 export PFEM2_TEST_LAZY=1
 for k in "refuses" "reference_dumps and swizzle64" "reference_dumps and linear" "oracle and swizzle64" "oracle and linear" \
          "cylinder or clamped or growth" "eager or step_host_and_upload" "pipelined"; do

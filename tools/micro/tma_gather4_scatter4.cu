@@ -6,6 +6,8 @@
 //   mode 0  tile load (32 rows)  -> tile store (32 rows)            the dense reference
 //   mode 1  tile load            -> 8 x scatter4 to dest[]          move pass writing straight to the re-sorted positions
 //   mode 2  8 x gather4 by src[] -> tile store                      move pass reading through a permutation (lazy re-sort)
+//   mode 3  as mode 2, but lanes 0..7 issue one gather4 each and the 128 bytes of row indices of a tile arrive with ONE coalesced load
+//           issued an iteration ahead (the form k_advect_locate_lazy uses since round 1e; mode 2 = one lane, each index load in front of its gather4)
 // usage: tma_gather4_scatter4 <mode> <box_rows of the gather/scatter map: 1 or 4> <run length R> <log2 n> [swizzle: 0 none (default), 1 = 64-byte]
 // swizzle 1 encodes ALL maps with CU_TENSOR_MAP_SWIZZLE_64B: mode 2 then answers the open question of the lazy re-sort in
 // isolation -- do the rows of a gather4 land where the 32-row tile store expects them?  ("wrong pieces 0" = yes)
@@ -81,12 +83,33 @@ k_copy(const __grid_constant__ CUtensorMap tile_in, const __grid_constant__ CUte
             tile_load(buf0 + b * kTile, &tile_in, tile << 5, bar0 + b * 8);
         }
     };
-    if (lane == 0 && w0 < tiles) issue_load(w0, 0);
+    auto load_rows = [&](int tile) {
+        int4 r = make_int4(0, 0, 0, 0);
+        if (lane < 8 && tile < tiles) r = __ldg(perm + (size_t)tile * 8 + lane);
+        return r;
+    };
+    int4 rows = make_int4(0, 0, 0, 0);
+    if (MODE == 3) {
+        rows = load_rows(w0);
+        if (w0 < tiles) {
+            if (lane == 0) mbar_expect(bar0, kTile);
+            __syncwarp();
+            if (lane < 8) gather4(buf0 + lane * 256, &g_in, rows, bar0);
+        }
+        rows = load_rows(w0 + wt);
+    } else if (lane == 0 && w0 < tiles) issue_load(w0, 0);
     uint32_t b = 0, par = 0;
     for (int tile = w0; tile < tiles; tile += wt) {
         if (lane == 0) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (tile + wt < tiles) issue_load(tile + wt, b ^ 1);
+            if (MODE == 3) {
+                if (tile + wt < tiles) mbar_expect(bar0 + (b ^ 1) * 8, kTile);
+            } else if (tile + wt < tiles) issue_load(tile + wt, b ^ 1);
+        }
+        if (MODE == 3) {
+            __syncwarp();
+            if (lane < 8 && tile + wt < tiles) gather4(buf0 + (b ^ 1) * kTile + lane * 256, &g_in, rows, bar0 + (b ^ 1) * 8);
+            rows = load_rows(tile + 2 * wt);
         }
         mbar_wait(bar0 + b * 8, par);
         const uint32_t cur = buf0 + b * kTile;
@@ -125,9 +148,9 @@ __global__ void k_fill(int4 *a, long long pieces)
 }
 __global__ void k_check(const int4 *src_or_dst, const int *perm, int n, int mode, unsigned long long *bad)
 {
-    // mode 1: dst[perm[i]] holds record i; mode 2: dst[i] holds record perm[i]; mode 0: dst[i] holds record i
+    // mode 1: dst[perm[i]] holds record i; modes 2, 3: dst[i] holds record perm[i]; mode 0: dst[i] holds record i
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int row = mode == 1 ? perm[i] : i, want = mode == 2 ? perm[i] : i;
+        const int row = mode == 1 ? perm[i] : i, want = mode >= 2 ? perm[i] : i;
         for (int f = 0; f < 4; ++f) {
             const int4 v = src_or_dst[4ll * row + f];
             if (v.x != want || v.y != f) atomicAdd(bad, 1ull);
@@ -181,6 +204,7 @@ int main(int argc, char **argv)
         if (mode == 0) k_copy<0><<<grid, 256, smem>>>(t_in, t_out, g_in, s_out, (const int4 *)perm, tiles);
         if (mode == 1) k_copy<1><<<grid, 256, smem>>>(t_in, t_out, g_in, s_out, (const int4 *)perm, tiles);
         if (mode == 2) k_copy<2><<<grid, 256, smem>>>(t_in, t_out, g_in, s_out, (const int4 *)perm, tiles);
+        if (mode == 3) k_copy<3><<<grid, 256, smem>>>(t_in, t_out, g_in, s_out, (const int4 *)perm, tiles);
         cudaEventRecord(e1);
         cudaError_t e = cudaEventSynchronize(e1);
         if (e != cudaSuccess) { printf("mode %d box_rows %d R %d: kernel failed: %s\n", mode, box_rows, R, cudaGetErrorString(e)); return 4; }

@@ -578,6 +578,12 @@ int materialize(pfem2_handle *h)
     return PFEM2_OK;
 }
 
+#ifdef PFEM2_NO_FAST // A/B build (make variants): the move pass of rounds 1a-1d, start cell carried through the substep loop
+constexpr bool kNoFastForm = true;
+#else
+constexpr bool kNoFastForm = false;
+#endif
+
 template <int MODE, bool WALK, bool MASK64>
 void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int do_count)
 {
@@ -590,7 +596,7 @@ void launch_advect(pfem2_handle *h, NodalVel vel, double hsub, int substeps, int
         int c_lo = 0, c_hi = 0;
 #define PFEM2_ADV_TMA(NSUB)                                                                                                          \
     do {                                                                                                                             \
-        if (sb || !WALK) PFEM2_ADV_TMA_(NSUB, false); /* FAST is only a register-allocation matter: taken where ptxas spills less */ \
+        if (sb || !WALK || kNoFastForm) PFEM2_ADV_TMA_(NSUB, false); /* FAST is a register-allocation matter: taken where ptxas spills less */ \
         else PFEM2_ADV_TMA_(NSUB, true);                                                                                             \
     } while (0)
 #define PFEM2_ADV_TMA_(NSUB, FAST)                                                                                                   \

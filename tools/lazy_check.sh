@@ -1,6 +1,6 @@
 #!/bin/bash
 # Hardware bring-up of the lazy re-sort (pfem2_options.lazy_sort): the first gpurun call of round 2.
-#   gpurun --timeout 1500 -- 'bash tools/lazy_check.sh'
+#   make -C gpupfem2_b200/csrc all variants && gpurun --timeout 1800 -- 'bash tools/lazy_check.sh'
 # 1. parity tests of the path in both tile layouts (each in its own process under `timeout`: a faulting kernel poisons the
 #    context and must not hang the box);  2. A/B bench default vs lazy (64-byte swizzled tiles, then linear tiles) on channel16m.
 # Everything lands in gpurun_out/lazy_*.
@@ -31,6 +31,8 @@ except Exception as e:
 PY
 }
 run default PFEM2_LAZY_SORT=0
+# A/B of the spill-free FAST move pass against the form of rounds 1a-1d (build the variant first, here: make -C gpupfem2_b200/csrc variants)
+if [ -f gpupfem2_b200/_variants/libpfem2_nofast.so ]; then run default_nofast PFEM2_LAZY_SORT=0 PFEM2_LIB_PATH=$PWD/gpupfem2_b200/_variants/libpfem2_nofast.so; fi
 run lazy_swizzle64 PFEM2_LAZY_SORT=1 PFEM2_LAZY_SWIZZLE=1
 run lazy_linear PFEM2_LAZY_SORT=1 PFEM2_LAZY_SWIZZLE=0
 # 3. only if the lazy bench ran: launch list of one lazy step (shares) and one --set full capture of its three new kernels

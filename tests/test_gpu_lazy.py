@@ -145,7 +145,7 @@ def test_lazy_eager_correction_and_every_reader_of_the_physical_order(gpu, oracl
 
 
 def test_lazy_step_host_and_upload(gpu, oracle):
-    """pfem2_step_host (single chunk under lazy_sort) and a checkpoint / restart through download + upload."""
+    """pfem2_step_host (one chunk: small mesh) and a checkpoint / restart through download + upload."""
     c = cases.build_case("tiny_l3")
     oracle.complete_mesh(c.mesh)
     dm = gpu.DeviceMesh(c.mesh)

@@ -48,3 +48,88 @@ def test_casefile_roundtrip(tmp_path, oracle):
     assert hdr[0] == casefile.MAGIC and hdr[1] == m.n_nodes and hdr[2] == m.n_cells and hdr[7] == 2
     expect = 64 + 8 + 16 + m.n_nodes * 16 + m.n_cells * 12 + (m.n_cells + 1) * 4 + m.nbr_indices.size * 4 + m.n_nodes * 16
     assert raw.size == expect
+
+
+def test_lazy_resort_index_model():
+    """Index-level model of the lazy re-sort (gpupfem2_b200/csrc/pfem2_lazy.cuh + advect_lazy in pfem2_api.cu): the records move once per
+    step, a permutation src[] stands in for the physical sort.  The model mirrors the kernels' index logic (not their arithmetic) on random
+    movement with deletions and re-seeding and checks what the CUDA path relies on: src_new is a bijection onto the live rows, the
+    segments are sorted by cell, the dense array plus the appended re-seeds never exceeds n_old + added rows, the index arrays are padded
+    to whole tiles with valid rows, the chunked move pass partitions the tiles exactly, and materialise gives the order a physical
+    counting sort gives (as a set per cell: the slot order inside a cell is scheduling-dependent on the GPU)."""
+    rng = np.random.default_rng(5)
+    C, ppc, LOST = 97, 4, 0xFFFFFFFF
+    # state: two record buffers (payload = a unique tag per particle + its cell), cur, the permutation, the segment table
+    cap = 4096
+    tag = [np.zeros(cap, np.int64), np.zeros(cap, np.int64)]
+    cell = [np.full(cap, LOST, np.int64), np.full(cap, LOST, np.int64)]
+    cur, count, next_tag = 0, C * ppc, C * ppc
+    tag[0][:count] = np.arange(count)
+    cell[0][:count] = np.repeat(np.arange(C), ppc)
+    cell_start = np.arange(C + 1) * ppc
+    src, permuted = None, False
+    for step in range(12):
+        if not permuted:  # k_iota: identity, padded to a whole tile with row 0
+            padded = (count + 31) & ~31
+            src = np.where(np.arange(padded) < count, np.arange(padded), 0)
+        n_old = count
+        assert src.shape[0] == (n_old + 31) & ~31 and np.all(src < cap)
+        # chunked move pass (k_advect_locate_lazy with chunk_start): whole tiles, exact partition of [0, tiles)
+        K = 1 + step % 4
+        cb = [C * j // K for j in range(K + 1)]
+        covered = np.zeros((n_old + 31) // 32, np.int64)
+        out_tag, out_cell = tag[cur ^ 1], cell[cur ^ 1]
+        keys = np.full(((n_old + 31) & ~31), LOST, np.int64)
+        for j in range(K):
+            p_lo = min(cell_start[cb[j]], n_old) & ~31
+            n_hi = n_old if cb[j + 1] >= C else (min(cell_start[cb[j + 1]], n_old) & ~31)
+            for base in range(p_lo, n_hi, 32):
+                covered[base // 32] += 1
+                rows = src[base:base + 32]                      # 8 x gather4
+                t, c = tag[cur][rows].copy(), cell[cur][rows].copy()
+                valid = base + np.arange(32) < n_old
+                move = rng.integers(-3, 4, 32)                  # new cell: a neighbour, or lost
+                newc = np.where(rng.random(32) < 0.05, LOST, np.clip(c + move, 0, C - 1))
+                newc = np.where(valid, newc, LOST)
+                out_tag[base:base + 32] = t                     # dense tile store (padding lanes: a stale copy of row src = 0)
+                out_cell[base:base + 32] = np.where(valid, newc, c)
+                keys[base:base + 32] = newc
+        assert np.all(covered == 1), "the chunks do not partition the tiles"
+        cur ^= 1
+        # k_plan_cells / scan: every cell is topped up to at least ppc particles (the model's stand-in for the sub-cell check)
+        live = np.bincount(keys[keys != LOST], minlength=C)
+        missing = np.maximum(ppc - live, 0)
+        start = np.concatenate([[0], np.cumsum(live + missing)])
+        count = int(start[-1])
+        # k_rank: slot = cursor[cell]++ in an arbitrary (here: shuffled) order of the records
+        src_new = np.full((count + 31) & ~31, -1, np.int64)
+        cursor = start[:-1].copy()
+        for i in rng.permutation(n_old):
+            if keys[i] != LOST:
+                src_new[cursor[keys[i]]] = i
+                cursor[keys[i]] += 1
+        # k_reseed_lazy: appended rows behind the dense array, indices behind the cell's survivors; pad behind the last position
+        tail = 0
+        for c in rng.permutation(C):
+            for k in range(missing[c]):
+                d = n_old + tail
+                tail += 1
+                assert d < cap
+                tag[cur][d], cell[cur][d] = next_tag, c
+                next_tag += 1
+                src_new[start[c] + live[c] + k] = d
+        src_new[count:] = 0
+        assert tail == missing.sum() and n_old + tail <= cap
+        # invariants the projection / the next move pass rely on
+        s = src_new[:count]
+        assert np.all(s >= 0) and np.unique(s).shape[0] == count, "src_new is not a bijection onto the live rows"
+        assert np.all(np.diff(cell[cur][s]) >= 0) and np.all(cell[cur][s] != LOST)
+        assert np.array_equal(np.bincount(cell[cur][s], minlength=C), np.diff(start))
+        src, cell_start, permuted = src_new, start, True
+        if step % 5 == 4:  # k_materialize: out[j] = in[src[j]] -> the physically sorted array
+            tag[cur ^ 1][:count] = tag[cur][s]
+            cell[cur ^ 1][:count] = cell[cur][s]
+            cur ^= 1
+            permuted = False
+            assert np.all(np.diff(cell[cur][:count]) >= 0)
+            assert np.unique(tag[cur][:count]).shape[0] == count

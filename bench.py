@@ -279,10 +279,8 @@ def run_ours(args):
     dm, level, F, dt = build_problem(args, rank, world, device)
     W = (torch.zeros_like(F[0]), torch.zeros_like(F[0]))
     h = handler.ParticleHandler2D(dm, level, max_division_level=8, capacity_factor=args.capacity_factor,
-                                  scatter_tma=bool(int(os.environ.get("PFEM2_SCATTER_TMA", "0"))),
-                                  lane_per_record=bool(int(os.environ.get("PFEM2_LANE_PER_RECORD", "0"))),
                                   host_pipeline=int(os.environ.get("PFEM2_HOST_PIPELINE", "0")),
-                                  lazy_sort=bool(int(os.environ.get("PFEM2_LAZY_SORT", "0"))))  # experimental A/B switch, default off
+                                  lazy_sort=bool(int(os.environ.get("PFEM2_LAZY_SORT", "1"))))  # A/B switch: 0 = physical re-sort in every advect
     h.seed_particles()
     h.init_particle_velocity(F)
     torch.cuda.synchronize()
@@ -380,8 +378,7 @@ def run_ours(args):
                    "setup_s": t_setup},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
-    if int(os.environ.get("PFEM2_LAZY_SORT", "0")):
-        out["config"]["lazy_sort"] = True
+    out["config"]["lazy_sort"] = bool(int(os.environ.get("PFEM2_LAZY_SORT", "1")))
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args)
     h.close()

@@ -6,17 +6,18 @@
 // particle step never needs a host round trip.
 #pragma once
 
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace pfem2 {
 
-extern long long g_kernel_launches;
+extern std::atomic<long long> g_kernel_launches; // (handles may be driven from several host threads)
 extern int g_num_sms;
 #define PFEM2_LAUNCH(kernel, grid, block, smem, stream, ...)                                                        \
     do {                                                                                                            \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                                 \
-        ++::pfem2::g_kernel_launches;                                                                               \
+        ::pfem2::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);                                                                             \
     } while (0)
 
 inline int persistent_grid(long long max_blocks_needed, int blocks_per_sm)
@@ -162,12 +163,12 @@ inline size_t rs_hist_elems(long long capacity) { return (size_t)kRsRadix * rs_n
 inline size_t rs_scan_scratch_elems(long long capacity) { return scan_scratch_elems<int>(kRsRadix * rs_num_tiles(capacity)); }
 
 // derived device-side lengths of one sort: info[0] = number of tiles
-__global__ void k_rs_prepare(const int *__restrict__ n_ptr, int *__restrict__ info)
+static __global__ void k_rs_prepare(const int *__restrict__ n_ptr, int *__restrict__ info)
 {
     info[0] = (*n_ptr + kRsTile - 1) / kRsTile;
 }
 
-__global__ void __launch_bounds__(kRsThreads)
+static __global__ void __launch_bounds__(kRsThreads)
 k_rs_histogram(const unsigned *__restrict__ keys, const int *__restrict__ n_ptr, int shift, int *__restrict__ hist)
 {
     __shared__ int sh[kRsRadix];
@@ -188,7 +189,7 @@ k_rs_histogram(const unsigned *__restrict__ keys, const int *__restrict__ n_ptr,
     }
 }
 
-__global__ void __launch_bounds__(kRsThreads)
+static __global__ void __launch_bounds__(kRsThreads)
 k_rs_scatter(const unsigned *__restrict__ keys_in, const unsigned *__restrict__ vals_in, unsigned *__restrict__ keys_out,
              unsigned *__restrict__ vals_out, const int *__restrict__ n_ptr, int shift, const int *__restrict__ hist_scanned)
 {

@@ -84,6 +84,15 @@ __device__ __forceinline__ void tma_store_tile_2d(const void *tmap, int x, int y
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y), "r"(smem_src)
                  : "memory");
 }
+// four arbitrary rows of the [rows x 64 B] record tensor -> 256 contiguous bytes of shared memory (box {16, 1}: measured,
+// a 4-row box raises an illegal instruction)
+__device__ __forceinline__ void tma_gather4_rows(uint32_t smem_dst, const void *tmap, int4 rows, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                     smem_dst),
+                 "l"(tmap), "r"(0), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {

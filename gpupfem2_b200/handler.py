@@ -120,8 +120,8 @@ class ParticleHandler2D:
     FIELDS = ("x", "y", "l0", "l1", "l2", "vx", "vy", "cell", "id")
 
     def __init__(self, mesh: DeviceMesh, cell_division_level: int, *, subcell_mode=0, max_division_level=4,
-                 capacity_factor=1.5, verbose=False, exact_search=False, stable_order=False, scatter_tma=False, defer_correct=True,
-                 lane_per_record=False, host_pipeline=0, fuse_project=False, lazy_sort=False):
+                 capacity_factor=1.5, verbose=False, exact_search=False, stable_order=False, defer_correct=True, host_pipeline=0,
+                 lazy_sort=True):
         self._L = _lib.load()
         self.mesh = mesh  # borrowed for the handler's lifetime, like the reference's `const Mesh2D *`
         opt = _lib.Options()
@@ -133,11 +133,8 @@ class ParticleHandler2D:
         opt.verbose = 1 if verbose else 0
         opt.exact_search = 1 if exact_search else 0
         opt.stable_order = 1 if stable_order else 0
-        opt.scatter_tma = 1 if scatter_tma else 0
         opt.defer_correct = 1 if defer_correct else 0
-        opt.lane_per_record = 1 if lane_per_record else 0
         opt.host_pipeline = int(host_pipeline)
-        opt.fuse_project = 1 if fuse_project else 0
         opt.lazy_sort = 1 if lazy_sort else 0
         self._h = C.c_void_p()
         view = mesh.view()

@@ -159,11 +159,11 @@ class DistributedParticleHandler2D:
         #   "neighbour"  fixed-size [header | records] buffers to / from the adjacent strips over ncclSend / ncclRecv, counts stay
         #                on the device (no host round trip inside advect_particles);
         #   "exact"      counts first (host), then exactly sized payloads (all_to_all_single).
-        # "p2p" and "neighbour" need the default kernels (fast order, TMA-tiled move pass lists its emigrants).
+        # "p2p" and "neighbour" need the fast order (the move pass lists its emigrants).
         self.protocol = os.environ.get("PFEM2_MG_PROTOCOL", migration)  # env: A/B measurements
         if self.protocol not in ("p2p", "neighbour", "exact"):
             raise ValueError("migration must be 'p2p', 'neighbour' or 'exact'")
-        if opts.get("stable_order") or opts.get("lane_per_record") or os.environ.get("PFEM2_MG_FUSED") == "0":
+        if opts.get("stable_order") or os.environ.get("PFEM2_MG_FUSED") == "0":
             self.protocol = "exact"
         self._nbr = None
         if self.protocol != "exact":

@@ -30,7 +30,7 @@ ParticleHandler2D::ParticleHandler2D(const Mesh2D *mesh_, int cellDivisionLevel)
     pfem2_options opt;
     pfem2_default_options(&opt);
     opt.capacity_factor = 1.1; // CONSTANTS::MEMORY_REALLOCATION_COEFFICIENT; the library grows on demand like resize()
-    if (const char *e = getenv("PFEM2_LAZY_SORT")) opt.lazy_sort = atoi(e) != 0; // experimental lazy re-sort, in-situ A/B runs only
+    if (const char *e = getenv("PFEM2_LAZY_SORT")) opt.lazy_sort = atoi(e) != 0; // in-situ A/B runs: 0 = physical re-sort in every advect
     const int rc = pfem2_create(&handle, &view, cellDivisionLevel, &opt);
     if (rc != PFEM2_OK) {
         fprintf(stderr, "pfem2_b200: pfem2_create failed (code %d): %s\n", rc, pfem2_last_error(nullptr));

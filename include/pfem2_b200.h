@@ -6,7 +6,7 @@
  * API" is that C++ class, called by cases/Cylinder2D/main.cu:652-653,766,798,802,864 and
  * cases/PoiseuilleFlow2D/main.cu:513-514,622,657,661,723, and read by DataExport
  * (src/data_export.cu:97-104).  Each entry point below names the member it replaces; the header-
- * compatible C++ shim that forwards to them is gpupfem2_b200/shim/particles/particle_handler_2d.cuh
+ * compatible C++ shim that forwards to them is gpupfem2_b200/shim/pfem2_particle_handler_2d.cuh
  * (see INTEGRATION.md).
  *
  * Conventions
@@ -58,31 +58,25 @@ typedef struct pfem2_options {
     int verbose;            /* 1: print the reference's two stdout lines from the library itself */
     int exact_search;       /* 1: always use the reference's ordered one-ring scan; 0 (default): edge-walk fast path
                                that returns the same cell (falls back to the ordered scan in the tolerance band) */
-    int stable_order;       /* 0 (default): counting-sort scatter, slot order inside a cell depends on atomic retirement
-                               order; 1: deterministic order (stayers keep their order, movers radix-sorted by cell) */
-    int scatter_tma;        /* 1: stage the reorder scatter through shared memory with cp.async.bulk (TMA) per-warp pipelines;
-                               0 (default): register-staged variant (measured faster on B200, see profiles/) */
+    int stable_order;       /* 0 (default): fast order, the slot order inside a cell depends on atomic retirement order;
+                               1: deterministic order (physical re-sort: stayers keep their order, movers radix-sorted by cell) */
+    int reserved_scatter_tma; /* (round-1 A/B kernel variant, removed: must be 0) */
     int defer_correct;      /* 1 (default): correctParticleVelocity snapshots the nodal increment and the particle update is
                                folded into the next advect pass (bit-identical; applied eagerly before any other reader);
                                0: eager kernel */
-    int lane_per_record;    /* 0 (default): the advect pass moves 32-record tiles global <-> shared with the copy engine
-                               (cp.async.bulk.tensor, 64-byte swizzle) and the reorder scatter uses four lanes per record;
-                               1: one lane per 64-byte record with 128-bit global loads / stores in both (the earlier kernels:
-                               same results, bounded by L1 data-pipe wavefronts; kept for A/B measurements) */
+    int reserved_lane_per_record; /* (round-1 A/B kernel variant, removed: must be 0) */
     int host_pipeline;      /* pfem2_step_host: 0 (default) = 8 chunks on meshes of >= 262144 cells: the upload of the nodal field
                                overlaps the move pass and the download of the projected field overlaps the projection, chunk by
                                chunk of the cell range (dependencies derived from the mesh numbering); 1 = no pipelining; n > 1 =
                                n chunks */
-    int fuse_project;       /* EXPERIMENTAL, 0 (default) = off.  1: on a single GPU in the fast order, advectParticles runs the
-                               projection's cell pass concurrently with its re-sort scatter, trailing it by the reach of a particle
-                               so that the freshly written records are read from L2 instead of HBM; projectVelocityOntoGrid then only
-                               gathers the per-cell sums (same arithmetic, same sums; any mutation in between recomputes them).
-                               Measured break-even on B200 (see pfem2_kernels.cuh), hence opt-in */
-    int lazy_sort;          /* EXPERIMENTAL, 0 (default) = off.  1: lazy re-sort (single GPU, fast order, default kernels): the records move
-                               once per step.  advectParticles gathers its tiles through the permutation left by the previous step's
-                               counting sort (cp.async.bulk.tensor tile::gather4), writes them dense and ends with a 4-byte rank pass
-                               instead of the 128-byte-per-particle scatter; the projection reads through the permutation; every other
-                               reader of the physical order materialises the sorted array first.  Same results as the default */
+    int reserved_fuse_project; /* (round-1 experiment, measured break-even and removed: must be 0) */
+    int lazy_sort;          /* 1 (default): lazy re-sort -- the records move once per step.  advectParticles gathers its tiles through the
+                               permutation left by the previous step's counting sort (cp.async.bulk.tensor tile::gather4), writes them
+                               dense and ends with a 4-byte rank pass instead of a 128-byte-per-particle scatter; the projection reads
+                               through the permutation; every other reader of the physical order (getParticles, download, device
+                               records, the eager correction) materialises the sorted array first.  Same results; 14.3 instead of
+                               17.7 ms per step on the 16M-triangle channel.  0: physical re-sort in every advect.  Ignored (off)
+                               with stable_order */
 } pfem2_options;
 
 /* counters of the last pfem2_advect call (device-resident, read back on demand) */

@@ -47,22 +47,23 @@ def test_create_rejects_bad_arguments_without_touching_the_gpu():
     assert L.pfem2_destroy(None) == _lib.PFEM2_OK
 
 
-def test_lazy_sort_is_off_by_default_and_refuses_incompatible_options_before_touching_the_gpu():
-    """pfem2_options.lazy_sort (experimental) only combines with the default kernels; the check precedes every CUDA call."""
+def test_default_options_and_removed_variants_are_refused_before_touching_the_gpu():
+    """The lazy re-sort is the default; the round-1 A/B kernel variants are gone (their option fields are reserved and must be 0:
+    the check precedes every CUDA call)."""
     L = _lib.load()
     o = _lib.Options()
     L.pfem2_default_options(ctypes.byref(o))
-    assert o.lazy_sort == 0
+    assert o.lazy_sort == 1 and o.defer_correct == 1 and o.stable_order == 0
+    assert o.struct_size == ctypes.sizeof(_lib.Options)
     buf = (ctypes.c_double * 8)()
     fake = ctypes.cast(buf, ctypes.c_void_p)  # never dereferenced: the option check fails first
     view = _lib.MeshView(1, 3, fake, fake, fake, fake, fake)
     h = ctypes.c_void_p()
-    for name in ("stable_order", "lane_per_record", "fuse_project", "scatter_tma"):
+    for name in ("reserved_lane_per_record", "reserved_fuse_project", "reserved_scatter_tma"):
         L.pfem2_default_options(ctypes.byref(o))
-        o.lazy_sort = 1
         setattr(o, name, 1)
         assert L.pfem2_create(ctypes.byref(h), ctypes.byref(view), 2, ctypes.byref(o)) == _lib.PFEM2_EINVAL, name
-        assert b"lazy_sort" in L.pfem2_last_error(None)
+        assert b"removed" in L.pfem2_last_error(None)
         assert not h.value
 
 

@@ -74,11 +74,11 @@ def check_sorted_and_inside(h, dm):
     return n
 
 
-# the experimental lazy re-sort joins these tests only on request (PFEM2_TEST_LAZY=1, see tests/test_gpu_lazy.py)
-LAZY = [False, True] if os.environ.get("PFEM2_TEST_LAZY") == "1" else [False]
+# both ways of keeping the sorted order: the lazy re-sort (default) and the physical re-sort of every advect
+LAZY = [True, False]
 
 
-@pytest.mark.parametrize("lazy", LAZY, ids=lambda v: "lazy_sort" if v else "default")
+@pytest.mark.parametrize("lazy", LAZY, ids=lambda v: "lazy_sort" if v else "physical_resort")
 @pytest.mark.parametrize("size", list(SIZES))
 def test_full_size_properties(gpu, size, lazy):
     nx, ny, lx, ly = SIZES[size]
@@ -154,7 +154,7 @@ def test_checksum_of_checksums_between_kernel_variants(gpu):
     F = ((4.0 * y * (ly - y) / (ly * ly)).contiguous(), (0.05 * torch.sin(8.0 * dm.vertices[:, 0])).contiguous())
     dt = 0.4 * (lx / nx) * 3
     sums = []
-    variants = [{}, {"lane_per_record": True}, {"stable_order": True}, {"exact_search": True}] + ([{"lazy_sort": True}] if LAZY[-1] else [])
+    variants = [{}, {"lazy_sort": False}, {"stable_order": True}, {"exact_search": True}]
     for opts in variants:
         h = gpu.ParticleHandler2D(dm, 4, capacity_factor=1.2, **opts)
         h.seed_particles()

@@ -1,13 +1,9 @@
-"""Parity tests of the EXPERIMENTAL lazy re-sort (pfem2_options.lazy_sort, gpupfem2_b200/csrc/pfem2_lazy.cuh).
-
-OPT-IN: they run only with PFEM2_TEST_LAZY=1.  The path was integrated at the end of round 1 after the round's GPU budget was
-spent, so it has been compiled for sm_100a but has not run on hardware yet; until it has, a failure here must not stop the
-default `pytest -m gpu -x` run.  First thing to run in round 2: `tools/lazy_check.sh` (these tests, then an A/B bench).
+"""Parity tests aimed at the lazy re-sort (pfem2_options.lazy_sort, the default; gpupfem2_b200/csrc/pfem2_move.cuh k_move_gather,
+pfem2_resort.cuh k_rank / k_reseed_lazy / k_materialize): both shared-memory tile layouts of the gathered move pass,
+every reader of the physical order in the permuted state, growth, restart, the chunked pfem2_step_host.
 
 Same bar as test_gpu_parity.py: the reference's CUDA dumps and the CPU oracle; owner cells / positions / local coordinates /
 seed-remove sets bit-exact, velocities and projected nodal fields within 1e-12 relative."""
-import os
-
 import numpy as np
 import pytest
 
@@ -15,8 +11,7 @@ import cases
 from helpers import REL_TOL, assert_state_matches_golden, assert_states_equal, load_golden, rel_inf
 from test_gpu_parity import GOLDEN_CASES, dev_field, run_both
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PFEM2_TEST_LAZY") != "1", reason="experimental path: set PFEM2_TEST_LAZY=1")]
+pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
@@ -199,10 +194,37 @@ def test_lazy_pipelined_step_host_equals_the_three_calls(gpu, oracle, name, chun
     assert_states_equal(ha.download(), hb.download(), name)
 
 
-def test_lazy_refuses_what_it_does_not_support(gpu, oracle):
-    c = cases.build_case("tiny_l2")
-    oracle.complete_mesh(c.mesh)
-    dm = gpu.DeviceMesh(c.mesh)
-    for bad in ({"stable_order": True}, {"lane_per_record": True}, {"fuse_project": True}, {"scatter_tma": True}):
-        with pytest.raises(Exception):
-            gpu.ParticleHandler2D(dm, c.level, lazy_sort=True, **bad)
+def test_capacity_overflow_is_reported_not_written_out_of_bounds(gpu, oracle):
+    """A step that needs more rows than the capacity policy can foresee (the policy extrapolates the growth of the previous
+    step): every cell holds its whole population in ONE sub-cell, so the distribution check wants 15 new particles per cell on
+    top of a full array.  The plan must raise the overflow flag, the rank / re-seed kernels must not touch memory behind the
+    arrays (k_reseed_lazy padded src_new[] before looking at the flag), and the next call that synchronises the
+    counters must fail with PFEM2_ECAPACITY."""
+    from gpupfem2_b200.mesh import structured_channel
+
+    m = oracle.complete_mesh(structured_channel(60, 40, 6.0, 4.0, colmajor=True))
+    dm = gpu.DeviceMesh(m)
+    h = gpu.ParticleHandler2D(dm, 4, capacity_factor=1.05)
+    h.seed_particles()
+    f = (torch.zeros(m.n_nodes, dtype=torch.float64, device="cuda"), torch.zeros(m.n_nodes, dtype=torch.float64, device="cuda"))
+    h.init_particle_velocity(f)
+    s = h.download()
+    cap = h.stats()["capacity"]
+    first = np.flatnonzero(np.r_[True, np.diff(s["cell"].astype(np.int64)) != 0])  # one particle (sub-cell 0) per cell
+    assert first.size == m.n_cells
+    pick = first[np.arange(cap) % first.size]
+    h.upload({k: v[pick] for k, v in s.items()})
+    assert h.get_particle_count() == cap
+    with pytest.raises(gpu.Pfem2Error, match="capacity"):
+        h.advect_particles(f, 1e-9, 3)
+        h.get_particle_count()
+    torch.cuda.synchronize()  # no sticky CUDA error (an out-of-bounds write would surface here or in the next test)
+    h.close()
+    # the same device state is fine with room to grow
+    h = gpu.ParticleHandler2D(dm, 4, capacity_factor=3.5)
+    h.seed_particles()
+    h.init_particle_velocity(f)
+    h.upload({k: v[pick] for k, v in s.items()})
+    h.advect_particles(f, 1e-9, 3)
+    assert h.get_particle_count() == cap + 15 * m.n_cells
+    h.close()

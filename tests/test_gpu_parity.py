@@ -37,9 +37,14 @@ def dev_field(c, dev="cuda:0"):
 GOLDEN_CASES = ["tiny_l1", "tiny_l2", "tiny_l3", "tiny_l4", "tiny_box", "tiny_fast", "channel_l2", "channel_fast_rev", "cyl3_box"]
 
 
-@pytest.mark.parametrize("stable", [False, True], ids=["fast_order", "stable_order"])
+RESORT_MODES = {"lazy": {}, "physical": {"lazy_sort": False}, "stable_order": {"stable_order": True}}
+
+
+@pytest.mark.parametrize("mode", list(RESORT_MODES))
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_cuda_matches_reference_dumps(gpu, oracle, name, stable):
+def test_cuda_matches_reference_dumps(gpu, oracle, name, mode):
+    """The three ways the sorted order is kept: the lazy re-sort (default: permutation over a dense array, pfem2_move.cuh),
+    the physical counting-sort scatter of every advect (lazy_sort=0) and the deterministic stable order (radix-sorted movers)."""
     c = cases.build_case(name)
     g = load_golden(name)
     oracle.complete_mesh(c.mesh)  # one-ring from the validated O(C) builder; invJ recomputed on the device below
@@ -47,7 +52,7 @@ def test_cuda_matches_reference_dumps(gpu, oracle, name, stable):
     dm = gpu.DeviceMesh(c.mesh)
     if "invj" in g:
         assert np.array_equal(dm.inv_jacobi.cpu().numpy(), g["invj"]), "device inverse Jacobians differ from the reference's"
-    h = gpu.ParticleHandler2D(dm, c.level, stable_order=stable)
+    h = gpu.ParticleHandler2D(dm, c.level, **RESORT_MODES[mode])
     h.seed_particles()
     assert h.get_particle_count() == c.mesh.n_cells * c.level * c.level
     f, w = dev_field(c)
@@ -135,15 +140,6 @@ def test_eager_and_deferred_correction_give_identical_bits(gpu, oracle):
     for k in a:
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(w[0].cpu().numpy(), w2[0].cpu().numpy()) and np.array_equal(w[1].cpu().numpy(), w2[1].cpu().numpy())
-
-
-def test_tma_staged_scatter_matches_oracle(gpu, oracle):
-    """pfem2_options.scatter_tma: the cp.async.bulk (TMA) per-warp pipeline variant of the reorder scatter."""
-    m = cases._tiny(True)
-    fx, fy = cases._mix(m, 0.5, 1.0, 0.3, 1.0)
-    run_both(gpu, oracle, m, fx, fy, 4, 3, 0.2, 12, check_every=4, scatter_tma=True)
-    c = cases.build_case("cyl3_l2")
-    run_both(gpu, oracle, c.mesh, c.fx, c.fy, c.level, c.substeps, c.dt, 6, check_every=6, scatter_tma=True)
 
 
 def test_high_cfl_interior_deletions_match_oracle(gpu, oracle):
@@ -402,16 +398,18 @@ def test_walk_fast_path_equals_ordered_scan(gpu, oracle, name):
 
 
 @pytest.mark.parametrize("name", ["cyl3_l2", "channel_fast", "tiny_fast", "tiny_l4"])
-def test_tma_tiles_and_quad_scatter_equal_lane_per_record_kernels(gpu, oracle, name):
-    """The default data movement (advect: cp.async.bulk.tensor tiles with the 64-byte swizzle; scatter: four lanes per
-    record) against the one-lane-per-record kernels (pfem2_options.lane_per_record): identical bits in the deterministic
-    order, on meshes whose particle counts are not multiples of the 32-record tile (partial last tile, tensor-map
-    out-of-bounds rows) and with deletions, re-seeding and a pending deferred correction in every advect."""
+def test_lazy_resort_equals_physical_resort(gpu, oracle, name):
+    """The default (records move once per step: gathered move pass through the permutation, rank pass, appended re-seeds)
+    against the physical re-sort of every advect (in-place move pass, counting-sort scatter with four lanes per record):
+    same particle set bit for bit and the same counters in every step, on meshes whose particle counts are not multiples of the
+    32-record tile (partial last tile, tensor-map out-of-bounds rows) and with deletions, re-seeding and a pending deferred
+    correction in every advect.  (Fast order on both sides: the slot order inside a cell is not deterministic, so the projected
+    field is compared within the tolerance.)"""
     c = cases.build_case(name)
     oracle.complete_mesh(c.mesh)
     dm = gpu.DeviceMesh(c.mesh)
-    ha = gpu.ParticleHandler2D(dm, c.level, stable_order=True)
-    hb = gpu.ParticleHandler2D(dm, c.level, stable_order=True, lane_per_record=True)
+    ha = gpu.ParticleHandler2D(dm, c.level)
+    hb = gpu.ParticleHandler2D(dm, c.level, lazy_sort=False)
     f, w = dev_field(c)
     w2 = (torch.zeros_like(f[0]), torch.zeros_like(f[0]))
     for h in (ha, hb):
@@ -421,11 +419,10 @@ def test_tma_tiles_and_quad_scatter_equal_lane_per_record_kernels(gpu, oracle, n
         ha.step(f, w, c.dt, c.substeps)
         hb.step(f, w2, c.dt, c.substeps)
         assert ha.get_particle_count() == hb.get_particle_count()
-    a, b = ha.download(), hb.download()
-    for k in a:
-        assert np.array_equal(a[k], b[k]), k
-    assert ha.stats() == hb.stats()
-    assert np.array_equal(w[0].cpu().numpy(), w2[0].cpu().numpy()) and np.array_equal(w[1].cpu().numpy(), w2[1].cpu().numpy())
+        sa, sb = ha.stats(), hb.stats()
+        assert (sa["lost"], sa["added"], sa["movers"]) == (sb["lost"], sb["added"], sb["movers"]), f"step {s}"
+        assert rel_inf(w[0].cpu().numpy(), w2[0].cpu().numpy()) <= REL_TOL and rel_inf(w[1].cpu().numpy(), w2[1].cpu().numpy()) <= REL_TOL
+    assert_states_equal(ha.download(), hb.download(), name)
 
 
 def test_fast_order_quad_scatter_matches_oracle_after_capacity_growth(gpu, oracle):
@@ -465,15 +462,16 @@ def test_pipelined_step_host_equals_the_three_calls(gpu, oracle, name, chunks):
 
 
 @pytest.mark.parametrize("name", ["cyl3_l2", "channel_fast"])
-def test_trailing_projection_matches_oracle(gpu, oracle, name):
-    """pfem2_options.fuse_project (experimental): the projection's cell pass runs concurrently with the re-sort scatter
-    (producer / consumer kernels on two streams, progress counter, re-seeding inside the consumer) and
-    projectVelocityOntoGrid only gathers; particle set, counters and projected field must equal the oracle's, also when a
-    second projection or an eager correction follows."""
+def test_repeated_projection_and_forced_correction_match_oracle(gpu, oracle, name):
+    """projectVelocityOntoGrid twice in a row (the per-cell sums are still valid: same bits), then a correction that a reader of
+    the particle velocities forces to be applied eagerly (in the permuted state of the lazy re-sort this materialises the sorted
+    order first), then a third projection: particle set, counters and projected field must equal the oracle's."""
     c = cases.build_case(name)
-    h, o = run_both(gpu, oracle, c.mesh, c.fx, c.fy, c.level, c.substeps, c.dt, 8, check_every=2, fuse_project=True)
+    h, o = run_both(gpu, oracle, c.mesh, c.fx, c.fy, c.level, c.substeps, c.dt, 8, check_every=2)
     f, w = dev_field(c)
     w2 = (torch.zeros_like(f[0]), torch.zeros_like(f[0]))
+    h.advect_particles(f, c.dt, c.substeps)
+    o.advect_particles(c.fx, c.fy, c.dt, c.substeps)
     h.project_velocity_onto_grid(w)
     h.project_velocity_onto_grid(w2)  # partial sums are still valid: same bits
     assert np.array_equal(w[0].cpu().numpy(), w2[0].cpu().numpy())

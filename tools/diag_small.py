@@ -25,5 +25,5 @@ def run(tag, n=50, **opts):
     print(f"{tag:28s} wall {wall:8.3f} ms/step  events {e0.elapsed_time(e1)/n:8.3f}  step-call median {ts[n//2][0]*1e3:.3f} max {ts[-1][0]*1e3:.3f} ms; count-call median {sorted(x[1] for x in ts)[n//2]*1e3:.3f}")
     h.close()
 for rep in range(3):
-    run("tma/quads")
-    run("lane_per_record", lane_per_record=True)
+    run("default (lazy re-sort)")
+    run("physical re-sort", lazy_sort=False)

@@ -40,13 +40,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES = {  # algorithmic bytes per particle per launch (64 B fp64 SoA state)
-    # advect+locate: R(x,y,L,cell)=44 + W(x,y,L,cell)=44, independent of S; the velocity correction of the previous
-    # step is folded into this pass (pfem2_options.defer_correct), so its R(L,cell,v)=44 + W(v)=16 count here
-    "advect_locate": 88 + 60,
+    # move pass = advect+locate (R(x,y,L,cell)=44 + W 44 taken alone) with the velocity correction of the previous step folded
+    # in (pfem2_options.defer_correct; R(L,cell,v)=44 + W(v)=16 taken alone): the fused pass reads and writes every field ONCE,
+    # R(x,y,L,cell,v)=60 + W 60
+    "advect_locate": 120,
     "project_cells": 44,  # R(L,cell,v)
 }
-ALG_BYTES_STEP = 192
-TRAFFIC_FILE = "r01b_traffic.json"  # latest committed ncu --set full capture of the three main kernels
+ALG_BYTES_STEP = 192  # the three calls as separate passes (88 + 44 + 60); the reference point of roofline.step
+TRAFFIC_FILE = "r02_traffic.json"  # committed ncu --set full capture of the HEAD kernels (tools/traffic_from_ncu.py)
 
 WORKLOADS = {
     # name: (nx, ny, lx, ly, default level)
@@ -237,7 +238,7 @@ def build_problem(args, rank, world, device):
     from gpupfem2_b200 import handler
 
     if args.workload in WORKLOADS:
-        nx, ny, lx, ly, level, umax, dt = channel_params(args)
+        nx, ny, lx, ly, level, umax, dt = channel_params(args, world)
         dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device)
         fx, fy = nodal_field(args, dm.vertices[:, 0].contiguous(), dm.vertices[:, 1].contiguous(), lx, ly, umax)
         return dm, level, (fx.contiguous(), fy.contiguous()), dt
@@ -257,51 +258,66 @@ def build_problem(args, rank, world, device):
     return dm, args.level or 2, (fx, torch.zeros_like(fx)), dt
 
 
-def run_ours(args):
+def traffic_table():
+    """DRAM bytes per particle of every kernel of the step, from the committed ncu --set full capture of the HEAD kernels
+    (profiles/TRAFFIC_FILE: dram__bytes_read.sum + dram__bytes_write.sum per launch on channel16m)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
+    except Exception:
+        return None
+
+
+def measure(args, rank, world, local, full):
+    """One workload on `world` GPUs (this process = rank `rank`): warm-up, K device-timed steps, roofline, and -- full=True, the
+    headline -- the end-to-end leg with HOST nodal buffers.  Returns the JSON dict on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)  # its version banner would land on stdout next to the ONE JSON line
-        from gpupfem2_b200 import multi_gpu
-
-        return multi_gpu.bench_main(args, rank, world, local)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the particle step has no CPU fallback")
-    torch.cuda.set_device(local)
-    device = f"cuda:{local}"
     from gpupfem2_b200 import handler
 
+    device = f"cuda:{local}"
+    multi = world > 1
     t_setup = time.time()
     dm, level, F, dt = build_problem(args, rank, world, device)
     W = (torch.zeros_like(F[0]), torch.zeros_like(F[0]))
-    h = handler.ParticleHandler2D(dm, level, max_division_level=8, capacity_factor=args.capacity_factor,
-                                  host_pipeline=int(os.environ.get("PFEM2_HOST_PIPELINE", "0")),
-                                  lazy_sort=bool(int(os.environ.get("PFEM2_LAZY_SORT", "1"))))  # A/B switch: 0 = physical re-sort in every advect
+    lazy = bool(int(os.environ.get("PFEM2_LAZY_SORT", "1")))  # A/B switch: 0 = physical re-sort in every advect
+    opts = dict(max_division_level=8, capacity_factor=args.capacity_factor, lazy_sort=lazy)
+    if multi:
+        from gpupfem2_b200 import multi_gpu
+
+        ny = WORKLOADS[args.workload][1]
+        bounds = multi_gpu.strip_bounds(dm.n_cells, world, align=2 * ny)
+        h = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world, **opts)
+        inner = h.h
+    else:
+        h = handler.ParticleHandler2D(dm, level, host_pipeline=int(os.environ.get("PFEM2_HOST_PIPELINE", "0")), **opts)
+        inner = h
     h.seed_particles()
     h.init_particle_velocity(F)
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
-    small = h.get_particle_count() * 64 < 256e6  # state could sit in the 126 MB L2 -> flush between timed iterations
+    small = inner.get_particle_count() * 64 < 256e6  # state could sit in the 126 MB L2 -> flush between timed iterations
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=device) if small else None
 
-    sampler = ClockSampler(local)  # started before the warm-up so that its start-up (NVML init) is over when the timing begins
+    sampler = ClockSampler(local) if rank == 0 else None  # started before the warm-up so that its start-up (NVML init) is over
     for _ in range(args.warmup):
         h.step(F, W, dt, args.substeps)
     h.get_particle_count()
     torch.cuda.synchronize()
-    sampler.wait_first_sample()
-
-    h.set_profiling(True)
-    h.phase_times(reset=True)
+    if sampler:
+        sampler.wait_first_sample()
+    if multi:
+        dist.barrier()
+    inner.set_profiling(True)
+    inner.phase_times(reset=True)
     launches0 = handler.kernel_launches()
-    sampler.mark()
+    if sampler:
+        sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     counts = []
     torch.cuda.synchronize()
+    if multi:
+        dist.barrier()
     for k in range(args.steps):
         if flush is not None:
             flush.fill_(float(k))
@@ -310,79 +326,202 @@ def run_ours(args):
         ev[k][1].record()
         counts.append(h.get_particle_count())  # waits only for the advect's counter read-back
     torch.cuda.synchronize()
-    clocks = sampler.stop()
+    if multi:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
     launches = handler.kernel_launches() - launches0
     ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(ms)
-    phases = h.phase_times(reset=True)
-    h.set_profiling(False)
-    psteps = float(sum(counts))
+    # large states: one interval over the K steps (what lies between two steps is part of the job); flushed small states: the
+    # flush sits between the per-step pairs
+    total_ms = ev[0][0].elapsed_time(ev[-1][1]) if flush is None else sum(ms)
+    phases = inner.phase_times(reset=True)
+    inner.set_profiling(False)
+    sent = h.last_sent if multi else 0
+    checksum = h.state_checksum()  # order-independent, global (all-reduced over the strips): identical for every N
+    t = torch.tensor([total_ms, float(sum(counts)), float(sent)], dtype=torch.float64, device=device)
+    if multi:
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, psteps, sent = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    else:
+        psteps = float(sum(counts))
     value = psteps / (total_ms * 1e-3)
 
-    # roofline of the dominant kernel (by device time) among the three algorithmic passes
+    # roofline of the dominant kernel (by device time) among the algorithmic passes; rank 0's GPU
     peak, peak_src = peaks()
-    pmean = psteps / args.steps
+    pmean_rank = sum(counts) / args.steps
     per_phase = {}
     for name, (pms, calls) in phases.items():
         per_phase[name] = {"ms_per_step": pms / args.steps, "share": pms / total_ms if total_ms else 0.0}
         if name in ALG_BYTES and pms > 0:
-            per_phase[name]["alg_GBps"] = ALG_BYTES[name] * pmean / (pms / args.steps * 1e-3) / 1e9
+            per_phase[name]["alg_GBps"] = ALG_BYTES[name] * pmean_rank / (pms / args.steps * 1e-3) / 1e9
     dom = max(ALG_BYTES, key=lambda n: phases[n][0])
     dom_ms = phases[dom][0] / args.steps
-    achieved = ALG_BYTES[dom] * pmean / (dom_ms * 1e-3) / 1e9
-    traffic = None
-    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/r01b_traffic.json)
-        tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
-        if args.workload == "channel16m" and dom in tj:
-            traffic = tj[dom]["bytes_per_particle"] * pmean
-    except Exception:
-        pass
+    achieved = ALG_BYTES[dom] * pmean_rank / (dom_ms * 1e-3) / 1e9
+    tt = traffic_table() if args.workload == "channel16m" and (args.level or 4) == 4 and lazy else None
+    traffic = step_traffic = None
+    if tt:
+        traffic = tt["phases"][dom]["bytes_per_particle"] * pmean_rank
+        step_traffic = tt["step"]["bytes_per_particle"] * pmean_rank
+    step_ach = ALG_BYTES_STEP * value / 1e9 / world
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": f"profiles/{TRAFFIC_FILE} (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled to this run's particle count)" if traffic else None,
+                "traffic": traffic,
+                "traffic_source": (f"profiles/{TRAFFIC_FILE} (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch at HEAD, scaled to "
+                                   "this run's particle count)") if traffic else None,
                 "peak_source": peak_src, "alg_bytes_per_particle": ALG_BYTES[dom],
-                "step": {"achieved": ALG_BYTES_STEP * value / 1e9, "frac": ALG_BYTES_STEP * value / 1e9 / peak,
-                         "alg_bytes_per_particle_step": ALG_BYTES_STEP},
+                "alg_bytes_note": "move pass: R(x,y,L,cell,v) 60 + W 60 with the velocity correction of the previous step folded in "
+                                  "(each field read and written once); projection: R(L,cell,v) 44",
+                "step": {"achieved": step_ach, "frac": step_ach / peak, "alg_bytes_per_particle_step": ALG_BYTES_STEP,
+                         "traffic": step_traffic, "note": "per GPU" if multi else None},
                 "phases": per_phase}
+    if multi:
+        roofline["note"] = "rank 0, per GPU"
 
-    # e2e: the same step through the C-ABI call with pinned HOST nodal buffers (H2D + D2H inside the timed region)
-    prev_affinity = bind_to_gpu_local_cpus(local)  # pinned buffers next to the GPU (NUMA); restored before the CPU baseline runs
-    hF = [t.cpu().pin_memory() for t in F]
-    hW = [torch.empty_like(t).pin_memory() for t in hF]
-    e2e_counts = []
-    h.step_host(hF[0], hF[1], hW[0], hW[1], dt, args.substeps)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_counts.append(h.step_host(hF[0], hF[1], hW[0], hW[1], dt, args.substeps))
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    if prev_affinity:
-        os.sched_setaffinity(0, prev_affinity)
-    nodal_bytes = 2 * dm.n_nodes * 8
-    e2e = {"value": float(sum(e2e_counts)) / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": nodal_bytes,
-           "d2h_bytes_per_step": nodal_bytes + 32, "ms_per_step": t_e2e / args.steps * 1e3,
-           "host_cpus": ("bound to the GPU-local CPUs (NVML affinity)" if prev_affinity else "process default"),
-           "api": "pfem2_step_host (C ABI), pinned host nodal buffers in, projected nodal field + count out; the call pipelines the "
-                  "upload with the move pass and the projection with the download in chunks of the cell range (pfem2_options.host_pipeline)"}
-
-    state_gb = pmean * 64 / 1e9
+    e2e = None
+    if full:
+        # e2e: the same step with pinned HOST nodal buffers (H2D + D2H inside the timed region).  One GPU: the C-ABI call
+        # pfem2_step_host; N GPUs: every rank stages its own slice of the nodal field (DistributedParticleHandler2D.step_host)
+        prev_affinity = bind_to_gpu_local_cpus(local)  # pinned buffers next to the GPU (NUMA); restored before the CPU baseline runs
+        hF = [t_.cpu().pin_memory() for t_ in F]
+        hW = [torch.empty_like(t_).pin_memory() for t_ in hF]
+        if multi:
+            step_host = lambda: h.step_host(hF, hW, F, W, dt, args.substeps)  # noqa: E731
+            h2d, d2h = h.host_bytes_per_step(args.substeps)
+            hb = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=device)
+            dist.all_reduce(hb)
+            h2d, d2h = int(hb[0]), int(hb[1])
+            api = ("DistributedParticleHandler2D.step_host: every rank uploads the slice of the pinned host nodal field its strip's advect "
+                   "reads, runs advect / migrate / project / halo / correct through the C ABI, downloads the projected slice it owns")
+        else:
+            step_host = lambda: h.step_host(hF[0], hF[1], hW[0], hW[1], dt, args.substeps)  # noqa: E731
+            h2d, d2h = 2 * dm.n_nodes * 8, 2 * dm.n_nodes * 8 + 32
+            api = ("pfem2_step_host (C ABI), pinned host nodal buffers in, projected nodal field + count out; the call pipelines the upload "
+                   "with the move pass and the projection with the download in chunks of the cell range (pfem2_options.host_pipeline)")
+        step_host()
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        e2e_counts = []
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            e2e_counts.append(step_host())
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        if prev_affinity:
+            os.sched_setaffinity(0, prev_affinity)
+        te = torch.tensor([t_e2e, float(sum(e2e_counts))], dtype=torch.float64, device=device)
+        if multi:
+            a, b = te.clone(), te.clone()
+            dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            t_e2e, e2e_ps = float(a[0]), float(b[1])
+        else:
+            e2e_ps = float(sum(e2e_counts))
+        e2e = {"value": e2e_ps / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": t_e2e / args.steps * 1e3, "timing": "host clock around K calls, synchronised on both sides, max over ranks",
+               "host_cpus": ("bound to the GPU-local CPUs (NVML affinity)" if prev_affinity else "process default"), "api": api}
+    mesh_bytes = sum(int(t_.numel()) * t_.element_size() for t_ in (dm.vertices, dm.cells, dm.inv_jacobi, dm.nbr_offsets, dm.nbr_indices))
+    h.close()
+    del h, inner
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    state_gb = pmean_rank * 64 / 1e9
+    sm = sorted(ms)
     out = {
         "metric": "particle-steps/sec (advect+locate+sort+project+correct)", "value": value, "unit": "particle-steps/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "ms_per_step_min": sm[0], "ms_per_step_median": statistics.median(sm),
         "higher_is_better": True, "scaling": "weak" if args.workload in WEAK else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_description(args), "particles_mean": pmean, "cells": dm.n_cells, "nodes": dm.n_nodes,
-                   "substeps": args.substeps, "dt": dt,
+        "config": {"workload": workload_description(args, world) + (f", strip-partitioned over {world} GPUs (quad columns)" if multi else ""),
+                   "particles_mean": psteps / args.steps, "cells": dm.n_cells, "nodes": dm.n_nodes,
+                   "substeps": args.substeps, "dt": dt, "lazy_sort": lazy,
                    "l2": (f"flushed between timed iterations (512 MiB write; state {state_gb:.3f} GB could fit the 126 MB L2)"
-                          if small else f"inputs larger than L2 ({state_gb:.1f} GB of particle state per pass)"),
-                   "timing": "CUDA events on the launching (legacy default) stream, one pair per step",
-                   "setup_s": t_setup},
-        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                          if small else f"inputs larger than L2 ({state_gb:.1f} GB of particle state per pass and GPU)"),
+                   "timing": "CUDA events on the launching (legacy default) stream around the K steps" + (", max over ranks, barrier on both sides" if multi else ""),
+                   "mesh_bytes_per_rank": mesh_bytes, "setup_s": t_setup},
+        "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
+        "state_checksum": {"value": [int(v) for v in checksum.tolist()],
+                           "what": "order-independent wrapping int64 sums over the GLOBAL particle set after warm-up + timed steps: "
+                                   "[count, bits(x), bits(y), bits(L0), bits(L1), bits(L2), cell]; identical for every N"},
     }
-    out["config"]["lazy_sort"] = bool(int(os.environ.get("PFEM2_LAZY_SORT", "1")))
-    if not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args)
-    h.close()
-    print(json.dumps(out))
+    if e2e:
+        out["e2e"] = e2e
+    if multi:
+        out["config"]["migrated_particles_per_step"] = sent
+        out["config"]["migration_protocol"] = h_protocol_description(os.environ.get("PFEM2_MG_PROTOCOL", "p2p"))
+    return out
+
+
+def h_protocol_description(protocol):
+    return {"p2p": "p2p: NVLink peer memory (CUDA IPC): emigrant records and interface-node accumulators stored straight into the neighbour "
+                   "strip's HBM, device-side sequence flags; no NCCL and no host in the loop",
+            "neighbour": "neighbour: fixed-size migration buffers [header | records] to / from the adjacent strips (ncclSend / ncclRecv, "
+                         "counts stay on the device) + pairwise isend/irecv of interface-node accumulators (NCCL)",
+            "exact": "exact: all_to_all_single (counts, 64-byte particle records) + pairwise isend/irecv of interface-node accumulators "
+                     "(NCCL)"}.get(protocol, protocol)
+
+
+EXTRAS = (  # BASELINE.json's other headline sizes, nested under "extra" of the headline line at every N
+    ("channel16m_level6", {"workload": "channel16m", "level": 6},
+     "configs[3] bracket: 36/cell = 576M particles (BASELINE quotes 32/cell = 512M, not expressible in the reference: levels are squares)"),
+    ("stress2m", {"workload": "stress2m", "level": 0}, "configs[4]: high-CFL vortex lattice, 2M triangles PER GPU (weak scaling)"),
+)
+
+
+def run_ours(args):
+    import copy
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the particle step has no CPU fallback")
+    torch.cuda.set_device(local)
+    parity = None
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"  # stdout carries the ONE JSON line
+        if args.workload not in WORKLOADS:
+            raise SystemExit("multi-GPU bench runs the synthetic channel workloads")
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        from gpupfem2_b200 import multi_gpu
+
+        # parity gate inside the same launch: N strips against one GPU on a small case (+ the N4 spill case); a mismatch raises
+        parity = multi_gpu.parity_selfcheck(rank, world, f"cuda:{local}")
+    out = measure(args, rank, world, local, full=True)
+    extras = {}
+    if args.extra and args.workload == "channel16m" and not args.level:
+        for name, over, what in EXTRAS:
+            a = copy.copy(args)
+            a.workload, a.level = over["workload"], over["level"]
+            a.cfl, a.capacity_factor = 0.25, 1.3  # (channel_params derives the stress case's own values from these defaults)
+            a.steps, a.warmup = min(args.steps, 5), 3
+            try:
+                line = measure(a, rank, world, local, full=False)
+                if line:
+                    line["what"] = what
+            except Exception as e:  # an extra must never take the headline down
+                line = {"error": f"{type(e).__name__}: {e}"[:300], "what": what}
+            if rank == 0:
+                extras[name] = line
+    if rank == 0:
+        if parity:
+            out["parity_check"] = "ok"
+            out["parity"] = parity
+        if extras:
+            out["extra"] = extras
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -477,6 +616,7 @@ def main():
     ap.add_argument("--cfl", type=float, default=0.25, help="CFL per substep at the channel centre")
     ap.add_argument("--capacity-factor", type=float, default=1.3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the nested level-6 / stress2m lines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "ours" and args.gpus > 1 and "WORLD_SIZE" not in os.environ:

@@ -1146,6 +1146,19 @@ int pfem2_get_phase_times(pfem2_handle *h, double *ms, long long *calls, int res
     return PFEM2_OK;
 }
 
+int pfem2_node_ranges(pfem2_handle *h, int substeps, int *out4)
+{
+    if (!h || !out4 || substeps < 1) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    const int rc = ensure_v2_node_range(h, substeps);
+    if (rc) return rc;
+    out4[0] = h->v2_node_lo;
+    out4[1] = h->v2_node_hi;
+    out4[2] = h->own_node_lo;
+    out4[3] = h->own_node_hi;
+    return PFEM2_OK;
+}
+
 int pfem2_set_owned_cells(pfem2_handle *h, int cell_lo, int cell_hi)
 {
     if (!h) return PFEM2_EINVAL;

@@ -258,6 +258,36 @@ class ParticleHandler2D:
         a.append(np.ascontiguousarray(state.get("id", np.zeros(n, dtype=np.uint32)), dtype=np.uint32))
         self._check(self._L.pfem2_upload(self._h, n, *[v.ctypes.data for v in a]), "upload")
 
+    def device_records(self) -> torch.Tensor:
+        """Zero-copy (count, 8) float64 view of the 64-byte records in the sorted (physical) order: {x, y | L0, L1 | L2, (cell, id)
+        | vx, vy}.  Materialises a pending permutation and applies a pending correction first; valid until the next mutating call."""
+        n = self.get_particle_count()
+        p = C.c_void_p()
+        self._check(self._L.pfem2_device_records(self._h, C.byref(p)), "device_records")
+        if not n:
+            return torch.empty((0, 8), dtype=torch.float64, device=self.mesh.device)
+        return _wrap_device(p.value, (n, 8), "<f8", self.mesh.device)
+
+    def state_checksum(self) -> torch.Tensor:
+        """Order-independent checksum of the particle SET, evaluated on the device: int64 tensor
+        [count, sum bits(x), sum bits(y), sum bits(L0), sum bits(L1), sum bits(L2), sum cell] with wrapping sums.  Two runs hold
+        the same particles in the same cells at bit-identical positions iff these agree (up to 2^-64 collisions); summing the
+        tensors of the strips of a multi-GPU run gives the checksum of the global state.  Velocities and ids are left out: the
+        last bits of the velocities depend on the summation order of the projection, ids of re-seeded particles are slot numbers."""
+        rec = self.device_records().view(torch.int64)
+        out = torch.zeros(7, dtype=torch.int64, device=self.mesh.device)
+        out[0] = rec.shape[0]
+        if rec.shape[0]:
+            out[1:6] = rec[:, :5].sum(dim=0)
+            out[6] = (rec[:, 5] & 0xFFFFFFFF).sum()
+        return out
+
+    def node_ranges(self, substeps: int):
+        """(in_lo, in_hi, own_lo, own_hi): the nodes whose velocity an advect reads / whose projection this handle owns."""
+        out = (C.c_int * 4)()
+        self._check(self._L.pfem2_node_ranges(self._h, substeps, out), "node_ranges")
+        return tuple(int(v) for v in out)
+
     def cell_starts(self) -> torch.Tensor:
         p = C.c_void_p()
         self._check(self._L.pfem2_cell_starts(self._h, C.byref(p)), "cell_starts")

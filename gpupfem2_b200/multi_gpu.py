@@ -20,10 +20,7 @@ tensors, CUDA over NCCL in production and CPU over gloo in tests/test_multi_rank
 from __future__ import annotations
 
 import ctypes as C
-import json
 import os
-import sys
-import time
 
 import numpy as np
 import torch
@@ -55,16 +52,28 @@ def interface_nodes(cells, bounds, rank: int) -> dict:
     """{neighbour rank: sorted node ids shared by this rank's cells and the neighbour's cells}.
 
     `cells` is the (C, 3) connectivity as a torch tensor (any device) or numpy array.  Only non-empty
-    intersections are returned; for strips these are the adjacent ranks."""
+    intersections are returned; for strips these are the adjacent ranks.  Two strips whose node id ranges are disjoint
+    cannot share a node, so the (expensive) set intersection is only made where the ranges overlap: nothing is assumed
+    about the numbering, a partition that is not a strip partition yields its non-adjacent pairs as well."""
     t = torch.as_tensor(cells) if not isinstance(cells, torch.Tensor) else cells
     t = t.to(torch.int64)
-    mine = torch.unique(t[int(bounds[rank]):int(bounds[rank + 1])])
+    n_ranks = len(bounds) - 1
+    span = {}
+    for r in range(n_ranks):
+        if bounds[r] < bounds[r + 1]:
+            lo, hi = torch.aminmax(t[int(bounds[r]):int(bounds[r + 1])])
+            span[r] = (int(lo), int(hi))
+    if rank not in span:
+        return {}
+    mine = None
     out = {}
-    for r in range(len(bounds) - 1):
-        if r == rank or bounds[r] == bounds[r + 1]:
+    for r in range(n_ranks):
+        if r == rank or r not in span:
             continue
-        if abs(r - rank) > 1 and t.shape[0] > 4_000_000:
-            continue  # large strip meshes: only adjacent strips can share nodes
+        if span[r][0] > span[rank][1] or span[r][1] < span[rank][0]:
+            continue  # disjoint node id ranges: no shared node
+        if mine is None:
+            mine = torch.unique(t[int(bounds[rank]):int(bounds[rank + 1])])
         theirs = torch.unique(t[int(bounds[r]):int(bounds[r + 1])])
         shared = mine[torch.isin(mine, theirs)]
         if shared.numel():
@@ -143,6 +152,9 @@ class DistributedParticleHandler2D:
 
         self._lib = _lib
         self.L = _lib.load()
+        if mesh.device.type == "cuda" and torch.cuda.current_stream(mesh.device).cuda_stream != 0:
+            # the library works on the legacy default stream; the NCCL transports order their transfers against torch's CURRENT stream
+            raise RuntimeError("DistributedParticleHandler2D must be created and driven on torch's default stream")
         self.mesh = mesh
         self.rank, self.world, self.group = rank, world, group
         self.bounds = np.ascontiguousarray(bounds, dtype=np.int32)
@@ -284,8 +296,35 @@ class DistributedParticleHandler2D:
         self.project_velocity_onto_grid(work)
         self.correct_particle_velocity(frozen, work)
 
+    def step_host(self, h_frozen, h_work, d_frozen, d_work, dt, substeps) -> int:
+        """The step with HOST nodal buffers (pinned torch tensors over the global node range, one set per rank): uploads the
+        slice of the nodal field this strip's advect can read, runs the step, downloads the slice of the projected field this
+        strip owns (interface nodes: identical bits on both strips after the halo sum) and returns the strip's particle count.
+        d_frozen / d_work are the rank's device staging arrays.  Copies and kernels are ordered on the default stream."""
+        ilo, ihi, olo, ohi = self.h.node_ranges(substeps)
+        for k in range(2):
+            d_frozen[k][ilo:ihi].copy_(h_frozen[k][ilo:ihi], non_blocking=True)
+        self.step(d_frozen, d_work, dt, substeps)
+        for k in range(2):
+            h_work[k][olo:ohi].copy_(d_work[k][olo:ohi], non_blocking=True)
+        n = self.get_particle_count()
+        torch.cuda.current_stream(self.mesh.device).synchronize()
+        return n
+
+    def host_bytes_per_step(self, substeps):
+        ilo, ihi, olo, ohi = self.h.node_ranges(substeps)
+        return 2 * 8 * (ihi - ilo), 2 * 8 * (ohi - olo) + 4
+
     def get_particle_count(self):
         return self.h.get_particle_count()
+
+    def state_checksum(self) -> torch.Tensor:
+        """handler.ParticleHandler2D.state_checksum summed over the strips: the checksum of the GLOBAL particle set, equal to a
+        single GPU's on the same problem iff owner cells and positions agree bit for bit."""
+        t = self.h.state_checksum()
+        if dist.is_initialized():
+            dist.all_reduce(t, group=self.group)  # wrapping int64 sums
+        return t
 
     def global_particle_count(self):
         t = torch.tensor([self.get_particle_count()], dtype=torch.int64, device=self.mesh.device)
@@ -303,99 +342,106 @@ class DistributedParticleHandler2D:
 
 
 # ------------------------------------------------------------------------------------------------
-# bench.py entry for N > 1 (launched by torchrun, one rank per GPU)
+# run-time parity check of the strip-partitioned path (bench.py runs it inside the same torchrun before it times anything)
 # ------------------------------------------------------------------------------------------------
-def bench_main(args, rank, world, local):
-    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sys.path.insert(0, ROOT)
-    import bench
+def parity_selfcheck(rank, world, device, steps=6, migration="p2p") -> dict:
+    """A small channel over `world` strips against ONE GPU on the same global problem (rank 0 runs both): global particle count
+    and the order-independent state checksum (owner cells, positions, local coordinates: bit-exact) after every step, projected
+    nodal field of every strip's nodes within 1e-12, and the tolerance-band spill of the occupancy bits across a strip
+    boundary (crafted state, the strips must re-seed exactly like one GPU).  Raises on a mismatch.
+    (tests/mg_worker.py is the full version: all transports, the stable order, canonicalised state comparison.)"""
     from . import handler
 
-    torch.cuda.set_device(local)
-    device = f"cuda:{local}"
-    if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device(device))
-    if args.workload not in bench.WORKLOADS:
-        raise SystemExit("multi-GPU bench runs the synthetic channel workloads")
-    nx, ny, lx, ly, level, umax, dt = bench.channel_params(args, world)
-    dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device)
-    fx, fy = bench.nodal_field(args, dm.vertices[:, 0].contiguous(), dm.vertices[:, 1].contiguous(), lx, ly, umax)
-    F = (fx.contiguous(), fy.contiguous())
-    W = (torch.zeros_like(F[0]), torch.zeros_like(F[0]))
+    nx, ny, level, S = 16 * world, 16, 4, 3
+    dm = handler.device_structured_channel(nx, ny, 0.5 * world, 0.5, colmajor=True, device=device)
+    x, y = dm.vertices[:, 0].contiguous(), dm.vertices[:, 1].contiguous()
+    k = 2.0 * np.pi / 0.25
+    F = ((4.0 * y * (0.5 - y) / 0.25 + 0.3 * torch.sin(k * x) * torch.cos(k * y)).contiguous(),
+         (-0.3 * torch.cos(k * x) * torch.sin(k * y)).contiguous())
+    dt = 0.3 * (0.5 * world / nx) * S
     bounds = strip_bounds(dm.n_cells, world, align=2 * ny)
-    h = DistributedParticleHandler2D(dm, level, bounds, rank, world, max_division_level=8, capacity_factor=args.capacity_factor)
+    h = DistributedParticleHandler2D(dm, level, bounds, rank, world, migration=migration)
+    W = (torch.zeros_like(x), torch.zeros_like(x))
+    ref = RW = None
+    if rank == 0:
+        ref = handler.ParticleHandler2D(dm, level)
+        RW = (torch.zeros_like(x), torch.zeros_like(x))
+    for hh in (h, ref):
+        if hh is not None:
+            hh.seed_particles()
+            hh.init_particle_velocity(F)
+    mine = torch.unique(dm.cells[int(bounds[rank]):int(bounds[rank + 1])].to(torch.int64))
+    worst = torch.zeros(1, dtype=torch.float64, device=device)
+    migrated = 0
+    for s in range(steps):
+        h.step(F, W, dt, S)
+        migrated += h.last_sent
+        cs = h.state_checksum()
+        if rank == 0:
+            ref.step(F, RW, dt, S)
+            rcs = ref.state_checksum()
+            if not torch.equal(cs, rcs):
+                raise RuntimeError(f"multi-GPU parity: state checksum after step {s + 1} differs: {cs.tolist()} on {world} GPUs, {rcs.tolist()} on one")
+        ref_w = [RW[0] if rank == 0 else torch.empty_like(x), RW[1] if rank == 0 else torch.empty_like(x)]
+        for t in ref_w:
+            dist.broadcast(t, 0)
+        for a, b in zip(W, ref_w):
+            worst = torch.maximum(worst, (a[mine] - b[mine]).abs().max() / b.abs().max().clamp_min(1e-300))
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    moved = torch.tensor([migrated], dtype=torch.int64, device=device)
+    dist.all_reduce(moved)
+    if float(worst) > 1e-12:
+        raise RuntimeError(f"multi-GPU parity: projected nodal field differs by {float(worst):.3e} relative (bar 1e-12)")
+    if int(moved) == 0:
+        raise RuntimeError("multi-GPU parity: the check case migrated no particle")
+    out = {"gpus": world, "steps": steps, "particles": int(cs[0]), "migrated": int(moved), "nodal_rel_err": float(worst),
+           "state_checksum": [int(v) for v in cs.tolist()], "transport": h.protocol}
+    h.close()
+    if ref is not None:
+        ref.close()
+    out["spill"] = _spill_selfcheck(rank, world, device, migration)
+    return out
+
+
+def _spill_selfcheck(rank, world, device, migration):
+    """SURVEY N4 across a strip boundary (see tests/mg_worker.py::spill_case): a particle in the tolerance band of the LAST cell
+    of rank 0 sets an occupancy bit in the word of the FIRST cell of rank 1 and suppresses one re-seed there."""
+    from . import handler
+
+    nx, ny, level = 4 * world, 4, 2
+    ppc = level * level
+    dm = handler.device_structured_channel(nx, ny, 0.5 * world, 0.5, colmajor=True, device=device)
+    zero = torch.zeros(dm.n_nodes, dtype=torch.float64, device=device)
+    F, W = (zero, zero.clone()), (zero.clone(), zero.clone())
+    bounds = strip_bounds(dm.n_cells, world, align=2 * ny)
+    ref = handler.ParticleHandler2D(dm, level)
+    ref.seed_particles()
+    ref.init_particle_velocity(F)
+    s = ref.download()  # seeded order: particle of (cell, sub-cell) at cell * ppc + sub-cell
+    c = int(bounds[1]) - 1
+    tri = dm.cells[c].cpu().numpy().view(np.uint32)
+    v = dm.vertices.cpu().numpy()[tri.astype(np.int64)]
+    L = np.array([0.3, -1.0e-6, 0.7 + 1.0e-6])
+    pos = L[0] * v[0] + L[1] * v[1] + L[2] * v[2]
+    keep = np.ones(s["x"].shape[0], dtype=bool)
+    keep[(c + 1) * ppc + 0] = keep[(c + 1) * ppc + 1] = False
+    st = {k: a[keep] for k, a in s.items()}
+    add = {"x": pos[0], "y": pos[1], "l0": L[0], "l1": L[1], "l2": L[2], "vx": 0.0, "vy": 0.0, "cell": c, "id": 0}
+    st = {k: np.concatenate([a, np.asarray([add[k]], dtype=a.dtype)]) for k, a in st.items()}
+    ref.upload(st)
+    ref.step(F, W, 0.01, 3)
+    single = (ref.get_particle_count(), ref.stats()["added"])
+    ref.close()
+    h = DistributedParticleHandler2D(dm, level, bounds, rank, world, migration=migration)
     h.seed_particles()
     h.init_particle_velocity(F)
-    sampler = bench.ClockSampler(local) if rank == 0 else None
-    for _ in range(args.warmup):
-        h.step(F, W, dt, args.substeps)
-    h.get_particle_count()
-    torch.cuda.synchronize()
-    if sampler:
-        sampler.wait_first_sample()
-        sampler.mark()
-    dist.barrier()
-    h.h.set_profiling(True)
-    h.h.phase_times(reset=True)
-    launches0 = handler.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    counts, sent = [], 0
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0.record()
-    for _ in range(args.steps):
-        h.step(F, W, dt, args.substeps)
-        counts.append(h.get_particle_count())
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms = e0.elapsed_time(e1)
-    sent = h.last_sent * args.steps  # the last step's hand-over (read outside the timed region), steady state
-    clocks = sampler.stop() if sampler else None
-    phases = h.h.phase_times(reset=True)
-    launches = handler.kernel_launches() - launches0
-    t = torch.tensor([ms, float(sum(counts)), float(sent)], dtype=torch.float64, device=device)
-    tmax = t.clone()
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    tsum = t.clone()
-    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    if rank == 0:
-        total_ms = float(tmax[0])
-        psteps = float(tsum[1])
-        value = psteps / (total_ms * 1e-3)
-        peak, peak_src = bench.peaks()
-        pmean_rank = sum(counts) / args.steps
-        dom = max(bench.ALG_BYTES, key=lambda n: phases[n][0])
-        dom_ms = phases[dom][0] / args.steps
-        achieved = bench.ALG_BYTES[dom] * pmean_rank / (dom_ms * 1e-3) / 1e9
-        out = {
-            "metric": "particle-steps/sec (advect+locate+sort+project+correct)", "value": value, "unit": "particle-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak" if args.workload in bench.WEAK else "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": bench.workload_description(args, world) + f", strip-partitioned over {world} GPUs (quad columns)",
-                       "particles_mean": psteps / args.steps, "cells": dm.n_cells, "nodes": dm.n_nodes, "substeps": args.substeps, "dt": dt,
-                       "l2": "inputs larger than L2", "timing": "CUDA events on rank-local default stream, max over ranks, barrier on both sides",
-                       "migrated_particles_per_step": float(tsum[2]) / args.steps,
-                       "migration_protocol": h.protocol,
-                       "collectives": {
-                           "p2p": "NVLink peer memory (CUDA IPC): emigrant records and interface-node accumulators stored straight into the "
-                                  "neighbour strip's HBM, device-side sequence flags; no NCCL and no host in the loop",
-                           "neighbour": "fixed-size migration buffers [header | records] to / from the adjacent strips (ncclSend / ncclRecv, "
-                                        "counts stay on the device) + pairwise isend/irecv of interface-node accumulators (NCCL)",
-                           "exact": "all_to_all_single (counts, 64-byte particle records) + pairwise isend/irecv of interface-node "
-                                    "accumulators (NCCL)"}[h.protocol]},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "alg_bytes_per_particle": bench.ALG_BYTES[dom], "note": "rank 0, per GPU",
-                         "step": {"achieved": bench.ALG_BYTES_STEP * value / 1e9 / world, "frac": bench.ALG_BYTES_STEP * value / 1e9 / world / peak,
-                                  "alg_bytes_per_particle_step": bench.ALG_BYTES_STEP, "note": "per GPU"},
-                         "phases": {k: {"ms_per_step": v[0] / args.steps} for k, v in phases.items()}},
-            "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * world,
-                    "note": "multi-GPU steps run through the public DistributedParticleHandler2D API; per step each rank reads back its "
-                            "particle count (one host sync), nodal fields stay device-resident"},
-            "gpu_launches": int(launches), "clocks": clocks,
-        }
-        print(json.dumps(out))
+    own = (st["cell"] >= int(bounds[rank])) & (st["cell"] < int(bounds[rank + 1]))
+    h.h.upload({k: a[own] for k, a in st.items()})
+    h.step(F, W, 0.01, 3)
+    multi = h.global_particle_count()
     h.close()
-    dist.barrier()
-    dist.destroy_process_group()
+    if single[1] != 1:
+        raise RuntimeError(f"multi-GPU parity: the crafted spill state re-seeded {single[1]} sub-cells on one GPU, expected 1")
+    if multi != single[0]:
+        raise RuntimeError(f"multi-GPU parity: {world} GPUs hold {multi} particles, one GPU {single[0]}: spill bits lost at the strip boundary")
+    return {"single_gpu_count": single[0], "multi_gpu_count": multi}

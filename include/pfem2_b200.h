@@ -155,6 +155,11 @@ int pfem2_cell_starts(pfem2_handle *h, const int **d_cell_start);
  *     project_accumulate ; <sum interface-node accumulators over NCCL> ; project_finalize ; correct
  * Records are the library's 64-byte particle records: {x, y | L0, L1 | L2, cell, id | vx, vy}. ---- */
 int pfem2_set_owned_cells(pfem2_handle *h, int cell_lo, int cell_hi); /* before pfem2_seed; seeds / re-seeds only these cells */
+/* node id ranges of a strip (host-side staging of nodal fields per rank): out4 = { in_lo, in_hi, own_lo, own_hi }.  An advect with
+ * `substeps` substeps reads the nodal velocity only at the nodes [in_lo, in_hi) (the cells a particle of the owned range can reach:
+ * band width of the one-ring lists x substeps); the projection writes and the correction reads the nodes [own_lo, own_hi) of the
+ * owned cells.  The whole node range on a single GPU. */
+int pfem2_node_ranges(pfem2_handle *h, int substeps, int *out4);
 int pfem2_advect_move(pfem2_handle *h, const double *d_vx, const double *d_vy, double dt, int substeps);
 /* per destination rank (cells [h_bounds[r], h_bounds[r+1])) the number of live particles that left the owned range */
 int pfem2_emigrants_count(pfem2_handle *h, const int *h_bounds, int n_ranks, int *h_counts);

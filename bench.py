@@ -68,7 +68,11 @@ def nodal_field(args, x, y, lx, ly, umax):
         mod = __import__("torch") if hasattr(x, "device") else __import__("numpy")
         k = 2.0 * math.pi / 0.5  # 50-cell vortices
         return (0.5 * umax + 0.5 * umax * mod.sin(k * x) * mod.cos(k * y), -0.5 * umax * mod.cos(k * x) * mod.sin(k * y))
-    return (4.0 * umax * y * (ly - y) / (ly * ly), 0.0 * y)
+    mod = __import__("torch") if hasattr(x, "device") else __import__("numpy")
+    t = 4.0 * umax * y * (ly - y)
+    # IEEE division like oracle/ref_harness.cu (on CUDA torch turns tensor / python-scalar into a multiplication by the rounded
+    # reciprocal): both arms of the bench then advect through bit-identical nodal fields
+    return (t / mod.full_like(t, ly * ly) if hasattr(x, "device") else t / (ly * ly), 0.0 * y)
 
 
 def peaks():
@@ -239,7 +243,16 @@ def build_problem(args, rank, world, device):
 
     if args.workload in WORKLOADS:
         nx, ny, lx, ly, level, umax, dt = channel_params(args, world)
-        dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device)
+        if world > 1:
+            # partitioned mesh: this rank generates only its own quad columns + the halo a particle can reach in one advect
+            from gpupfem2_b200 import multi_gpu
+
+            band = handler.mesh_band(handler.device_structured_channel(4, ny, 4 * lx / nx, ly, colmajor=True, device=device))
+            bounds = multi_gpu.strip_bounds(2 * nx * ny, world, align=2 * ny)
+            c0, c1 = multi_gpu.channel_slice_columns(nx, ny, bounds, rank, band, args.substeps)
+            dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device, col_lo=c0, col_hi=c1)
+        else:
+            dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device)
         fx, fy = nodal_field(args, dm.vertices[:, 0].contiguous(), dm.vertices[:, 1].contiguous(), lx, ly, umax)
         return dm, level, (fx.contiguous(), fy.contiguous()), dt
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
@@ -286,7 +299,7 @@ def measure(args, rank, world, local, full):
         from gpupfem2_b200 import multi_gpu
 
         ny = WORKLOADS[args.workload][1]
-        bounds = multi_gpu.strip_bounds(dm.n_cells, world, align=2 * ny)
+        bounds = multi_gpu.strip_bounds(dm.n_cells_global, world, align=2 * ny)
         h = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world, **opts)
         inner = h.h
     else:
@@ -435,7 +448,8 @@ def measure(args, rank, world, local, full):
         "ms_per_step_min": sm[0], "ms_per_step_median": statistics.median(sm),
         "higher_is_better": True, "scaling": "weak" if args.workload in WEAK else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_description(args, world) + (f", strip-partitioned over {world} GPUs (quad columns)" if multi else ""),
-                   "particles_mean": psteps / args.steps, "cells": dm.n_cells, "nodes": dm.n_nodes,
+                   "particles_mean": psteps / args.steps, "cells": dm.n_cells_global or dm.n_cells, "nodes": dm.n_nodes_global or dm.n_nodes,
+                   "cells_per_rank_mesh": dm.n_cells,
                    "substeps": args.substeps, "dt": dt, "lazy_sort": lazy,
                    "l2": (f"flushed between timed iterations (512 MiB write; state {state_gb:.3f} GB could fit the 126 MB L2)"
                           if small else f"inputs larger than L2 ({state_gb:.1f} GB of particle state per pass and GPU)"),

@@ -26,7 +26,7 @@ SYMBOLS = (
     "pfem2_immigrants_append", "pfem2_advect_finish", "pfem2_project_accumulate", "pfem2_project_finalize",
     "pfem2_set_rank_bounds", "pfem2_emigrants_pack_neighbours", "pfem2_immigrants_append_device",
     "pfem2_p2p_inbox_create", "pfem2_p2p_connect", "pfem2_emigrants_send_p2p", "pfem2_immigrants_recv_p2p",
-    "pfem2_project_halo_p2p", "pfem2_p2p_last_sent", "pfem2_project_dual", "pfem2_project_dual_ptrs", "pfem2_node_ranges",
+    "pfem2_project_halo_p2p", "pfem2_p2p_last_sent", "pfem2_project_dual", "pfem2_project_dual_ptrs", "pfem2_node_ranges", "pfem2_set_global_cell_offset", "pfem2_mesh_band",
 )
 
 
@@ -108,6 +108,8 @@ def load():
     L.pfem2_project_accumulate.argtypes = [vp, vp]
     L.pfem2_project_finalize.argtypes = [vp, vp, vp, vp]
     L.pfem2_node_ranges.argtypes = [vp, i, C.POINTER(i)]
+    L.pfem2_set_global_cell_offset.argtypes = [vp, i]
+    L.pfem2_mesh_band.argtypes = [i, vp, vp, C.POINTER(i), vp]
     L.pfem2_set_profiling.argtypes = [vp, i]
     L.pfem2_get_phase_times.argtypes = [vp, C.POINTER(d), C.POINTER(C.c_longlong), i]
     _lib = L

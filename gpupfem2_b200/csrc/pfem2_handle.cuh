@@ -99,7 +99,8 @@ struct pfem2_handle {
     double *nodal[4] = {nullptr, nullptr, nullptr, nullptr}; // F.x F.y W.x W.y for pfem2_step_host
 
     // multi-GPU (strip partition)
-    int *mg_bounds = nullptr;     // device copy of the rank cell bounds (n_ranks + 1)
+    int cell_base = 0;            // the mesh view is the slice [cell_base, cell_base + n_cells) of the global cell numbering (partitioned mesh)
+    int *mg_bounds = nullptr;     // device copy of the rank cell bounds (n_ranks + 1), in this strip's numbering
     int *mg_rank_count = nullptr; // device, per destination rank (+ total)
     int mg_ranks = 0;
     std::vector<int> mg_host_counts;

@@ -21,6 +21,21 @@ int pfem2_mesh_inv_jacobi(int n_cells, const double *d_vertices, const unsigned 
     return PFEM2_OK;
 }
 
+int pfem2_mesh_band(int n_cells, const int *d_nbr_offsets, const int *d_nbr_indices, int *band, void *stream)
+{
+    pfem2_handle *h = nullptr;
+    if (n_cells <= 0 || !d_nbr_offsets || !d_nbr_indices || !band) return fail(nullptr, PFEM2_EINVAL, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceTemps tmp;
+    int *dev = nullptr;
+    CU(tmp.alloc(&dev, 1));
+    CU(cudaMemsetAsync(dev, 0, sizeof(int), st));
+    PFEM2_LAUNCH(k_band_width, grid_for(n_cells, kThreads, 1 << 30), kThreads, 0, st, n_cells, d_nbr_offsets, d_nbr_indices, dev);
+    CU(cudaMemcpyAsync(band, dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return PFEM2_OK;
+}
+
 int pfem2_sort_pairs(int n, int key_bits, unsigned *keys, unsigned *vals, unsigned *keys_tmp, unsigned *vals_tmp, int *result_in_tmp,
                      void *stream)
 {

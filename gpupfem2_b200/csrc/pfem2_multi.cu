@@ -27,8 +27,11 @@ int store_rank_bounds(pfem2_handle *h, const int *h_bounds, int n_ranks)
         h->mg_ranks = n_ranks;
     }
     h->mg_host_bounds.assign(h_bounds, h_bounds + n_ranks + 1);
-    // pageable host source: the copy is staged before the call returns, so the vector may change afterwards
-    CU(cudaMemcpyAsync(h->mg_bounds, h->mg_host_bounds.data(), sizeof(int) * (n_ranks + 1), cudaMemcpyHostToDevice, h->stream));
+    // the device copy is in THIS strip's cell numbering (global - cell_base; may be negative / beyond n_cells for far strips)
+    std::vector<int> local(h_bounds, h_bounds + n_ranks + 1);
+    for (int &b : local) b -= h->cell_base;
+    CU(cudaMemcpyAsync(h->mg_bounds, local.data(), sizeof(int) * (n_ranks + 1), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream)); // `local` is a host temporary
     return PFEM2_OK;
 }
 
@@ -41,7 +44,7 @@ int append_migration_block(pfem2_handle *h, const int4 *buf, int capacity_record
     // rank pass, and everybody is summed into stay[] (the fast order keeps no separate arrival counts)
     unsigned *keys = h->lazy_move ? h->keys[1] : nullptr;
     int *arrive = h->lazy_move ? nullptr : h->arrive;
-    PFEM2_LAUNCH(k_immigrant_append_dev, grid, kThreads, 0, st, h->soa[h->cur], h->ctr, buf, capacity_records, keys);
+    PFEM2_LAUNCH(k_immigrant_append_dev, grid, kThreads, 0, st, h->soa[h->cur], h->ctr, buf, capacity_records, keys, h->cell_base);
     PFEM2_LAUNCH(k_count_appended_dev, grid, kThreads, 0, st, h->soa[h->cur], h->ctr, buf, capacity_records, h->opt.subcell_mode ? 1 : 0,
                  h->mesh.n_cells, h->ppc, h->level, h->sub_step, h->stay, arrive, h->cell_mask);
     PFEM2_LAUNCH(k_add_count_dev, 1, 1, 0, st, h->ctr, buf, capacity_records, h->cell_mask, h->own_lo, h->own_hi, from_left ? 1 : 0);
@@ -106,10 +109,10 @@ int pfem2_emigrants_pack(pfem2_handle *h, void *d_records, long long capacity_re
     if (h->mg_fused && h->mg_fused_total >= 0) {
         if (h->mg_fused_total > 0)
             PFEM2_LAUNCH(k_emigrant_pack_list, grid_for(h->mg_fused_total), kThreads, 0, st, h->soa[h->cur], h->keys[0], h->mg_fused_total,
-                         h->mg_bounds, h->mg_ranks, h->mg_rank_count, (int4 *)d_records);
+                         h->mg_bounds, h->mg_ranks, h->mg_rank_count, (int4 *)d_records, h->cell_base);
     } else
     PFEM2_LAUNCH(k_emigrant_pack, grid_for(h->capacity), kThreads, 0, st, h->soa[h->cur], h->ctr, h->own_lo, h->own_hi, h->mg_bounds,
-                 h->mg_ranks, h->mg_rank_count, (int4 *)d_records);
+                 h->mg_ranks, h->mg_rank_count, (int4 *)d_records, h->cell_base);
     CU(cudaStreamSynchronize(st)); // `off` is a host temporary
     return PFEM2_OK;
 }
@@ -123,7 +126,7 @@ int pfem2_immigrants_append(pfem2_handle *h, const void *d_records, int n)
     CU(cudaSetDevice(h->device));
     if ((long long)h->host_count + n > h->capacity) return fail(h, PFEM2_ECAPACITY, "no room for the immigrants");
     PFEM2_LAUNCH(k_immigrant_append, grid_for(n), kThreads, 0, h->stream, h->soa[h->cur], h->ctr, (const int4 *)d_records, n,
-                 h->lazy_move ? h->keys[1] : (unsigned *)nullptr);
+                 h->lazy_move ? h->keys[1] : (unsigned *)nullptr, h->cell_base);
     if (h->mg_fused) { // the move pass counted the residents; the immigrants are counted here (no pass over everybody later)
         PFEM2_LAUNCH(k_count_appended, grid_for(n), kThreads, 0, h->stream, h->soa[h->cur], h->ctr, n, h->opt.subcell_mode ? 1 : 0,
                      h->mesh.n_cells, h->ppc, h->level, h->sub_step, h->stay, h->lazy_move ? (int *)nullptr : h->arrive, h->cell_mask);
@@ -131,6 +134,14 @@ int pfem2_immigrants_append(pfem2_handle *h, const void *d_records, int n)
     PFEM2_LAUNCH(k_add_count, 1, 1, 0, h->stream, h->ctr, n);
     h->host_count += n;
     CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int pfem2_set_global_cell_offset(pfem2_handle *h, int cell_offset)
+{
+    if (!h || cell_offset < 0) return PFEM2_EINVAL;
+    if (h->seeded || h->mg_ranks) return fail(h, PFEM2_ESTATE, "set_global_cell_offset after seed / set_rank_bounds");
+    h->cell_base = cell_offset;
     return PFEM2_OK;
 }
 
@@ -162,7 +173,7 @@ int pfem2_emigrants_pack_neighbours(pfem2_handle *h, int rank, void *d_left, voi
     // the number of emigrants lives on the device (rank_count[n_ranks]): a fixed grid strides over the list
     PFEM2_LAUNCH(k_emigrant_pack_nbr, grid_for(capacity_records, kThreads, g_num_sms * 2), kThreads, 0, st, h->soa[h->cur], h->keys[0],
                  h->mg_rank_count, h->mg_ranks, h->mg_bounds, rank, (int4 *)d_left, (int4 *)d_right, capacity_records, h->ctr,
-                 h->cell_mask, h->own_hi, h->mesh.n_cells);
+                 h->cell_mask, h->own_hi, h->mesh.n_cells, h->cell_base);
     h->mg_fused_total = -1; // consumed
     CU(cudaGetLastError());
     return PFEM2_OK;
@@ -263,7 +274,7 @@ int pfem2_emigrants_send_p2p(pfem2_handle *h, int rank)
     MigrationHeader *hr = pr ? (MigrationHeader *)(pr + p2p_block_offset(cap, parity)) : nullptr;
     PFEM2_LAUNCH(k_emigrant_pack_p2p, grid_for(cap, kThreads, g_num_sms * 2), kThreads, 0, st, h->soa[h->cur], h->keys[0], h->mg_rank_count,
                  h->mg_ranks, h->mg_bounds, rank, hl ? (int4 *)(hl + 1) : nullptr, hr ? (int4 *)(hr + 1) : nullptr, cap, h->ctr,
-                 h->p2p.cursors);
+                 h->p2p.cursors, h->cell_base);
     PFEM2_LAUNCH(k_p2p_publish_migration, 1, 1, 0, st, hl, pl ? &((P2PInboxHead *)pl)->flag_mig : nullptr, hr,
                  pr ? &((P2PInboxHead *)pr)->flag_mig : nullptr, h->p2p.cursors, cap, h->cell_mask, h->own_hi, h->mesh.n_cells, seq);
     h->mg_fused_total = -1; // consumed

@@ -30,7 +30,7 @@ k_emigrant_count(ParticleSoA p, const Counters *ctr, int own_lo, int own_hi, con
 // exclusive prefix of the counts) and removes them from the local array (cell = lost).
 static __global__ void __launch_bounds__(kThreads)
 k_emigrant_pack(ParticleSoA p, const Counters *ctr, int own_lo, int own_hi, const int *__restrict__ bounds, int n_ranks,
-                int *__restrict__ rank_cursor, int4 *__restrict__ out)
+                int *__restrict__ rank_cursor, int4 *__restrict__ out, int cell_base)
 {
     const int n = ctr->count;
     const int lane = threadIdx.x & 31;
@@ -50,7 +50,9 @@ k_emigrant_pack(ParticleSoA p, const Counters *ctr, int own_lo, int own_hi, cons
         int4 *rec = out + 4 * (size_t)slot;
         rec[0] = *reinterpret_cast<const int4 *>(p.pos + i);
         rec[1] = *reinterpret_cast<const int4 *>(p.lab + i);
-        rec[2] = *reinterpret_cast<const int4 *>(p.tail + i);
+        int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
+        t.z += cell_base; // records between strips carry GLOBAL cell ids
+        rec[2] = t;
         rec[3] = *reinterpret_cast<const int4 *>(p.vel + i);
         st_cell(p.tail + i, kLostCell);
     }
@@ -60,15 +62,16 @@ k_emigrant_pack(ParticleSoA p, const Counters *ctr, int own_lo, int own_hi, cons
 // them grouped by destination rank (rank_cursor starts at the exclusive prefix of the counts) and remove them locally.
 static __global__ void __launch_bounds__(kThreads)
 k_emigrant_pack_list(ParticleSoA p, const unsigned *__restrict__ emig_idx, int n_emig, const int *__restrict__ bounds, int n_ranks,
-                     int *__restrict__ rank_cursor, int4 *__restrict__ out)
+                     int *__restrict__ rank_cursor, int4 *__restrict__ out, int cell_base)
 {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_emig; j += gridDim.x * blockDim.x) {
         const unsigned i = emig_idx[j];
-        const int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
+        int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
         const int slot = atomicAdd(rank_cursor + rank_of_cell((unsigned)t.z, bounds, n_ranks), 1);
         int4 *rec = out + 4 * (size_t)slot;
         rec[0] = *reinterpret_cast<const int4 *>(p.pos + i);
         rec[1] = *reinterpret_cast<const int4 *>(p.lab + i);
+        t.z += cell_base;
         rec[2] = t;
         rec[3] = *reinterpret_cast<const int4 *>(p.vel + i);
         st_cell(p.tail + i, kLostCell);
@@ -104,12 +107,13 @@ k_count_appended(ParticleSoA p, const Counters *ctr, int m, int subcell_mode, in
 // immigrants: 64-byte records appended behind the current array
 // (keys != nullptr, lazy re-sort: the appended rows also get their entry in the dense key array the rank pass reads)
 static __global__ void __launch_bounds__(kThreads)
-k_immigrant_append(ParticleSoA p, Counters *ctr, const int4 *__restrict__ in, int m, unsigned *__restrict__ keys)
+k_immigrant_append(ParticleSoA p, Counters *ctr, const int4 *__restrict__ in, int m, unsigned *__restrict__ keys, int cell_base)
 {
     const int n = ctr->count;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
         const int4 *rec = in + 4 * (size_t)j;
-        const int4 t = rec[2];
+        int4 t = rec[2];
+        t.z -= cell_base; // global -> this strip's numbering
         *reinterpret_cast<int4 *>(p.pos + (n + j)) = rec[0];
         *reinterpret_cast<int4 *>(p.lab + (n + j)) = rec[1];
         *reinterpret_cast<int4 *>(p.tail + (n + j)) = t;
@@ -144,7 +148,7 @@ static_assert(sizeof(MigrationHeader) == sizeof(ParticleRec), "the header occupi
 static __global__ void __launch_bounds__(kThreads)
 k_emigrant_pack_nbr(ParticleSoA p, const unsigned *__restrict__ emig_idx, const int *__restrict__ rank_count, int n_ranks,
                     const int *__restrict__ bounds, int rank, int4 *out_left, int4 *out_right, int cap, Counters *ctr,
-                    const unsigned long long *__restrict__ cell_mask, int own_hi, int n_cells)
+                    const unsigned long long *__restrict__ cell_mask, int own_hi, int n_cells, int cell_base)
 {
     const int n_emig = rank_count[n_ranks];
     if (blockIdx.x == 0 && threadIdx.x < 4 && out_right) {
@@ -153,8 +157,9 @@ k_emigrant_pack_nbr(ParticleSoA p, const unsigned *__restrict__ emig_idx, const 
     }
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_emig; j += gridDim.x * blockDim.x) {
         const unsigned i = emig_idx[j];
-        const int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
+        int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
         const int dest = rank_of_cell((unsigned)t.z, bounds, n_ranks);
+        t.z += cell_base; // records between strips carry GLOBAL cell ids
         int4 *out = dest == rank - 1 ? out_left : (dest == rank + 1 ? out_right : nullptr);
         st_cell(p.tail + i, kLostCell);
         if (!out) { // more than one strip away in one step (or no such neighbour): the strips are too thin for this time step
@@ -183,13 +188,15 @@ __device__ __forceinline__ int migration_count(const int4 *buf, int cap)
 
 // immigrants of one received migration buffer, appended behind the current array (count taken from the header)
 static __global__ void __launch_bounds__(kThreads)
-k_immigrant_append_dev(ParticleSoA p, const Counters *ctr, const int4 *__restrict__ buf, int cap, unsigned *__restrict__ keys)
+k_immigrant_append_dev(ParticleSoA p, const Counters *ctr, const int4 *__restrict__ buf, int cap, unsigned *__restrict__ keys,
+                       int cell_base)
 {
     const int m = migration_count(buf, cap), n = ctr->count;
     if ((long long)n + m > ctr->capacity) return; // k_add_count_dev raises the overflow flag
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
         const int4 *rec = buf + 4 * ((size_t)j + 1);
-        const int4 t = rec[2];
+        int4 t = rec[2];
+        t.z -= cell_base; // global -> this strip's numbering
         *reinterpret_cast<int4 *>(p.pos + (n + j)) = rec[0];
         *reinterpret_cast<int4 *>(p.lab + (n + j)) = rec[1];
         *reinterpret_cast<int4 *>(p.tail + (n + j)) = t;
@@ -296,13 +303,15 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 // from LOCAL cursors (no atomics over NVLink).  rec_left / rec_right point at the first record of the peer's block.
 static __global__ void __launch_bounds__(kThreads)
 k_emigrant_pack_p2p(ParticleSoA p, const unsigned *__restrict__ emig_idx, const int *__restrict__ rank_count, int n_ranks,
-                    const int *__restrict__ bounds, int rank, int4 *rec_left, int4 *rec_right, int cap, Counters *ctr, int *cursors)
+                    const int *__restrict__ bounds, int rank, int4 *rec_left, int4 *rec_right, int cap, Counters *ctr, int *cursors,
+                    int cell_base)
 {
     const int n_emig = rank_count[n_ranks];
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_emig; j += gridDim.x * blockDim.x) {
         const unsigned i = emig_idx[j];
-        const int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
+        int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
         const int dest = rank_of_cell((unsigned)t.z, bounds, n_ranks);
+        t.z += cell_base; // records between strips carry GLOBAL cell ids
         const int side = dest == rank - 1 ? 0 : (dest == rank + 1 ? 1 : -1);
         int4 *out = side == 0 ? rec_left : (side == 1 ? rec_right : nullptr);
         st_cell(p.tail + i, kLostCell);

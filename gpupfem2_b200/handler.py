@@ -24,6 +24,9 @@ class Pfem2Error(RuntimeError):
 class DeviceMesh:
     """The reference Mesh2D's device arrays (src/mesh_2d.cuh:18-44) as torch CUDA tensors."""
 
+    cell_base = node_base = 0        # offsets of a mesh slice into the global numbering (partitioned multi-GPU runs)
+    n_cells_global = n_nodes_global = None
+
     def __init__(self, mesh: HostMesh, device="cuda:0", build_missing=True):
         self.device = torch.device(device)
         self.n_nodes, self.n_cells = mesh.n_nodes, mesh.n_cells
@@ -70,33 +73,73 @@ class DeviceMesh:
                              self.inv_jacobi.data_ptr(), self.nbr_offsets.data_ptr(), self.nbr_indices.data_ptr())
 
 
-def device_structured_channel(nx, ny, lx, ly, colmajor=True, device="cuda:0") -> "DeviceMesh":
+def device_structured_channel(nx, ny, lx, ly, colmajor=True, device="cuda:0", col_lo=None, col_hi=None) -> "DeviceMesh":
     """mesh.structured_channel generated directly in HBM (same numbering and the same x = i*hx, y = j*hy
-    arithmetic, so the vertex bits agree with the host generator and with oracle/ref_harness.cu)."""
+    arithmetic, so the vertex bits agree with the host generator and with oracle/ref_harness.cu).
+
+    col_lo / col_hi (colmajor only): only the quad columns [col_lo, col_hi) of the global channel are generated -- the mesh
+    slice of one strip of a partitioned multi-GPU run (owned columns + halo).  Cell and node ids are relative to the slice
+    (`cell_base`, `node_base` give the offsets into the global numbering, `n_cells_global` the global size); coordinates use
+    the GLOBAL column index, so their bits are those of the global mesh."""
     dev = torch.device(device)
     hx, hy = lx / nx, ly / ny
-    i = torch.arange(nx + 1, device=dev, dtype=torch.int64)
+    i0, i1 = (0, nx) if col_lo is None else (int(col_lo), int(col_hi))
+    if (i0, i1) != (0, nx) and not colmajor:
+        raise ValueError("column slices need the column-major numbering")
+    if not 0 <= i0 < i1 <= nx:
+        raise ValueError("bad column range")
+    i = torch.arange(i0, i1 + 1, device=dev, dtype=torch.int64)
     j = torch.arange(ny + 1, device=dev, dtype=torch.int64)
+    ni = i1 - i0
     if colmajor:  # node = i*(ny+1)+j
-        x = (i.to(torch.float64) * hx)[:, None].expand(nx + 1, ny + 1)
-        y = (j.to(torch.float64) * hy)[None, :].expand(nx + 1, ny + 1)
+        x = (i.to(torch.float64) * hx)[:, None].expand(ni + 1, ny + 1)
+        y = (j.to(torch.float64) * hy)[None, :].expand(ni + 1, ny + 1)
     else:  # node = j*(nx+1)+i
         x = (i.to(torch.float64) * hx)[None, :].expand(ny + 1, nx + 1)
         y = (j.to(torch.float64) * hy)[:, None].expand(ny + 1, nx + 1)
     vertices = torch.stack([x.reshape(-1), y.reshape(-1)], dim=1).contiguous()
 
-    def nid(a, b):
+    def nid(a, b):  # (a = column index relative to the slice)
         return a * (ny + 1) + b if colmajor else b * (nx + 1) + a
 
-    qi = torch.arange(nx, device=dev, dtype=torch.int64)
+    qi = torch.arange(ni, device=dev, dtype=torch.int64)
     qj = torch.arange(ny, device=dev, dtype=torch.int64)
     if colmajor:  # quad = i*ny+j
-        I, J = qi[:, None].expand(nx, ny).reshape(-1), qj[None, :].expand(nx, ny).reshape(-1)
+        I, J = qi[:, None].expand(ni, ny).reshape(-1), qj[None, :].expand(ni, ny).reshape(-1)
     else:  # quad = j*nx+i
         I, J = qi[None, :].expand(ny, nx).reshape(-1), qj[:, None].expand(ny, nx).reshape(-1)
     a, b, c, d = nid(I, J), nid(I + 1, J), nid(I + 1, J + 1), nid(I, J + 1)
     cells = torch.stack([a, b, c, a, c, d], dim=1).reshape(-1, 3).to(torch.int32).contiguous()
-    return DeviceMesh.from_tensors(vertices, cells)
+    dm = DeviceMesh.from_tensors(vertices, cells)
+    dm.cell_base, dm.node_base = 2 * ny * i0, (ny + 1) * i0
+    dm.n_cells_global, dm.n_nodes_global = 2 * nx * ny, (nx + 1) * (ny + 1)
+    return dm
+
+
+def device_mesh_slice(vertices, cells, cell_lo: int, cell_hi: int, device="cuda:0") -> "DeviceMesh":
+    """The cells [cell_lo, cell_hi) of a global mesh (host arrays or tensors: vertices (N, 2) float64, cells (C, 3)) as a
+    DeviceMesh of its own: node ids relative to the smallest node id the slice touches.  For numberings in which a contiguous
+    cell range touches a contiguous-enough node range (banded numberings: sort the cells by centroid x and number the nodes
+    accordingly); inverse Jacobians and the one-ring are rebuilt on the device, cell by cell the same bits as the global mesh's."""
+    v = torch.as_tensor(np.ascontiguousarray(vertices, dtype=np.float64)) if not isinstance(vertices, torch.Tensor) else vertices
+    c = torch.as_tensor(np.ascontiguousarray(cells).astype(np.int64)) if not isinstance(cells, torch.Tensor) else cells.to(torch.int64)
+    sl = c[int(cell_lo):int(cell_hi)]
+    n_lo, n_hi = int(sl.min()), int(sl.max()) + 1
+    dm = DeviceMesh.from_tensors(v[n_lo:n_hi].to(device).contiguous(), (sl - n_lo).to(torch.int32).to(device).contiguous())
+    dm.cell_base, dm.node_base = int(cell_lo), n_lo
+    dm.n_cells_global, dm.n_nodes_global = int(c.shape[0]), int(v.shape[0])
+    return dm
+
+
+def mesh_band(mesh: "DeviceMesh") -> int:
+    """max |neighbour - cell| over the one-ring lists: how far a particle's cell INDEX can move in one substep."""
+    L = _lib.load()
+    out = C.c_int(0)
+    with torch.cuda.device(mesh.device):
+        rc = L.pfem2_mesh_band(mesh.n_cells, mesh.nbr_offsets.data_ptr(), mesh.nbr_indices.data_ptr(), C.byref(out), None)
+    if rc:
+        raise Pfem2Error(L.pfem2_last_error(None).decode())
+    return out.value
 
 
 def device_one_ring(n_nodes: int, cells: torch.Tensor):

@@ -10,9 +10,13 @@ contiguous strips (for the x-major channel numbering: slabs of quad columns); ra
      strips are exchanged pairwise and added BEFORE the division (a + b is commutative in IEEE arithmetic, so
      both sides get the same bits).
 
-Every rank holds the whole (read-only) mesh and nodal field: 16M triangles cost about 3 GB of HBM per GPU, and it
-lets the locate step resolve a particle that crosses the interface exactly like the single-GPU rule (own cell,
-then ascending one-ring) without halo bookkeeping.
+The mesh is PARTITIONED (round 2): a rank holds its own cells plus a halo of the cells a particle can reach in one advect
+(band width of the one-ring lists x substeps on either side of the strip, `halo_cells`), as a mesh slice with its own
+numbering (handler.device_structured_channel(col_lo=, col_hi=) / handler.device_mesh_slice; `cell_base`, `node_base` are the
+offsets into the global numbering).  Inside the halo the locate step resolves a crossing particle exactly like the single-GPU
+rule (own cell, then ascending one-ring: the slice's one-ring lists are the global ones for every cell a particle of the strip
+can visit); records that cross strips carry global cell ids.  Passing the whole global mesh to every rank (cell_base = 0) still
+works and is what the replicated-mesh tests do.
 
 The host logic here (partition, interface node lists, exchange protocol) is backend-agnostic: it moves torch
 tensors, CUDA over NCCL in production and CPU over gloo in tests/test_multi_rank_gloo.py.
@@ -79,6 +83,19 @@ def interface_nodes(cells, bounds, rank: int) -> dict:
         if shared.numel():
             out[r] = torch.sort(shared).values
     return out
+
+
+def halo_cells(band: int, substeps: int) -> int:
+    """Cells a strip's mesh slice needs on either side of its own range: a particle's cell index changes by at most `band`
+    (pfem2_mesh_band) per substep, and the one-ring scan of the last substep looks one more ring ahead."""
+    return int(band) * (int(substeps) + 1)
+
+
+def channel_slice_columns(nx: int, ny: int, bounds, rank: int, band: int, substeps: int):
+    """Quad columns [col_lo, col_hi) of the x-major channel that rank `rank` needs: its own columns + the halo."""
+    per_col = 2 * ny
+    halo = -(-halo_cells(band, substeps) // per_col)
+    return max(0, int(bounds[rank]) // per_col - halo), min(nx, -(-int(bounds[rank + 1]) // per_col) + halo)
 
 
 def exchange_records(send_buf: torch.Tensor, send_counts, group=None):
@@ -157,10 +174,19 @@ class DistributedParticleHandler2D:
             raise RuntimeError("DistributedParticleHandler2D must be created and driven on torch's default stream")
         self.mesh = mesh
         self.rank, self.world, self.group = rank, world, group
-        self.bounds = np.ascontiguousarray(bounds, dtype=np.int32)
+        self.bounds = np.ascontiguousarray(bounds, dtype=np.int32)  # GLOBAL cell ids
+        self.cell_base = int(getattr(mesh, "cell_base", 0))         # the mesh may be a slice of the global one (partitioned run)
+        lo, hi = int(self.bounds[rank]) - self.cell_base, int(self.bounds[rank + 1]) - self.cell_base
+        if not 0 <= lo <= hi <= mesh.n_cells:
+            raise ValueError("the mesh slice does not contain the strip's own cells")
         self.h = handler.ParticleHandler2D(mesh, cell_division_level, **opts)
-        self.h._check(self.L.pfem2_set_owned_cells(self.h._h, int(self.bounds[rank]), int(self.bounds[rank + 1])), "set_owned_cells")
-        self.iface = interface_nodes(mesh.cells.view(torch.int32), self.bounds, rank)
+        if self.cell_base:
+            self.h._check(self.L.pfem2_set_global_cell_offset(self.h._h, self.cell_base), "set_global_cell_offset")
+        self.h._check(self.L.pfem2_set_owned_cells(self.h._h, lo, hi), "set_owned_cells")
+        # interface nodes in the slice's numbering; both strips see the cells on either side of their common boundary (halo >= one
+        # ring), so they find the same nodes in the same (ascending) order
+        local_bounds = np.clip(self.bounds.astype(np.int64) - self.cell_base, 0, mesh.n_cells)
+        self.iface = interface_nodes(mesh.cells.view(torch.int32), local_bounds, rank)
         self.acc3 = torch.zeros((mesh.n_nodes, 3), dtype=torch.float64, device=mesh.device)
         self._sent = 0
         self.last_received = 0
@@ -322,6 +348,7 @@ class DistributedParticleHandler2D:
         """handler.ParticleHandler2D.state_checksum summed over the strips: the checksum of the GLOBAL particle set, equal to a
         single GPU's on the same problem iff owner cells and positions agree bit for bit."""
         t = self.h.state_checksum()
+        t[6] += t[0] * self.cell_base  # cell ids of a mesh slice -> global
         if dist.is_initialized():
             dist.all_reduce(t, group=self.group)  # wrapping int64 sums
         return t
@@ -332,7 +359,11 @@ class DistributedParticleHandler2D:
         return int(t.item())
 
     def download(self):
-        return self.h.download()
+        """This strip's particles; cell ids GLOBAL."""
+        s = self.h.download()
+        if self.cell_base:
+            s["cell"] = (s["cell"].astype(np.int64) + self.cell_base).astype(np.uint32)
+        return s
 
     def close(self):
         if self.protocol == "p2p" and dist.is_initialized():
@@ -353,24 +384,37 @@ def parity_selfcheck(rank, world, device, steps=6, migration="p2p") -> dict:
     from . import handler
 
     nx, ny, level, S = 16 * world, 16, 4, 3
-    dm = handler.device_structured_channel(nx, ny, 0.5 * world, 0.5, colmajor=True, device=device)
-    x, y = dm.vertices[:, 0].contiguous(), dm.vertices[:, 1].contiguous()
+    lx, ly = 0.5 * world, 0.5
     k = 2.0 * np.pi / 0.25
-    F = ((4.0 * y * (0.5 - y) / 0.25 + 0.3 * torch.sin(k * x) * torch.cos(k * y)).contiguous(),
-         (-0.3 * torch.cos(k * x) * torch.sin(k * y)).contiguous())
-    dt = 0.3 * (0.5 * world / nx) * S
-    bounds = strip_bounds(dm.n_cells, world, align=2 * ny)
+
+    def field(m):
+        x, y = m.vertices[:, 0].contiguous(), m.vertices[:, 1].contiguous()
+        return ((4.0 * y * (0.5 - y) / 0.25 + 0.3 * torch.sin(k * x) * torch.cos(k * y)).contiguous(),
+                (-0.3 * torch.cos(k * x) * torch.sin(k * y)).contiguous())
+
+    dt = 0.3 * (lx / nx) * S
+    bounds = strip_bounds(2 * nx * ny, world, align=2 * ny)
+    # the strips run on PARTITIONED meshes (own columns + halo), the single-GPU reference on the global mesh
+    band = handler.mesh_band(handler.device_structured_channel(4, ny, 4 * lx / nx, ly, colmajor=True, device=device))
+    c0, c1 = channel_slice_columns(nx, ny, bounds, rank, band, S)
+    dm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device, col_lo=c0, col_hi=c1)
+    F = field(dm)
+    x = F[0]
     h = DistributedParticleHandler2D(dm, level, bounds, rank, world, migration=migration)
     W = (torch.zeros_like(x), torch.zeros_like(x))
-    ref = RW = None
+    ref = RW = RF = None
+    n_glob = (nx + 1) * (ny + 1)
     if rank == 0:
-        ref = handler.ParticleHandler2D(dm, level)
-        RW = (torch.zeros_like(x), torch.zeros_like(x))
-    for hh in (h, ref):
-        if hh is not None:
-            hh.seed_particles()
-            hh.init_particle_velocity(F)
-    mine = torch.unique(dm.cells[int(bounds[rank]):int(bounds[rank + 1])].to(torch.int64))
+        gm = handler.device_structured_channel(nx, ny, lx, ly, colmajor=True, device=device)
+        RF = field(gm)
+        ref = handler.ParticleHandler2D(gm, level)
+        RW = (torch.zeros_like(RF[0]), torch.zeros_like(RF[0]))
+        ref.seed_particles()
+        ref.init_particle_velocity(RF)
+    h.seed_particles()
+    h.init_particle_velocity(F)
+    own = slice(int(bounds[rank]) - dm.cell_base, int(bounds[rank + 1]) - dm.cell_base)
+    mine = torch.unique(dm.cells[own].to(torch.int64))  # nodes of this strip's own cells (slice numbering)
     worst = torch.zeros(1, dtype=torch.float64, device=device)
     migrated = 0
     for s in range(steps):
@@ -378,15 +422,16 @@ def parity_selfcheck(rank, world, device, steps=6, migration="p2p") -> dict:
         migrated += h.last_sent
         cs = h.state_checksum()
         if rank == 0:
-            ref.step(F, RW, dt, S)
+            ref.step(RF, RW, dt, S)
             rcs = ref.state_checksum()
             if not torch.equal(cs, rcs):
                 raise RuntimeError(f"multi-GPU parity: state checksum after step {s + 1} differs: {cs.tolist()} on {world} GPUs, {rcs.tolist()} on one")
-        ref_w = [RW[0] if rank == 0 else torch.empty_like(x), RW[1] if rank == 0 else torch.empty_like(x)]
+        ref_w = [RW[0] if rank == 0 else torch.empty(n_glob, dtype=torch.float64, device=device),
+                 RW[1] if rank == 0 else torch.empty(n_glob, dtype=torch.float64, device=device)]
         for t in ref_w:
             dist.broadcast(t, 0)
         for a, b in zip(W, ref_w):
-            worst = torch.maximum(worst, (a[mine] - b[mine]).abs().max() / b.abs().max().clamp_min(1e-300))
+            worst = torch.maximum(worst, (a[mine] - b[mine + dm.node_base]).abs().max() / b.abs().max().clamp_min(1e-300))
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
     moved = torch.tensor([migrated], dtype=torch.int64, device=device)
     dist.all_reduce(moved)

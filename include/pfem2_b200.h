@@ -179,6 +179,12 @@ int pfem2_advect_finish(pfem2_handle *h, const double *d_vx, const double *d_vy)
  * the caller uses emigrants_count / emigrants_pack.  An overflowing buffer or an emigrant bound for a non-adjacent strip sets
  * the sticky overflow flag: the next call that synchronises the counters fails with PFEM2_ECAPACITY. */
 int pfem2_set_rank_bounds(pfem2_handle *h, const int *h_bounds, int n_ranks);
+/* Partitioned mesh: the handle's mesh view holds only the slice [cell_offset, cell_offset + n_cells) of a GLOBAL cell numbering (the
+ * strip's own cells plus the halo cells a particle can reach in one advect: pfem2_mesh_band x substeps on either side), with node
+ * ids relative to the slice's first node.  Everything inside the handle works in the slice's numbering; the rank bounds stay
+ * global and particle records that cross strips carry global cell ids (translated by the pack / append kernels).  Call before
+ * pfem2_set_rank_bounds and pfem2_seed.  0 (default): the view is the global mesh. */
+int pfem2_set_global_cell_offset(pfem2_handle *h, int cell_offset);
 /* d_left / d_right: migration buffers for rank - 1 / rank + 1 (NULL where there is no such strip) */
 int pfem2_emigrants_pack_neighbours(pfem2_handle *h, int rank, void *d_left, void *d_right, int capacity_records);
 /* from_left != 0: the buffer came from rank - 1 (its spill words are OR-ed into this strip's first cells) */
@@ -215,6 +221,10 @@ int pfem2_mesh_inv_jacobi(int n_cells, const double *d_vertices, const unsigned 
  * d_indices of *nnz ints. */
 int pfem2_mesh_one_ring(int n_nodes, int n_cells, const unsigned *d_cells, int *d_offsets, int *d_indices, int *nnz,
                         void *stream);
+
+/* band width of a cell numbering: max |neighbour - cell| over the one-ring lists.  A particle's cell index changes by at most this
+ * much per substep, which bounds the halo a strip needs (band x substeps cells on either side of its range). */
+int pfem2_mesh_band(int n_cells, const int *d_nbr_offsets, const int *d_nbr_indices, int *band, void *stream);
 
 /* ---- stand-alone device radix sort of (cell key, particle index) pairs (exposed for tests) ---- */
 int pfem2_sort_pairs(int n, int key_bits, unsigned *d_keys, unsigned *d_vals, unsigned *d_keys_tmp, unsigned *d_vals_tmp,

@@ -11,6 +11,12 @@
  *   ref_harness timecase <case.bin> <steps> <warmup>   time the particle step on a case file (shipped meshes)
  *   ref_harness time  <nx> <ny> <lx> <ly> <level> <substeps> <dt> <umax> <steps> <warmup> [colmajor]
  *                                                  time the particle step on a synthetic channel
+ *   ref_harness digest <nx> <ny> <lx> <ly> <level> <substeps> <dt> <umax> <steps> <out_prefix>
+ *                                                  full-size parity: per step one JSON line with the particle count and
+ *                                                  order-independent checksums of the reference's particle state (wrapping
+ *                                                  int64 sums of the bit patterns of x, y, L0, L1, L2 and of the cell ids;
+ *                                                  plain double sums of the velocities); the projected nodal field of the
+ *                                                  last step goes to <out_prefix>_w.bin
  *
  * Meshes are injected into Mesh2D through its const getters (the members are deviceVectors with
  * public allocate()), bypassing loadMeshFromFile and its O(C^2) neighbour fill (mesh_2d.cu:107-139);
@@ -355,8 +361,80 @@ static int run_time(int argc, char **argv)
     return 0;
 }
 
+/* full-size parity against the reference itself without a multi-GB dump: order-independent checksums per step */
+static int run_digest(int argc, char **argv)
+{
+    if (argc < 12) { fprintf(stderr, "usage: digest nx ny lx ly level substeps dt umax steps out_prefix\n"); return 2; }
+    const int nx = atoi(argv[2]), ny = atoi(argv[3]);
+    const double lx = atof(argv[4]), ly = atof(argv[5]);
+    const int level = atoi(argv[6]), S = atoi(argv[7]);
+    const double dt = atof(argv[8]), umax = atof(argv[9]);
+    const int steps = atoi(argv[10]);
+    const std::string prefix = argv[11];
+    std::vector<Point2> verts;
+    std::vector<uint3> cells;
+    channel(nx, ny, lx, ly, true, verts, cells);
+    std::vector<int> off, idx;
+    one_ring((int)verts.size(), cells, off, idx);
+    const int N = (int)verts.size();
+    std::vector<double> fx(N), fy(N, 0.0);
+    for (int i = 0; i < N; ++i) fx[i] = 4.0 * umax * verts[i].y * (ly - verts[i].y) / (ly * ly);
+    Mesh2D mesh;
+    inject_mesh(mesh, verts, cells, off, idx);
+    NodalField F, W;
+    F.init(N, fx.data(), fy.data());
+    W.init(N, nullptr, nullptr);
+    fflush(stdout);
+    FILE *real_out = fdopen(dup(fileno(stdout)), "w");
+    if (!freopen("/dev/null", "w", stdout)) return 2;
+    ParticleHandler2D ph(&mesh, level);
+    ph.seedParticles();
+    ph.initParticleVelocity(F.ptrs);
+    checkCudaErrors(cudaDeviceSynchronize());
+    std::vector<Particle2D> hp;
+    auto bits = [](double v) { int64_t b; memcpy(&b, &v, 8); return (uint64_t)b; };
+    for (int s = 0; s <= steps; ++s) {
+        if (s > 0) {
+            ph.advectParticles(F.ptrs, dt, S);
+            ph.projectVelocityOntoGrid(W.ptrs);
+            ph.correctParticleVelocity(F.ptrs, W.ptrs);
+            checkCudaErrors(cudaDeviceSynchronize());
+        }
+        const int n = ph.getParticleCount();
+        hp.resize(n);
+        copy_d2h(ph.getParticles(), hp.data(), n);
+        checkCudaErrors(cudaDeviceSynchronize());
+        uint64_t cs[6] = {0, 0, 0, 0, 0, 0};
+        double vx = 0.0, vy = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const Particle2D &p = hp[i];
+            cs[0] += bits(p.getPosition().x);
+            cs[1] += bits(p.getPosition().y);
+            cs[2] += bits(p.getLocalPosition().x);
+            cs[3] += bits(p.getLocalPosition().y);
+            cs[4] += bits(p.getLocalPosition().z);
+            cs[5] += (uint64_t)p.getCellID();
+            vx += p.getVelocity().x;
+            vy += p.getVelocity().y;
+        }
+        fprintf(real_out, "{\"step\": %d, \"count\": %d, \"checksum\": [%lld, %lld, %lld, %lld, %lld, %lld], \"vsum\": [%.17g, %.17g]}\n", s, n,
+                (long long)cs[0], (long long)cs[1], (long long)cs[2], (long long)cs[3], (long long)cs[4], (long long)cs[5], vx, vy);
+        fflush(real_out);
+    }
+    std::vector<double> w(2 * (size_t)N);
+    copy_d2h(W.comp[0].data, w.data(), N);
+    copy_d2h(W.comp[1].data, w.data() + N, N);
+    checkCudaErrors(cudaDeviceSynchronize());
+    FILE *g = fopen((prefix + "_w.bin").c_str(), "wb");
+    if (!g) return 2;
+    wr(g, w.data(), w.size());
+    fclose(g);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc >= 12 && !strcmp(argv[1], "digest")) return run_digest(argc, argv);
     if (argc >= 4 && !strcmp(argv[1], "dump")) return run_dump(argv[2], argv[3]);
     if (argc >= 2 && !strcmp(argv[1], "time")) return run_time(argc, argv);
     if (argc >= 5 && !strcmp(argv[1], "timecase")) return run_timecase(argv[2], atoi(argv[3]), atoi(argv[4]));

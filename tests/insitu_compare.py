@@ -32,8 +32,13 @@ def parse_vtu(path):
     return out
 
 
-def main():
-    case = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1] in ("poiseuille", "cylinder") else "poiseuille"
+def binaries(case="poiseuille"):
+    exename = {"poiseuille": "Poiseuille", "cylinder": "Cylinder"}[case]
+    return [os.path.join(ROOT, "oracle", "_ref", f"{exename}_{tag}") for tag in ("ref", "shim")]
+
+
+def compare(case="poiseuille"):
+    """Run the unmodified case against the reference library and against the drop-in; -> summary dict."""
     fixture, datname, exename, suffix = {"poiseuille": ("mesh_channel.npz", "ChannelMesh.dat", "Poiseuille", ""),
                                          "cylinder": ("mesh_cylinder3.npz", "CylinderMesh3.dat", "Cylinder", "_cylinder")}[case]
     work = tempfile.mkdtemp(prefix="insitu_")
@@ -80,8 +85,8 @@ def main():
     with open(os.path.join(ROOT, "gpurun_out", f"insitu_counts{suffix}.txt"), "w") as f:
         for i in range(n):
             f.write(f"{i + 1} {counts['ref'][i]} {counts['shim'][i]}\n")
-    print(json.dumps(summary, indent=1))
+    return summary
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(compare(sys.argv[1] if len(sys.argv) > 1 and sys.argv[1] in ("poiseuille", "cylinder") else "poiseuille"), indent=1))

@@ -483,3 +483,20 @@ def test_repeated_projection_and_forced_correction_match_oracle(gpu, oracle, nam
     o.correct_particle_velocity(c.fx, c.fy, wx, wy)
     o.project_velocity_onto_grid(wx, wy)
     assert rel_inf(w2[0].cpu().numpy(), wx) <= REL_TOL and rel_inf(w2[1].cpu().numpy(), wy) <= REL_TOL
+
+
+def test_insitu_drop_in_of_the_unmodified_poiseuille_case():
+    """The UNMODIFIED cases/PoiseuilleFlow2D/main.cu, linked once against the reference library and once against the library
+    whose ParticleHandler2D is the B200 drop-in (gpupfem2_b200/shim, built by __graft_entry__.build() where /root/reference
+    exists; the binaries travel to the box under oracle/_ref/): the particle counts printed by advectParticles must be identical
+    in every one of the 500 coupled steps and the exported nodal fields must agree to the Krylov tolerance of the FEM stage."""
+    import insitu_compare
+
+    if not all(os.path.exists(b) for b in insitu_compare.binaries("poiseuille")):
+        pytest.skip("oracle/_ref/Poiseuille_{ref,shim} not built (needs /root/reference at build time)")
+    s = insitu_compare.compare("poiseuille")
+    assert s["ref"]["rc"] == 0 and s["shim"]["rc"] == 0, s
+    assert s["count_steps_compared"] >= 100 and s["count_identical_steps"] == s["count_steps_compared"], s
+    assert s["ref"]["created"] == s["shim"]["created"]
+    worst = max((v for d in s["field_rel_inf_diff"].values() if isinstance(d, dict) for v in d.values()), default=None)
+    assert worst is not None and worst <= 1e-4, s["field_rel_inf_diff"]

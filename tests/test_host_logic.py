@@ -133,3 +133,35 @@ def test_lazy_resort_index_model():
             permuted = False
             assert np.all(np.diff(cell[cur][:count]) >= 0)
             assert np.unique(tag[cur][:count]).shape[0] == count
+
+
+def test_partitioned_mesh_slices_find_the_global_interface_nodes():
+    """Mesh partition (multi_gpu.channel_slice_columns / the `cell_base` convention): every rank only holds its own quad
+    columns + the halo, in a numbering of its own.  The interface node lists it derives from the slice must be the global
+    ones (shifted by the slice's first node) in the same ascending order on both sides of every boundary, and the halo must
+    cover band x (substeps + 1) cells."""
+    import torch
+
+    from gpupfem2_b200 import multi_gpu
+    from gpupfem2_b200.mesh import structured_channel
+
+    nx, ny, world, S = 36, 5, 4, 3
+    m = structured_channel(nx, ny, 3.6, 0.5, colmajor=True)
+    cells = m.cells.astype(np.int64)
+    bounds = multi_gpu.strip_bounds(m.n_cells, world, align=2 * ny)
+    band = 2 * ny + 3  # vertex-sharing one-ring of the x-major channel (checked against the device value in the GPU tests)
+    assert multi_gpu.halo_cells(band, S) == band * (S + 1)
+    glob = {r: multi_gpu.interface_nodes(torch.as_tensor(cells), bounds, r) for r in range(world)}
+    for r in range(world):
+        c0, c1 = multi_gpu.channel_slice_columns(nx, ny, bounds, r, band, S)
+        lo, hi = 2 * ny * c0, 2 * ny * c1
+        assert lo <= max(0, bounds[r] - multi_gpu.halo_cells(band, S)) and hi >= min(m.n_cells, bounds[r + 1] + multi_gpu.halo_cells(band, S))
+        node_base = (ny + 1) * c0
+        local_cells = cells[lo:hi] - node_base
+        assert local_cells.min() == 0 and local_cells.max() == (ny + 1) * (c1 - c0 + 1) - 1  # exactly the slice's own nodes
+        local_bounds = np.clip(bounds.astype(np.int64) - lo, 0, hi - lo)
+        mine = multi_gpu.interface_nodes(torch.as_tensor(local_cells), local_bounds, r)
+        assert sorted(mine) == sorted(glob[r])
+        for nb, idx in mine.items():
+            assert abs(nb - r) == 1
+            assert torch.equal(idx + node_base, glob[r][nb])

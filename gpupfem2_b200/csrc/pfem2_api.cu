@@ -302,10 +302,12 @@ int materialize(pfem2_handle *h)
 // ------------------------------------------------------------------------------------------------
 // advectParticles, first half: S x (advect + locate) fused into one pass
 // ------------------------------------------------------------------------------------------------
-void launch_pack_nodal(pfem2_handle *h, int node_lo, int node_hi, NodalVel vel)
+// interleave the nodal velocity; begin = true: the launch also opens the advect (counters, emigrant counters, re-seed cursor)
+void launch_pack_nodal(pfem2_handle *h, int node_lo, int node_hi, NodalVel vel, bool begin)
 {
-    if (node_hi > node_lo)
-        PFEM2_LAUNCH(k_pack_nodal, grid_for(node_hi - node_lo, kThreads, 1 << 30), kThreads, 0, h->stream, node_lo, node_hi, vel, h->v2);
+    if (node_hi <= node_lo && !begin) return;
+    PFEM2_LAUNCH(k_pack_nodal, grid_for(std::max(node_hi - node_lo, 1), kThreads, 1 << 30), kThreads, 0, h->stream, node_lo, node_hi, vel, h->v2,
+                 begin ? h->ctr : (Counters *)nullptr, h->capacity, h->mg_rank_count, h->mg_fused ? h->mg_ranks + 1 : 0, h->tail_cursor);
 }
 
 // one launch of the move pass over the cells [c_lo, c_hi) of the segment table `cstart` (nullptr: everybody)
@@ -388,24 +390,20 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     h->partials_valid = false;
     h->last_substeps = substeps;
     const double hsub = dt / substeps; // particle_handler_2d.cu:330, host double
-    {   // per-cell scratch of the owned range (+ a few cells for the tolerance-band spill of the occupancy bits)
+    {   // per-cell scratch of the owned range (+ a few cells for the tolerance-band spill of the occupancy bits).  arrive[] is only
+        // written by the stable order (it stays zero otherwise) and cursor[] is initialised by k_init_cursor
         const size_t lo = (size_t)h->own_lo, len = (size_t)std::min(C, h->own_hi + 4) - lo + 1;
         CU(cudaMemsetAsync(h->stay + lo, 0, sizeof(int) * len, st));
-        CU(cudaMemsetAsync(h->arrive + lo, 0, sizeof(int) * len, st));
-        CU(cudaMemsetAsync(h->cursor + lo, 0, sizeof(int) * len, st));
+        if (!lazy || h->arrive_dirty) CU(cudaMemsetAsync(h->arrive + lo, 0, sizeof(int) * len, st));
+        h->arrive_dirty = !lazy; // (the physical paths count arrivals separately)
         CU(cudaMemsetAsync(h->cell_mask + lo, 0, sizeof(unsigned long long) * len, st));
     }
-    PFEM2_LAUNCH(k_begin_advect, 1, 1, 0, st, h->ctr, h->capacity);
     h->mg_fused = fused;
-    if (fused) {
-        do_count = 1;
-        CU(cudaMemsetAsync(h->mg_rank_count, 0, sizeof(int) * (h->mg_ranks + 1), st));
-    }
+    if (fused) do_count = 1;
     if (!h->v2) CU(cudaMalloc((void **)&h->v2, sizeof(double2) * (size_t)h->mesh.n_nodes));
     if ((rc = ensure_v2_node_range(h, substeps))) return rc;
     if (lazy) {
         if (!h->tail_cursor) CU(cudaMalloc((void **)&h->tail_cursor, sizeof(int)));
-        CU(cudaMemsetAsync(h->tail_cursor, 0, sizeof(int), st));
         if (!h->permuted) { // physically sorted (seed, upload, materialize): the identity permutation
             const int padded = (h->host_count + 31) & ~31;
             PFEM2_LAUNCH(k_iota, grid_for(padded), kThreads, 0, st, h->vals[h->perm_buf], h->ctr, padded);
@@ -418,7 +416,7 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     {
         PhaseScope ps(h, PFEM2_PHASE_ADVECT);
         if (!h->pipe.active) {
-            launch_pack_nodal(h, h->v2_node_lo, h->v2_node_hi, vel); // all nodes on a single GPU; a strip's reach otherwise
+            launch_pack_nodal(h, h->v2_node_lo, h->v2_node_hi, vel, true); // all nodes on a single GPU; a strip's reach otherwise
             const int grid = grid_for(h->capacity, kAdvThreads, g_num_sms * kAdvBlocksPerSM); // persistent: all resident blocks
             launch_move(h, lazy, hsub, substeps, do_count, grid, nullptr, 0, C);
         } else {
@@ -430,7 +428,7 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
             for (int j = 0; j < pp.K; ++j) {
                 for (; pp.packed_slices <= pp.up_slice[j]; ++pp.packed_slices) {
                     cudaStreamWaitEvent(st, pp.up_ev[pp.packed_slices], 0);
-                    launch_pack_nodal(h, pp.ns[pp.packed_slices], pp.ns[pp.packed_slices + 1], vel);
+                    launch_pack_nodal(h, pp.ns[pp.packed_slices], pp.ns[pp.packed_slices + 1], vel, pp.packed_slices == 0);
                 }
                 launch_move(h, lazy, hsub, substeps, do_count, grid, h->cell_start[h->cs], pp.cb[j], pp.cb[j + 1]);
             }
@@ -450,14 +448,18 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
 // advectParticles, second half: distribution check (plan) + re-sort by owning cell + re-seed
 // ------------------------------------------------------------------------------------------------
 // plan: packed[c] = survivors + missing of cell c; scan -> segment starts; count / overflow
-static void launch_plan(pfem2_handle *h, bool reseed)
+// with_cursor: the cursors of the counting sort / rank pass are initialised too (k_init_cursor, which then also closes the plan)
+static void launch_plan(pfem2_handle *h, bool reseed, bool with_cursor)
 {
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells, lo = h->own_lo, hi = h->own_hi, own_n = hi - lo; // cell-wise work only over the owned range
     PFEM2_LAUNCH(k_plan_cells, grid_for(own_n, kThreads, 1 << 30), kThreads, 0, st, C, lo, hi, h->ppc, reseed ? 1 : 0, h->stay, h->arrive,
                  h->cell_mask, h->packed, h->ctr);
     exclusive_scan_dev<unsigned long long>(h->packed + lo, h->packed + lo, h->own_len_dev, 1, 0, own_n, h->scan_scratch64, st);
-    PFEM2_LAUNCH(k_plan_finish, 1, 1, 0, st, hi, h->packed, h->ctr);
+    if (with_cursor)
+        PFEM2_LAUNCH(k_init_cursor, grid_for(std::max(own_n, 1), kThreads, 1 << 30), kThreads, 0, st, lo, hi, h->packed, h->cursor, h->ctr);
+    else
+        PFEM2_LAUNCH(k_plan_finish, 1, 1, 0, st, hi, h->packed, h->ctr);
 }
 
 // Physical re-sort into the other buffer.  stable: stayers keep their relative order, the movers listed in keys[0]/vals[0]
@@ -475,7 +477,7 @@ static int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable,
     }
     PhaseScope ps(h, PFEM2_PHASE_REORDER);
     const int lo = h->own_lo, hi = h->own_hi, own_n = hi - lo;
-    launch_plan(h, reseed);
+    launch_plan(h, reseed, !stable);
     ParticleSoA src = h->soa[h->cur], dst = h->soa[h->cur ^ 1];
     if (stable) {
         if (have_stayers)
@@ -484,7 +486,6 @@ static int reorder(pfem2_handle *h, bool reseed, bool have_stayers, bool stable,
         PFEM2_LAUNCH(k_scatter_movers, grid_for(h->capacity), kThreads, 0, st, src, dst, C, &h->ctr->n_movers, h->keys[flip],
                      h->vals[flip], h->stay, h->packed, h->ctr);
     } else {
-        PFEM2_LAUNCH(k_init_cursor, grid_for(own_n, kThreads, 1 << 30), kThreads, 0, st, lo, hi, h->packed, h->cursor);
         // 12 eight-record groups in flight per warp, 2 blocks per SM (measured on channel16m: U x blocks = 8x3 6.40 ms,
         // 12x2 6.16, 16x2 6.40, 20x2 7.4, 24x1 7.3, 8x4 6.7, 4x6 6.7 for the whole reorder phase)
         PFEM2_LAUNCH((k_scatter_all_quads<12, 2>), grid_for(h->capacity), kThreads, 0, st, src, dst, &h->ctr->n_old, h->cursor, h->ctr);
@@ -504,8 +505,7 @@ static int rank_and_reseed(pfem2_handle *h, NodalVel vel)
     cudaStream_t st = h->stream;
     PhaseScope ps(h, PFEM2_PHASE_REORDER);
     const int lo = h->own_lo, hi = h->own_hi, own_n = hi - lo;
-    launch_plan(h, true);
-    PFEM2_LAUNCH(k_init_cursor, grid_for(own_n, kThreads, 1 << 30), kThreads, 0, st, lo, hi, h->packed, h->cursor);
+    launch_plan(h, true, true);
     unsigned *src_new = h->vals[h->perm_buf ^ 1];
     PFEM2_LAUNCH(k_rank, grid_for(h->capacity), kThreads, 0, st, (const unsigned *)h->keys[1], (const int *)&h->ctr->n_old, h->cursor, src_new,
                  h->ctr);
@@ -1073,6 +1073,7 @@ int pfem2_upload(pfem2_handle *h, int n, const double *x, const double *y, const
     }
     // commit: the uploaded state replaces everything, including a correction not yet applied and a permutation of the replaced state
     h->partials_valid = false;
+    h->arrive_dirty = true;
     h->dv_pending = false;
     h->permuted = false;
     cudaStream_t st = h->stream;

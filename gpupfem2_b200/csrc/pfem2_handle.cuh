@@ -79,7 +79,8 @@ struct pfem2_handle {
     unsigned *stay_bits = nullptr;           // capacity / 32 + 2: ballot of particles that stayed in their cell (stable order)
     int *warp_movers = nullptr;              // capacity / 32 + 2: movers per warp, scanned in place (stable order)
     int *warp_scan_scratch = nullptr;
-    int *stay = nullptr, *arrive = nullptr, *cursor = nullptr; // n_cells + 1 each (one allocation, zeroed together)
+    int *stay = nullptr, *arrive = nullptr, *cursor = nullptr; // n_cells + 1 each (one allocation)
+    bool arrive_dirty = false;               // arrive[] may hold counts of a physical re-sort (the lazy path needs it zero and never writes it)
     unsigned long long *cell_mask = nullptr; // n_cells + 1
     unsigned long long *packed = nullptr;    // n_cells + 2 (scan in place)
     unsigned long long *scan_scratch64 = nullptr;
@@ -130,7 +131,8 @@ struct pfem2_handle {
         void *peer[2] = {nullptr, nullptr};     // theirs: the inbox neighbour `side` keeps for me (IPC mapping)
         int *idx[2] = {nullptr, nullptr};       // interface node ids shared with neighbour `side` (ascending), device
         int n_idx[2] = {0, 0};
-        int *cursors = nullptr;                 // device: [0], [1] pack cursors per side, [2] records handed over by the last send
+        int *cursors = nullptr;                 // device: [0], [1] pack cursors per side, [2] records handed over by the last send,
+                                                // [3] block counter of the fused kernels ("last block done")
         unsigned mig_seq = 0, halo_seq = 0;     // deliveries made so far (block parity = seq & 1)
     } p2p;
 
@@ -221,7 +223,7 @@ int advect_finish(pfem2_handle *h, NodalVel vel, int need_count);
 void launch_project_cells(pfem2_handle *h, int c_lo = -1, int c_hi = -1);
 void launch_project_nodes(pfem2_handle *h, int node_lo, int node_hi, double *vx, double *vy, double *const *table, double *cx, double *cy,
                           double *const *table_copy);
-void launch_pack_nodal(pfem2_handle *h, int node_lo, int node_hi, NodalVel vel);
+void launch_pack_nodal(pfem2_handle *h, int node_lo, int node_hi, NodalVel vel, bool begin);
 int node_range_of_cells(pfem2_handle *h, int cell_lo, int cell_hi, int &lo, int &hi);
 
 } // namespace host

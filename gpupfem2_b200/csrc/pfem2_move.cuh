@@ -497,8 +497,22 @@ static __global__ void __launch_bounds__(kThreads) k_iota(unsigned *__restrict__
 }
 
 // nodal velocity, interleaved for the advect pass: V2[n] = (Vx[n], Vy[n])
-static __global__ void __launch_bounds__(kThreads) k_pack_nodal(int node_lo, int node_hi, NodalVel vel, double2 *__restrict__ V2)
+// begin_ctr != nullptr: thread 0 also opens the advect (the former one-thread kernel k_begin_advect: counters of the pass, the
+// emigrant counters and the re-seed cursor reset) -- one launch less per step
+static __global__ void __launch_bounds__(kThreads)
+k_pack_nodal(int node_lo, int node_hi, NodalVel vel, double2 *__restrict__ V2, Counters *begin_ctr, int capacity, int *rank_count,
+             int n_rank_count, int *tail_cursor)
 {
+    if (begin_ctr && blockIdx.x == 0 && threadIdx.x == 0) {
+        begin_ctr->lost = 0;
+        begin_ctr->movers = 0;
+        begin_ctr->added = 0;
+        begin_ctr->capacity = capacity;
+        begin_ctr->n_old = begin_ctr->count;
+        begin_ctr->n_warps = (begin_ctr->count + 31) >> 5;
+        for (int k = 0; k < n_rank_count; ++k) rank_count[k] = 0;
+        if (tail_cursor) *tail_cursor = 0;
+    }
     const double *Vx, *Vy;
     vel.resolve(Vx, Vy);
     const int i = node_lo + blockIdx.x * blockDim.x + threadIdx.x;

@@ -272,11 +272,10 @@ int pfem2_emigrants_send_p2p(pfem2_handle *h, int rank)
     unsigned char *pl = (unsigned char *)h->p2p.peer[0], *pr = (unsigned char *)h->p2p.peer[1];
     MigrationHeader *hl = pl ? (MigrationHeader *)(pl + p2p_block_offset(cap, parity)) : nullptr;
     MigrationHeader *hr = pr ? (MigrationHeader *)(pr + p2p_block_offset(cap, parity)) : nullptr;
-    PFEM2_LAUNCH(k_emigrant_pack_p2p, grid_for(cap, kThreads, g_num_sms * 2), kThreads, 0, st, h->soa[h->cur], h->keys[0], h->mg_rank_count,
-                 h->mg_ranks, h->mg_bounds, rank, hl ? (int4 *)(hl + 1) : nullptr, hr ? (int4 *)(hr + 1) : nullptr, cap, h->ctr,
-                 h->p2p.cursors, h->cell_base);
-    PFEM2_LAUNCH(k_p2p_publish_migration, 1, 1, 0, st, hl, pl ? &((P2PInboxHead *)pl)->flag_mig : nullptr, hr,
-                 pr ? &((P2PInboxHead *)pr)->flag_mig : nullptr, h->p2p.cursors, cap, h->cell_mask, h->own_hi, h->mesh.n_cells, seq);
+    // pack + publish in one launch: the block that finishes last writes the headers, fences (system scope) and releases the flags
+    PFEM2_LAUNCH(k_p2p_send, grid_for(cap, kThreads, g_num_sms * 2), kThreads, 0, st, h->soa[h->cur], h->keys[0], h->mg_rank_count, h->mg_ranks,
+                 h->mg_bounds, rank, hl, pl ? &((P2PInboxHead *)pl)->flag_mig : nullptr, hr, pr ? &((P2PInboxHead *)pr)->flag_mig : nullptr, cap,
+                 h->ctr, h->p2p.cursors, h->cell_base, h->cell_mask, h->own_hi, h->mesh.n_cells, seq, (unsigned *)(h->p2p.cursors + 3));
     h->mg_fused_total = -1; // consumed
     CU(cudaGetLastError());
     return PFEM2_OK;
@@ -296,11 +295,16 @@ int pfem2_immigrants_recv_p2p(pfem2_handle *h)
     unsigned char *il = h->p2p.peer[0] ? (unsigned char *)h->p2p.inbox[0] : nullptr; // a neighbour delivers only if it is connected
     unsigned char *ir = h->p2p.peer[1] ? (unsigned char *)h->p2p.inbox[1] : nullptr;
     if (!il && !ir) return PFEM2_OK;
-    PFEM2_LAUNCH(k_p2p_wait, 1, 1, 0, st, il ? &((const P2PInboxHead *)il)->flag_mig : nullptr,
-                 ir ? &((const P2PInboxHead *)ir)->flag_mig : nullptr, seq, h->ctr, p2p_timeout_ns());
-    int rc;
-    if (il && (rc = append_migration_block(h, (const int4 *)(il + p2p_block_offset(cap, parity)), cap, 1))) return rc;
-    if (ir && (rc = append_migration_block(h, (const int4 *)(ir + p2p_block_offset(cap, parity)), cap, 0))) return rc;
+    // wait + append both blocks + their per-cell statistics + the new count in one launch.  Lazy re-sort: the rows go behind the
+    // dense output of the move pass, they also get their entry in the dense key array of the rank pass, and everybody is summed
+    // into stay[] (the fast order keeps no separate arrival counts)
+    PFEM2_LAUNCH(k_p2p_receive, grid_for(cap, kThreads, g_num_sms * 2), kThreads, 0, st, h->soa[h->cur], h->ctr,
+                 il ? &((const P2PInboxHead *)il)->flag_mig : nullptr, ir ? &((const P2PInboxHead *)ir)->flag_mig : nullptr, seq, p2p_timeout_ns(),
+                 il ? (const int4 *)(il + p2p_block_offset(cap, parity)) : nullptr, ir ? (const int4 *)(ir + p2p_block_offset(cap, parity)) : nullptr,
+                 cap, h->lazy_move ? h->keys[1] : (unsigned *)nullptr, h->cell_base, h->opt.subcell_mode ? 1 : 0, h->mesh.n_cells, h->ppc, h->level,
+                 h->sub_step, h->stay, h->lazy_move ? (int *)nullptr : h->arrive, h->cell_mask, h->own_lo, h->own_hi,
+                 (unsigned *)(h->p2p.cursors + 3));
+    CU(cudaGetLastError());
     return PFEM2_OK;
 }
 
@@ -313,26 +317,22 @@ int pfem2_project_halo_p2p(pfem2_handle *h, double *d_acc3)
     if (!h->p2p.peer[0] && !h->p2p.peer[1]) return PFEM2_OK;
     const unsigned seq = ++h->p2p.halo_seq;
     const int parity = (int)(seq & 1u);
-    unsigned *flags[2] = {nullptr, nullptr};
-    for (int k = 0; k < 2; ++k) {
-        if (!h->p2p.peer[k]) continue;
-        unsigned char *peer = (unsigned char *)h->p2p.peer[k];
-        const int n = h->p2p.n_idx[k];
-        if (n)
-            PFEM2_LAUNCH(k_halo_send, grid_for(n, kThreads, 1 << 30), kThreads, 0, st, d_acc3, h->p2p.idx[k], n,
-                         (double *)(peer + p2p_halo_offset(cap, n, parity)));
-        flags[k] = &((P2PInboxHead *)peer)->flag_halo;
-    }
-    PFEM2_LAUNCH(k_p2p_publish_flag, 1, 1, 0, st, flags[0], flags[1], seq);
-    PFEM2_LAUNCH(k_p2p_wait, 1, 1, 0, st, h->p2p.peer[0] ? &((const P2PInboxHead *)h->p2p.inbox[0])->flag_halo : nullptr,
-                 h->p2p.peer[1] ? &((const P2PInboxHead *)h->p2p.inbox[1])->flag_halo : nullptr, seq, h->ctr, p2p_timeout_ns());
-    for (int k = 0; k < 2; ++k) {
-        if (!h->p2p.peer[k]) continue;
-        const int n = h->p2p.n_idx[k];
-        if (n)
-            PFEM2_LAUNCH(k_halo_add, grid_for(n, kThreads, 1 << 30), kThreads, 0, st, d_acc3, h->p2p.idx[k], n,
-                         (const double *)((unsigned char *)h->p2p.inbox[k] + p2p_halo_offset(cap, n, parity)));
-    }
+    // two launches: store my interface sums into both neighbours' halo blocks + release the flags (last block);
+    // wait for theirs + add (two contributions per shared node: a + b == b + a bit for bit)
+    unsigned char *peer[2] = {(unsigned char *)h->p2p.peer[0], (unsigned char *)h->p2p.peer[1]};
+    unsigned char *inbox[2] = {(unsigned char *)h->p2p.inbox[0], (unsigned char *)h->p2p.inbox[1]};
+    const int n[2] = {peer[0] ? h->p2p.n_idx[0] : 0, peer[1] ? h->p2p.n_idx[1] : 0};
+    const int total = std::max(n[0] + n[1], 1);
+    PFEM2_LAUNCH(k_halo_send2, grid_for(total, kThreads, 1 << 30), kThreads, 0, st, d_acc3, h->p2p.idx[0], n[0],
+                 peer[0] ? (double *)(peer[0] + p2p_halo_offset(cap, h->p2p.n_idx[0], parity)) : nullptr,
+                 peer[0] ? &((P2PInboxHead *)peer[0])->flag_halo : nullptr, h->p2p.idx[1], n[1],
+                 peer[1] ? (double *)(peer[1] + p2p_halo_offset(cap, h->p2p.n_idx[1], parity)) : nullptr,
+                 peer[1] ? &((P2PInboxHead *)peer[1])->flag_halo : nullptr, seq, (unsigned *)(h->p2p.cursors + 3));
+    PFEM2_LAUNCH(k_halo_recv2, grid_for(total, kThreads, 1 << 30), kThreads, 0, st, d_acc3,
+                 peer[0] ? &((const P2PInboxHead *)inbox[0])->flag_halo : nullptr, peer[1] ? &((const P2PInboxHead *)inbox[1])->flag_halo : nullptr,
+                 seq, h->ctr, p2p_timeout_ns(), h->p2p.idx[0], n[0],
+                 peer[0] ? (const double *)(inbox[0] + p2p_halo_offset(cap, h->p2p.n_idx[0], parity)) : nullptr, h->p2p.idx[1], n[1],
+                 peer[1] ? (const double *)(inbox[1] + p2p_halo_offset(cap, h->p2p.n_idx[1], parity)) : nullptr);
     CU(cudaGetLastError());
     return PFEM2_OK;
 }

@@ -413,6 +413,211 @@ static __global__ void k_p2p_init_head(P2PInboxHead *hd, int cap, int n_nodes)
     hd->n_halo_nodes = n_nodes;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused forms of the P2P step (round 2: 30 -> 17 launches per strip and step; at 8 GPUs a step is ~2 ms and every launch +
+// drain costs ~5 us).  "Last block" pattern: every block counts in on a device word after a __threadfence(); the block that
+// finds the count complete does the one-thread epilogue (headers, flags, counters) and resets the word.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool last_block_done(unsigned *done)
+{
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(done, 1u);
+        s_last = prev == gridDim.x - 1;
+        if (s_last) *done = 0u;
+    }
+    __syncthreads();
+    return s_last;
+}
+
+// k_emigrant_pack_p2p + k_p2p_publish_migration
+static __global__ void __launch_bounds__(kThreads)
+k_p2p_send(ParticleSoA p, const unsigned *__restrict__ emig_idx, const int *__restrict__ rank_count, int n_ranks,
+           const int *__restrict__ bounds, int rank, MigrationHeader *hdr_left, unsigned *flag_left, MigrationHeader *hdr_right,
+           unsigned *flag_right, int cap, Counters *ctr, int *cursors, int cell_base, const unsigned long long *__restrict__ cell_mask,
+           int own_hi, int n_cells, unsigned seq, unsigned *done)
+{
+    int4 *rec_left = hdr_left ? reinterpret_cast<int4 *>(hdr_left + 1) : nullptr;
+    int4 *rec_right = hdr_right ? reinterpret_cast<int4 *>(hdr_right + 1) : nullptr;
+    const int n_emig = rank_count[n_ranks];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_emig; j += gridDim.x * blockDim.x) {
+        const unsigned i = emig_idx[j];
+        int4 t = *reinterpret_cast<const int4 *>(p.tail + i);
+        const int dest = rank_of_cell((unsigned)t.z, bounds, n_ranks);
+        t.z += cell_base; // records between strips carry GLOBAL cell ids
+        const int side = dest == rank - 1 ? 0 : (dest == rank + 1 ? 1 : -1);
+        int4 *out = side == 0 ? rec_left : (side == 1 ? rec_right : nullptr);
+        st_cell(p.tail + i, kLostCell);
+        if (!out) {
+            atomicOr(&ctr->overflow, kOverflowMigration);
+            continue;
+        }
+        const int slot = atomicAdd(cursors + side, 1);
+        if (slot >= cap) {
+            atomicOr(&ctr->overflow, kOverflowMigration);
+            continue;
+        }
+        int4 *rec = out + 4 * (size_t)slot;
+        rec[0] = *reinterpret_cast<const int4 *>(p.pos + i);
+        rec[1] = *reinterpret_cast<const int4 *>(p.lab + i);
+        rec[2] = t;
+        rec[3] = *reinterpret_cast<const int4 *>(p.vel + i);
+    }
+    __threadfence_system(); // this block's peer stores are performed before it counts in
+    if (!last_block_done(done)) return;
+    if (threadIdx.x == 0) {
+        if (hdr_left) {
+            const int n = cursors[0];
+            hdr_left->count = n;
+            hdr_left->flags = n > cap ? 1 : 0;
+            for (int k = 0; k < 4; ++k) hdr_left->spill[k] = 0ull;
+        }
+        if (hdr_right) {
+            const int n = cursors[1];
+            hdr_right->count = n;
+            hdr_right->flags = n > cap ? 1 : 0;
+            for (int k = 0; k < 4; ++k) hdr_right->spill[k] = own_hi + k < n_cells ? cell_mask[own_hi + k] : 0ull;
+        }
+        cursors[2] = cursors[0] + cursors[1]; // what this strip handed over (read back on demand)
+        cursors[0] = cursors[1] = 0;
+        __threadfence_system();
+        if (flag_left) st_release_sys(flag_left, seq);
+        if (flag_right) st_release_sys(flag_right, seq);
+    }
+}
+
+// every block: wait until both neighbours have delivered sequence number `seq` (thread 0 spins, watchdog); false = timed out
+__device__ __forceinline__ bool p2p_block_wait(const unsigned *flag_a, const unsigned *flag_b, unsigned seq, Counters *ctr,
+                                               unsigned long long timeout_ns)
+{
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        const unsigned long long t0 = global_timer_ns();
+        const unsigned *flags[2] = {flag_a, flag_b};
+        for (int k = 0; k < 2 && ok; ++k) {
+            if (!flags[k]) continue;
+            while ((int)(ld_acquire_sys(flags[k]) - seq) < 0) {
+                if (global_timer_ns() - t0 > timeout_ns) {
+                    atomicOr(&ctr->overflow, kOverflowP2PTimeout);
+                    ok = 0;
+                    break;
+                }
+                __nanosleep(200);
+            }
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
+// k_p2p_wait + (k_immigrant_append_dev + k_count_appended_dev + k_add_count_dev) x 2: the immigrants of both inbox blocks are
+// appended behind the array (left block first), counted into the per-cell statistics, and the last block grows the array
+static __global__ void __launch_bounds__(kThreads)
+k_p2p_receive(ParticleSoA p, Counters *ctr, const unsigned *flag_l, const unsigned *flag_r, unsigned seq, unsigned long long timeout_ns,
+              const int4 *__restrict__ buf_l, const int4 *__restrict__ buf_r, int cap, unsigned *__restrict__ keys, int cell_base,
+              int subcell_mode, int n_cells, int ppc, int level, double sub_step, int *__restrict__ stay, int *__restrict__ arrive,
+              unsigned long long *__restrict__ cell_mask, int own_lo, int own_hi, unsigned *done)
+{
+    if (!p2p_block_wait(flag_l, flag_r, seq, ctr, timeout_ns)) return;
+    const int ml = buf_l ? migration_count(buf_l, cap) : 0, mr = buf_r ? migration_count(buf_r, cap) : 0;
+    const int m = ml + mr, n0 = ctr->count;
+    const bool fits = (long long)n0 + m <= ctr->capacity;
+    const int lane = threadIdx.x & 31;
+    if (fits) {
+        for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < m; base += gridDim.x * blockDim.x) {
+            const int j = base + lane;
+            bool live = false;
+            unsigned c = 0;
+            double L0 = 0, L1 = 0, L2 = 0;
+            if (j < m) {
+                const int4 *rec = j < ml ? buf_l + 4 * ((size_t)j + 1) : buf_r + 4 * ((size_t)(j - ml) + 1);
+                const int4 a = rec[0], b = rec[1], v = rec[3];
+                int4 t = rec[2];
+                t.z -= cell_base; // global -> this strip's numbering
+                *reinterpret_cast<int4 *>(p.pos + (n0 + j)) = a;
+                *reinterpret_cast<int4 *>(p.lab + (n0 + j)) = b;
+                *reinterpret_cast<int4 *>(p.tail + (n0 + j)) = t;
+                *reinterpret_cast<int4 *>(p.vel + (n0 + j)) = v;
+                if (keys) keys[n0 + j] = (unsigned)t.z; // lazy re-sort: dense key array of the rank pass
+                c = (unsigned)t.z;
+                live = c != kLostCell;
+                L0 = __hiloint2double(b.y, b.x);
+                L1 = __hiloint2double(b.w, b.z);
+                L2 = __hiloint2double(t.y, t.x);
+            }
+            const unsigned mb = __ballot_sync(0xffffffffu, live);
+            accumulate_cell_stats(subcell_mode, live, c, L0, L1, L2, 0u, mb, lane, n_cells, ppc, level, sub_step, stay, arrive, cell_mask);
+        }
+    }
+    if (!last_block_done(done)) return;
+    if (threadIdx.x == 0) {
+        int add = m;
+        for (int k = 0; k < 2; ++k) {
+            const MigrationHeader *hd = reinterpret_cast<const MigrationHeader *>(k ? buf_r : buf_l);
+            if (hd && (hd->count > cap || hd->count < 0 || hd->flags)) ctr->overflow |= kOverflowMigration;
+        }
+        if (!fits) {
+            ctr->overflow |= 1;
+            add = 0;
+        }
+        ctr->count += add;
+        ctr->n_old = ctr->count;
+        ctr->n_warps = (ctr->count + 31) >> 5;
+        if (buf_l) { // the left neighbour's spilled occupancy bits join this strip's first cells
+            const MigrationHeader *hd = reinterpret_cast<const MigrationHeader *>(buf_l);
+            for (int k = 0; k < 4; ++k)
+                if (own_lo + k < own_hi && hd->spill[k]) cell_mask[own_lo + k] |= hd->spill[k];
+        }
+    }
+}
+
+// projection halo, both sides in one launch: k_halo_send x 2 + k_p2p_publish_flag
+static __global__ void __launch_bounds__(kThreads)
+k_halo_send2(const double *__restrict__ acc3, const int *__restrict__ idx_l, int n_l, double *peer_l, unsigned *flag_l,
+             const int *__restrict__ idx_r, int n_r, double *peer_r, unsigned *flag_r, unsigned seq, unsigned *done)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_l + n_r) {
+        const bool left = i < n_l;
+        const int k = left ? i : i - n_l;
+        const double *a = acc3 + 3 * (size_t)(left ? idx_l[k] : idx_r[k]);
+        double *o = (left ? peer_l : peer_r) + 3 * (size_t)k;
+        o[0] = a[0];
+        o[1] = a[1];
+        o[2] = a[2];
+    }
+    __threadfence_system();
+    if (!last_block_done(done)) return;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (flag_l) st_release_sys(flag_l, seq);
+        if (flag_r) st_release_sys(flag_r, seq);
+    }
+}
+
+// k_p2p_wait + k_halo_add x 2
+static __global__ void __launch_bounds__(kThreads)
+k_halo_recv2(double *__restrict__ acc3, const unsigned *flag_l, const unsigned *flag_r, unsigned seq, Counters *ctr,
+             unsigned long long timeout_ns, const int *__restrict__ idx_l, int n_l, const double *__restrict__ halo_l,
+             const int *__restrict__ idx_r, int n_r, const double *__restrict__ halo_r)
+{
+    if (!p2p_block_wait(flag_l, flag_r, seq, ctr, timeout_ns)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_l + n_r) return;
+    const bool left = i < n_l;
+    const int k = left ? i : i - n_l;
+    double *a = acc3 + 3 * (size_t)(left ? idx_l[k] : idx_r[k]);
+    const double *hsrc = (left ? halo_l : halo_r) + 3 * (size_t)k;
+    a[0] = __dadd_rn(a[0], hsrc[0]);
+    a[1] = __dadd_rn(a[1], hsrc[1]);
+    a[2] = __dadd_rn(a[2], hsrc[2]);
+}
+
 // projection, multi-GPU flavour: per-node accumulators {sum L v_x, sum L v_y, sum L} without the division, so that the
 // contributions of the strips sharing an interface node can be added before kFinalizeVelocityProjection's division
 static __global__ void __launch_bounds__(kThreads)

@@ -79,7 +79,7 @@ static __global__ void k_plan_finish(int own_hi, const unsigned long long *__res
     const long long total = (long long)(unsigned)(t & 0xffffffffull);
     ctr->live = (int)total - ctr->added;
     if (total > ctr->capacity) {
-        ctr->overflow = 1;
+        ctr->overflow |= 1; // (other bits: migration / P2P watchdog)
         ctr->count = 0; // nothing valid to iterate over; the host reports PFEM2_ECAPACITY
     } else {
         ctr->count = (int)total;
@@ -173,10 +173,21 @@ k_scatter_all_quads(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_
     }
 }
 
-// cursor[c] = new segment start of cell c (low half of the scanned plan word), for the fast scatter
+// cursor[c] = new segment start of cell c (low half of the scanned plan word), for the fast scatter / the rank pass.
+// finish_ctr != nullptr: thread 0 also closes the plan (k_plan_finish: live count, new count, overflow flag)
 static __global__ void __launch_bounds__(kThreads)
-k_init_cursor(int own_lo, int own_hi, const unsigned long long *__restrict__ packed_start, int *__restrict__ cursor)
+k_init_cursor(int own_lo, int own_hi, const unsigned long long *__restrict__ packed_start, int *__restrict__ cursor, Counters *finish_ctr)
 {
+    if (finish_ctr && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long total = (long long)(unsigned)(packed_start[own_hi] & 0xffffffffull);
+        finish_ctr->live = (int)total - finish_ctr->added;
+        if (total > finish_ctr->capacity) {
+            finish_ctr->overflow |= 1;
+            finish_ctr->count = 0; // nothing valid to iterate over; the host reports PFEM2_ECAPACITY
+        } else {
+            finish_ctr->count = (int)total;
+        }
+    }
     const int c = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (c < own_hi) cursor[c] = (int)(unsigned)(packed_start[c] & 0xffffffffull);
 }

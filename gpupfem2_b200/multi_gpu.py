@@ -224,6 +224,8 @@ class DistributedParticleHandler2D:
         ok, handles = True, {}
         if any(abs(r - rank) != 1 for r in self.iface):
             ok = False  # not a strip partition: nodes shared with a non-adjacent rank
+        if len(self.iface) == 2 and bool(torch.isin(self.iface[rank - 1], self.iface[rank + 1]).any()):
+            ok = False  # a strip so thin that one node touches both neighbours: the fused halo kernel adds each side independently
         if ok:
             for side, nb in ((0, rank - 1), (1, rank + 1)):
                 if not 0 <= nb < world:

@@ -404,8 +404,9 @@ def measure(args, rank, world, local, full):
             hb = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=device)
             dist.all_reduce(hb)
             h2d, d2h = int(hb[0]), int(hb[1])
-            api = ("DistributedParticleHandler2D.step_host: every rank uploads the slice of the pinned host nodal field its strip's advect "
-                   "reads, runs advect / migrate / project / halo / correct through the C ABI, downloads the projected slice it owns")
+            api = ("pfem2_step_host_p2p (C ABI, one call per rank and step): the slice of the pinned host nodal field the strip's advect reads is "
+                   "uploaded in chunks under the move pass, migration and halo sums over NVLink peer memory, the projected slice the strip "
+                   "owns is downloaded under the projection (interface nodes after the halo sum)")
         else:
             step_host = lambda: h.step_host(hF[0], hF[1], hW[0], hW[1], dt, args.substeps)  # noqa: E731
             h2d, d2h = 2 * dm.n_nodes * 8, 2 * dm.n_nodes * 8 + 32

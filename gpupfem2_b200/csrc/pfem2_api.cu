@@ -200,7 +200,7 @@ int node_range_of_cells(pfem2_handle *h, int cell_lo, int cell_hi, int &lo, int 
 
 // Multi-GPU: the nodal arrays the move pass gathers from (interleaved velocity v2) only need the nodes of the cells a particle
 // of the owned range can reach in one call: its cell index changes by at most the band width of the one-ring lists per substep.
-static int ensure_v2_node_range(pfem2_handle *h, int substeps)
+int ensure_v2_node_range(pfem2_handle *h, int substeps)
 {
     const int C = h->mesh.n_cells;
     if (h->own_lo == 0 && h->own_hi == C) {
@@ -605,6 +605,20 @@ void launch_project_nodes(pfem2_handle *h, int node_lo, int node_hi, double *vx,
                      (const int *)h->node_inc, h->partial, vx, vy, table, cx, cy, table_copy);
 }
 
+void launch_project_nodes_acc_range(pfem2_handle *h, int node_lo, int node_hi, double *acc3)
+{
+    if (node_hi > node_lo)
+        PFEM2_LAUNCH(k_project_nodes_acc_range, grid_for(node_hi - node_lo, kThreads, 1 << 30), kThreads, 0, h->stream, node_lo, node_hi, h->own_lo,
+                     h->own_hi, h->node_off, (const int *)h->node_inc, h->partial, acc3);
+}
+
+void launch_project_finalize_range(pfem2_handle *h, int node_lo, int node_hi, const double *acc3, double *vx, double *vy)
+{
+    if (node_hi > node_lo)
+        PFEM2_LAUNCH(k_project_finalize_range, grid_for(node_hi - node_lo, kThreads, 1 << 30), kThreads, 0, h->stream, node_lo, node_hi, h->own_lo,
+                     h->own_hi, h->node_off, (const int *)h->node_inc, acc3, vx, vy);
+}
+
 static int do_project(pfem2_handle *h, double *vx, double *vy, double *const *table, double *cx = nullptr, double *cy = nullptr,
                       double *const *table_copy = nullptr)
 {
@@ -896,6 +910,7 @@ int pfem2_destroy(pfem2_handle *h)
     for (cudaEvent_t e : h->pipe.up_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->pipe.dn_ev) cudaEventDestroy(e);
     for (double *p : h->nodal) cudaFree(p);
+    cudaFree(h->acc3);
     for (auto &r : h->phase_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     if (h->host_ctr) cudaFreeHost(h->host_ctr);

@@ -98,6 +98,7 @@ struct pfem2_handle {
     void *aos = nullptr;
     size_t aos_bytes = 0;
     double *nodal[4] = {nullptr, nullptr, nullptr, nullptr}; // F.x F.y W.x W.y for pfem2_step_host
+    double *acc3 = nullptr;                                  // 3 * n_nodes node accumulators of pfem2_step_host_p2p
 
     // multi-GPU (strip partition)
     int cell_base = 0;            // the mesh view is the slice [cell_base, cell_base + n_cells) of the global cell numbering (partitioned mesh)
@@ -131,6 +132,7 @@ struct pfem2_handle {
         void *peer[2] = {nullptr, nullptr};     // theirs: the inbox neighbour `side` keeps for me (IPC mapping)
         int *idx[2] = {nullptr, nullptr};       // interface node ids shared with neighbour `side` (ascending), device
         int n_idx[2] = {0, 0};
+        int idx_lo[2] = {0, 0}, idx_hi[2] = {0, 0}; // node id range [lo, hi) of the interface with neighbour `side`
         int *cursors = nullptr;                 // device: [0], [1] pack cursors per side, [2] records handed over by the last send,
                                                 // [3] block counter of the fused kernels ("last block done")
         unsigned mig_seq = 0, halo_seq = 0;     // deliveries made so far (block parity = seq & 1)
@@ -224,6 +226,9 @@ void launch_project_cells(pfem2_handle *h, int c_lo = -1, int c_hi = -1);
 void launch_project_nodes(pfem2_handle *h, int node_lo, int node_hi, double *vx, double *vy, double *const *table, double *cx, double *cy,
                           double *const *table_copy);
 void launch_pack_nodal(pfem2_handle *h, int node_lo, int node_hi, NodalVel vel, bool begin);
+void launch_project_nodes_acc_range(pfem2_handle *h, int node_lo, int node_hi, double *acc3);
+void launch_project_finalize_range(pfem2_handle *h, int node_lo, int node_hi, const double *acc3, double *vx, double *vy);
+int ensure_v2_node_range(pfem2_handle *h, int substeps);
 int node_range_of_cells(pfem2_handle *h, int cell_lo, int cell_hi, int &lo, int &hi);
 
 } // namespace host

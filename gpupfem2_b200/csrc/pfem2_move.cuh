@@ -413,7 +413,7 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
     int n = ctr->count, p_lo = 0;
     if (chunk_start) {
         p_lo = min(__ldg(chunk_start + chunk_lo), n) & ~31;
-        if (chunk_hi < n_cells) n = min(__ldg(chunk_start + chunk_hi), n) & ~31;
+        if (chunk_hi < own_hi) n = min(__ldg(chunk_start + chunk_hi), n) & ~31; // (the last chunk of the owned range ends at the count)
     }
     const int first = p_lo + ((blockIdx.x * warps_per_block + warp) << 5);
     const int stride = (int)gridDim.x * (warps_per_block * 32);

@@ -226,6 +226,11 @@ int pfem2_p2p_inbox_create(pfem2_handle *h, int side, int capacity_records, int 
     CU(cudaStreamSynchronize(st)); // the head is initialised before anybody can map the inbox; the host index list may go away
     h->p2p.cap = capacity_records;
     h->p2p.n_idx[side] = n_interface_nodes;
+    h->p2p.idx_lo[side] = h->p2p.idx_hi[side] = 0;
+    if (n_interface_nodes) {
+        h->p2p.idx_lo[side] = *std::min_element(h_interface_nodes, h_interface_nodes + n_interface_nodes);
+        h->p2p.idx_hi[side] = *std::max_element(h_interface_nodes, h_interface_nodes + n_interface_nodes) + 1;
+    }
     cudaIpcMemHandle_t hd;
     CU(cudaIpcGetMemHandle(&hd, h->p2p.inbox[side]));
     memcpy(ipc_handle_out, &hd, sizeof hd);

@@ -212,6 +212,60 @@ k_project_nodes(int node_lo, int n_nodes, const int *__restrict__ node_off, cons
     }
 }
 
+
+// ---- strips (pfem2_step_host_p2p): the same two node passes over a node id RANGE, restricted to the nodes an owned cell touches ----
+__device__ __forceinline__ bool node_accumulate_owned(int i, int own_lo, int own_hi, const int *__restrict__ node_off,
+                                                      const int *__restrict__ node_inc, const double *__restrict__ partial, double &sx,
+                                                      double &sy, double &sw)
+{
+    bool owned = false;
+    sx = sy = sw = 0.0;
+    const int e = __ldg(node_off + i + 1);
+    for (int q = __ldg(node_off + i); q < e; ++q) {
+        const int inc = __ldg(node_inc + q);
+        const int cell = inc / 3;
+        owned |= cell >= own_lo && cell < own_hi;
+        const double *a = partial + 3 * (size_t)inc;
+        sx = __dadd_rn(sx, a[0]);
+        sy = __dadd_rn(sy, a[1]);
+        sw = __dadd_rn(sw, a[2]);
+    }
+    return owned;
+}
+
+// acc3[i] = the three sums of node i (no division: the neighbour strip's share of an interface node is added first)
+static __global__ void __launch_bounds__(kThreads)
+k_project_nodes_acc_range(int node_lo, int node_hi, int own_lo, int own_hi, const int *__restrict__ node_off, const int *__restrict__ node_inc,
+                          const double *__restrict__ partial, double *__restrict__ acc3)
+{
+    const int i = node_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= node_hi) return;
+    double sx, sy, sw;
+    if (!node_accumulate_owned(i, own_lo, own_hi, node_off, node_inc, partial, sx, sy, sw)) return;
+    acc3[3 * (size_t)i] = sx;
+    acc3[3 * (size_t)i + 1] = sy;
+    acc3[3 * (size_t)i + 2] = sw;
+}
+
+// kFinalizeVelocityProjection over the owned nodes of [node_lo, node_hi)
+static __global__ void __launch_bounds__(kThreads)
+k_project_finalize_range(int node_lo, int node_hi, int own_lo, int own_hi, const int *__restrict__ node_off, const int *__restrict__ node_inc,
+                         const double *__restrict__ acc3, double *__restrict__ vx, double *__restrict__ vy)
+{
+    const int i = node_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= node_hi) return;
+    bool owned = false;
+    const int e = __ldg(node_off + i + 1);
+    for (int q = __ldg(node_off + i); q < e && !owned; ++q) {
+        const int cell = __ldg(node_inc + q) / 3;
+        owned = cell >= own_lo && cell < own_hi;
+    }
+    if (!owned) return;
+    const double sw = acc3[3 * (size_t)i + 2];
+    vx[i] = __ddiv_rn(acc3[3 * (size_t)i], sw);
+    vy[i] = __ddiv_rn(acc3[3 * (size_t)i + 1], sw);
+}
+
 // ---------------------------------------------------------------------------------------------
 // correction: kCorrectParticleVelocity (:72-88); Vold == nullptr -> initParticleVelocity (:322-326)
 //   d_i = V_i - Vold_i (plain sub) ; inc = fma chain from 0 ; v = v + inc (plain add)

@@ -282,7 +282,7 @@ static __global__ void __launch_bounds__(kThreads) k_band_width(int n_cells, con
 }
 // For the K chunks [cb[j], cb[j+1]) of the cell range and a reach of `ext` cells (substeps x band width):
 //   up_need[j]  = 1 + the largest node id of any cell a particle of chunk j can visit (cells [cb[j]-ext, cb[j+1]+ext))
-//   dn_ready[j] = the smallest node id of any cell behind chunk j (cells >= cb[j+1]): nodes below it are complete once the
+//   dn_ready[j] = the smallest node id of any cell behind chunk j (cells [cb[j+1], cb[K])): nodes below it are complete once the
 //                 chunks 0..j have been projected
 static __global__ void __launch_bounds__(kThreads)
 k_chunk_node_ranges(int n_cells, const CellGeom *__restrict__ geom, int K, const int *__restrict__ cb, int ext, int *__restrict__ up_need,
@@ -299,7 +299,7 @@ k_chunk_node_ranges(int n_cells, const CellGeom *__restrict__ geom, int K, const
     for (int j = 0; j < K; ++j) {
         const long long lo = (long long)__ldg(cb + j) - ext, hi = (long long)__ldg(cb + j + 1) + ext;
         const int a = __reduce_max_sync(0xffffffffu, (valid && c >= lo && c < hi) ? mx + 1 : 0);
-        const int b = __reduce_min_sync(0xffffffffu, (valid && c >= __ldg(cb + j + 1)) ? mn : 0x7fffffff);
+        const int b = __reduce_min_sync(0xffffffffu, (valid && c >= __ldg(cb + j + 1) && c < __ldg(cb + K)) ? mn : 0x7fffffff);
         if ((threadIdx.x & 31) == 0) {
             if (a > 0) atomicMax(up_need + j, a);
             if (b != 0x7fffffff) atomicMin(dn_ready + j, b);

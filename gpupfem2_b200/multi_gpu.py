@@ -325,10 +325,17 @@ class DistributedParticleHandler2D:
         self.correct_particle_velocity(frozen, work)
 
     def step_host(self, h_frozen, h_work, d_frozen, d_work, dt, substeps) -> int:
-        """The step with HOST nodal buffers (pinned torch tensors over the global node range, one set per rank): uploads the
-        slice of the nodal field this strip's advect can read, runs the step, downloads the slice of the projected field this
-        strip owns (interface nodes: identical bits on both strips after the halo sum) and returns the strip's particle count.
-        d_frozen / d_work are the rank's device staging arrays.  Copies and kernels are ordered on the default stream."""
+        """The step with HOST nodal buffers (pinned torch tensors over this rank's node numbering): uploads the slice of the nodal
+        field this strip's advect can read, runs the step, downloads the slice of the projected field this strip owns (interface
+        nodes: identical bits on both strips after the halo sum) and returns the strip's particle count.
+        P2P transport: ONE C call (pfem2_step_host_p2p) that pipelines the copies with the move pass and the projection and
+        drives the whole multi-GPU step from C; NCCL transports: the slices are staged through d_frozen / d_work around step()."""
+        if self.protocol == "p2p":
+            n = C.c_int(0)
+            self.h._check(self.L.pfem2_step_host_p2p(self.h._h, self.rank, h_frozen[0].data_ptr(), h_frozen[1].data_ptr(),
+                                                     h_work[0].data_ptr(), h_work[1].data_ptr(), dt, substeps, C.byref(n)), "step_host_p2p")
+            self._sent = None
+            return n.value
         ilo, ihi, olo, ohi = self.h.node_ranges(substeps)
         for k in range(2):
             d_frozen[k][ilo:ihi].copy_(h_frozen[k][ilo:ihi], non_blocking=True)

@@ -209,6 +209,14 @@ int pfem2_emigrants_send_p2p(pfem2_handle *h, int rank);
 int pfem2_immigrants_recv_p2p(pfem2_handle *h);
 int pfem2_project_halo_p2p(pfem2_handle *h, double *d_acc3);
 int pfem2_p2p_last_sent(pfem2_handle *h, int *out); /* records handed over by the last emigrants_send_p2p (synchronises) */
+/* The whole step of ONE STRIP with host nodal buffers, driven from C (the multi-GPU form of pfem2_step_host; every rank calls it in
+ * the same step):  upload of the node slice the strip's advect reads (in chunks under the move pass) ; advect_move ;
+ * emigrants_send_p2p ; immigrants_recv_p2p ; advect_finish ; projection in chunks of the own cell range (interior nodes are divided
+ * and downloaded under the cell pass) ; project_halo_p2p ; interface nodes divided and downloaded ; correct.
+ * h_f* / h_w*: host arrays over the handle's node numbering (n_nodes of its mesh view); read / written only inside the ranges
+ * pfem2_node_ranges reports.  Needs connected P2P inboxes (pfem2_p2p_connect) and pfem2_set_rank_bounds. */
+int pfem2_step_host_p2p(pfem2_handle *h, int rank, const double *h_fx, const double *h_fy, double *h_wx, double *h_wy, double dt,
+                        int substeps, int *count_out);
 /* d_acc3: n_nodes x {sum L v_x, sum L v_y, sum L} of the particles this handle holds (no division) */
 int pfem2_project_accumulate(pfem2_handle *h, double *d_acc3);
 int pfem2_project_finalize(pfem2_handle *h, const double *d_acc3, double *d_vx, double *d_vy);

@@ -86,6 +86,29 @@ def main():
         for _ in range(nsteps):
             h.step(F, W, dt, S)
             moved += h.last_sent
+        host_steps = 0
+        if h.protocol == "p2p" and not stable:
+            # the C-side driver of the strip step with HOST nodal buffers (pfem2_step_host_p2p), plain and pipelined in 3 chunks
+            # (a second handle: host_pipeline is a create-time option); results land in pinned host arrays
+            hF = [t.cpu().pin_memory() for t in F]
+            hW = [torch.zeros_like(t).pin_memory() for t in hF]
+            host_steps = 3
+            for _ in range(host_steps):
+                h.step_host(hF, hW, F, W, dt, S)
+                moved += h.last_sent
+            W = (hW[0].to(dev), hW[1].to(dev))
+            h3 = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world, migration="p2p", host_pipeline=3)
+            h3.seed_particles()
+            h3.init_particle_velocity(F)
+            hW3 = [torch.zeros_like(t).pin_memory() for t in hF]
+            for _ in range(nsteps + host_steps):
+                h3.step_host(hF, hW3, F, None, dt, S)
+            assert torch.equal(h3.state_checksum(), h.state_checksum()), "pipelined pfem2_step_host_p2p: state differs from the plain form"
+            ilo, ihi, olo, ohi = h3.h.node_ranges(S)
+            for a, b in zip(hW3, hW):
+                e = (a[olo:ohi] - b[olo:ohi]).abs().max() / b.abs().max()
+                assert float(e) <= REL_TOL, f"pipelined pfem2_step_host_p2p: projected field differs by {float(e):.3e}"
+            h3.close()
         total = h.global_particle_count()
         state = h.download()
         mine = torch.zeros(dm.n_nodes, dtype=torch.bool, device=dev)
@@ -97,7 +120,7 @@ def main():
             ref.seed_particles()
             ref.init_particle_velocity(F)
             RW = (torch.zeros_like(fx), torch.zeros_like(fx))
-            for _ in range(nsteps):
+            for _ in range(nsteps + host_steps):
                 ref.step(F, RW, dt, S)
             merged = gathered[0][0]
             for g in gathered[1:]:

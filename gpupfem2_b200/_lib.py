@@ -26,7 +26,7 @@ SYMBOLS = (
     "pfem2_immigrants_append", "pfem2_advect_finish", "pfem2_project_accumulate", "pfem2_project_finalize",
     "pfem2_set_rank_bounds", "pfem2_emigrants_pack_neighbours", "pfem2_immigrants_append_device",
     "pfem2_p2p_inbox_create", "pfem2_p2p_connect", "pfem2_emigrants_send_p2p", "pfem2_immigrants_recv_p2p",
-    "pfem2_project_halo_p2p", "pfem2_p2p_last_sent", "pfem2_project_dual", "pfem2_project_dual_ptrs", "pfem2_node_ranges", "pfem2_set_global_cell_offset", "pfem2_mesh_band", "pfem2_step_host_p2p",
+    "pfem2_project_halo_p2p", "pfem2_p2p_last_sent", "pfem2_project_dual", "pfem2_project_dual_ptrs", "pfem2_node_ranges", "pfem2_set_global_cell_offset", "pfem2_mesh_band", "pfem2_step_host_p2p", "pfem2_advect_p2p", "pfem2_project_p2p",
 )
 
 
@@ -82,6 +82,8 @@ def load():
     L.pfem2_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.pfem2_export_aos.argtypes = [vp, C.POINTER(vp), C.POINTER(i)]
     L.pfem2_step_host.argtypes = [vp, vp, vp, vp, vp, d, i, C.POINTER(i)]
+    L.pfem2_advect_p2p.argtypes = [vp, i, vp, vp, d, i]
+    L.pfem2_project_p2p.argtypes = [vp, vp, vp, vp]
     L.pfem2_step_host_p2p.argtypes = [vp, i, vp, vp, vp, vp, d, i, C.POINTER(i)]
     L.pfem2_download.argtypes = [vp] + [vp] * 9
     L.pfem2_upload.argtypes = [vp, i] + [vp] * 9

@@ -311,8 +311,11 @@ void launch_pack_nodal(pfem2_handle *h, int node_lo, int node_hi, NodalVel vel, 
 }
 
 // one launch of the move pass over the cells [c_lo, c_hi) of the segment table `cstart` (nullptr: everybody)
-static void launch_move(pfem2_handle *h, bool lazy, double hsub, int substeps, int do_count, int grid, const int *cstart, int c_lo, int c_hi)
+// src = the buffer the pass reads (h->cur, or h->cur ^ 1 for the interior part of a split pass after the flip)
+static void launch_move(pfem2_handle *h, bool lazy, double hsub, int substeps, int do_count, int grid, const int *cstart, int c_lo, int c_hi,
+                        int src = -1, int part = 0)
 {
+    if (src < 0) src = h->cur;
     const int C = h->mesh.n_cells;
     const size_t smem = advect_tma_smem_bytes(kAdvThreads);
     const bool walk = h->opt.exact_search == 0;
@@ -322,10 +325,10 @@ static void launch_move(pfem2_handle *h, bool lazy, double hsub, int substeps, i
     cudaStream_t st = h->stream;
     if (lazy) {
 #define PFEM2_MOVE_GATHER(W, NSUB, SWZ)                                                                                                   \
-    PFEM2_LAUNCH((k_move_gather<W, NSUB, SWZ>), grid, kAdvThreads, smem, st, h->gmap[h->cur], h->omap[h->cur ^ 1],                          \
+    PFEM2_LAUNCH((k_move_gather<W, NSUB, SWZ>), grid, kAdvThreads, smem, st, h->gmap[src], h->omap[src ^ 1],                                \
                  (const int4 *)h->vals[h->perm_buf], h->keys[1], h->geom, h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, \
                  hsub, substeps, mode, C, h->ppc, h->level, h->sub_step, h->ctr, h->stay, h->cell_mask, dv2, h->own_lo, h->own_hi,         \
-                 h->mg_bounds, h->mg_ranks, h->mg_rank_count, emig, cstart, c_lo, c_hi)
+                 h->mg_bounds, h->mg_ranks, h->mg_rank_count, emig, cstart, c_lo, c_hi, part)
 #define PFEM2_MOVE_GATHER_W(W)                                                                                                            \
     do {                                                                                                                                  \
         if (!h->lazy_swizzle) PFEM2_MOVE_GATHER(W, 0, false);                                                                             \
@@ -341,7 +344,7 @@ static void launch_move(pfem2_handle *h, bool lazy, double hsub, int substeps, i
     const bool stable = h->opt.stable_order != 0;
     unsigned *sb = stable ? h->stay_bits : nullptr;
 #define PFEM2_MOVE_TILES(W, NSUB, FAST)                                                                                                   \
-    PFEM2_LAUNCH((k_move_tiles<W, NSUB, FAST>), grid, kAdvThreads, smem, st, h->tmap[h->cur], h->geom, h->edge_nbr, h->mesh.d_nbr_offsets,  \
+    PFEM2_LAUNCH((k_move_tiles<W, NSUB, FAST>), grid, kAdvThreads, smem, st, h->tmap[src], h->geom, h->edge_nbr, h->mesh.d_nbr_offsets,  \
                  h->mesh.d_nbr_indices, h->v2, hsub, substeps, mode, C, h->ppc, h->level, h->sub_step, h->ctr, sb, h->warp_movers, h->stay, \
                  stable ? h->arrive : (int *)nullptr, h->cell_mask, do_count, dv2, h->own_lo, h->own_hi, h->mg_bounds, h->mg_ranks,        \
                  h->mg_rank_count, emig, cstart, c_lo, c_hi)
@@ -359,7 +362,9 @@ static void launch_move(pfem2_handle *h, bool lazy, double hsub, int substeps, i
 #undef PFEM2_MOVE_TILES
 }
 
-int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_count, bool mg_move)
+// split (strips, lazy + fused only): this call moves only the cells within reach of the strip boundaries -- every emigrant comes from
+// there --, so that the caller can send them and move the interior (advect_move_interior) while the delivery travels
+int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_count, bool mg_move, bool split)
 {
     if (!h) return PFEM2_EINVAL;
     if (!h->seeded) return fail(h, PFEM2_ESTATE, "advect before seed");
@@ -415,7 +420,19 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     }
     {
         PhaseScope ps(h, PFEM2_PHASE_ADVECT);
-        if (!h->pipe.active) {
+        h->mv_interior_pending = false;
+        if (!h->pipe.active && split && lazy && fused && h->band >= 0) {
+            launch_pack_nodal(h, h->v2_node_lo, h->v2_node_hi, vel, true);
+            const long long reach = (long long)h->band * substeps;
+            const int bl = (int)std::min<long long>(h->own_lo + reach, h->own_hi), br = (int)std::max<long long>(h->own_hi - reach, bl);
+            const int *cstart = h->cell_start[h->cs];
+            const int gb = grid_for((long long)(reach + 1) * h->ppc * 2, kAdvThreads, g_num_sms * kAdvBlocksPerSM);
+            launch_move(h, lazy, hsub, substeps, do_count, gb, cstart, bl, br, -1, 1); // the cells next to the left strip boundary ...
+            launch_move(h, lazy, hsub, substeps, do_count, gb, cstart, bl, br, -1, 3); // ... and to the right one
+            h->mv_interior_pending = true;
+            h->mv_hsub = hsub; h->mv_substeps = substeps; h->mv_do_count = do_count; h->mv_bl = bl; h->mv_br = br;
+            h->mv_dv_pending = h->dv_pending; // the interior particles get the same deferred correction
+        } else if (!h->pipe.active) {
             launch_pack_nodal(h, h->v2_node_lo, h->v2_node_hi, vel, true); // all nodes on a single GPU; a strip's reach otherwise
             const int grid = grid_for(h->capacity, kAdvThreads, g_num_sms * kAdvBlocksPerSM); // persistent: all resident blocks
             launch_move(h, lazy, hsub, substeps, do_count, grid, nullptr, 0, C);
@@ -441,6 +458,22 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     h->lazy_move = lazy;
     h->dv_pending = false; // the move pass applied the deferred correction
     h->move_pending = true;
+    return PFEM2_OK;
+}
+
+// second part of a split move pass: the cells between the two boundary layers (reads the buffer the first part read: cur ^ 1 now)
+int advect_move_interior(pfem2_handle *h)
+{
+    if (!h->mv_interior_pending) return PFEM2_OK;
+    h->mv_interior_pending = false;
+    CU(cudaSetDevice(h->device));
+    PhaseScope ps(h, PFEM2_PHASE_ADVECT);
+    const int grid = grid_for(h->capacity, kAdvThreads, g_num_sms * kAdvBlocksPerSM);
+    const bool keep = h->dv_pending;
+    h->dv_pending = h->mv_dv_pending; // (launch_move hands dv2 to the kernel iff a correction is pending)
+    launch_move(h, true, h->mv_hsub, h->mv_substeps, h->mv_do_count, grid, h->cell_start[h->cs], h->mv_bl, h->mv_br, h->cur ^ 1, 2);
+    h->dv_pending = keep;
+    CU(cudaGetLastError());
     return PFEM2_OK;
 }
 
@@ -523,6 +556,7 @@ int advect_finish(pfem2_handle *h, NodalVel vel, int need_count)
 {
     if (!h) return PFEM2_EINVAL;
     if (!h->move_pending) return fail(h, PFEM2_ESTATE, "advect_finish without advect_move");
+    if (h->mv_interior_pending) return fail(h, PFEM2_ESTATE, "advect_finish before the interior part of a split move pass");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     int rc;
@@ -563,7 +597,7 @@ int advect_finish(pfem2_handle *h, NodalVel vel, int need_count)
 static int do_advect(pfem2_handle *h, NodalVel vel, double dt, int substeps)
 {
     int rc;
-    if ((rc = advect_move(h, vel, dt, substeps, 1, false))) return rc;
+    if ((rc = advect_move(h, vel, dt, substeps, 1, false, false))) return rc;
     return advect_finish(h, vel, 0);
 }
 

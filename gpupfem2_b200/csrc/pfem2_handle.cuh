@@ -110,6 +110,10 @@ struct pfem2_handle {
     bool mg_fused = false;    // the move pass in flight listed its emigrants and counted the per-cell statistics
     int mg_fused_total = 0;   // emigrants listed by that pass
     bool move_pending = false; // advect_move done, advect_finish outstanding
+    bool mv_interior_pending = false; // split move pass: the boundary layers are moved, the interior is outstanding (its parameters:)
+    double mv_hsub = 0.0;
+    int mv_substeps = 0, mv_do_count = 0, mv_bl = 0, mv_br = 0;
+    bool mv_dv_pending = false;
 
     // pfem2_step_host pipeline: the step runs in K chunks of the cell range so that the host <-> device copies of the nodal
     // fields overlap the move pass (upload) and the projection (download)
@@ -220,7 +224,8 @@ int materialize(pfem2_handle *h);    // lazy re-sort: make the sorted order phys
 int flush_correct(pfem2_handle *h);  // apply a deferred velocity correction now
 int mesh_band(pfem2_handle *h);      // band width of the cell numbering (one-time)
 bool lazy_enabled(const pfem2_handle *h);
-int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_count, bool mg_move);
+int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_count, bool mg_move, bool split);
+int advect_move_interior(pfem2_handle *h);
 int advect_finish(pfem2_handle *h, NodalVel vel, int need_count);
 void launch_project_cells(pfem2_handle *h, int c_lo = -1, int c_hi = -1);
 void launch_project_nodes(pfem2_handle *h, int node_lo, int node_hi, double *vx, double *vy, double *const *table, double *cx, double *cy,

@@ -387,8 +387,12 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
               int subcell_mode, int n_cells, int ppc, int level, double sub_step, Counters *ctr, int *__restrict__ stay,
               unsigned long long *__restrict__ cell_mask, const double2 *__restrict__ dV2, int own_lo, int own_hi,
               const int *__restrict__ rank_bounds, int n_ranks, int *__restrict__ rank_count, unsigned *__restrict__ emig_idx,
-              const int *__restrict__ chunk_start, int chunk_lo, int chunk_hi)
+              const int *__restrict__ chunk_start, int chunk_lo, int chunk_hi, int part)
 {
+    // part = 1, 2, 3: split pass of a strip (multi-GPU).  With t1 = start of cell chunk_lo rounded UP to a tile and t2 = start of cell
+    // chunk_hi rounded down (>= t1), part 1 moves the positions [0, t1) (every particle of the cells next to the left strip boundary),
+    // part 3 the positions [t2, count) (the cells next to the right boundary) and part 2 the interior [t1, t2): the host launches
+    // 1 and 3, sends the emigrants -- they all come from there -- and launches 2 while the delivery travels.
     // chunk_start != nullptr (pfem2_step_host, chunked): this launch moves the tiles whose FIRST sorted position lies in the segment range
     // of the cells [chunk_lo, chunk_hi) -- whole tiles, because the pass is not in place (a tile shared by two launches would be written
     // twice from the unmoved source).  Rounding the chunk's particle range down to tiles only moves work to an EARLIER chunk's neighbour on
@@ -412,8 +416,15 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
     // bound serves the loop and the validity of a lane
     int n = ctr->count, p_lo = 0;
     if (chunk_start) {
-        p_lo = min(__ldg(chunk_start + chunk_lo), n) & ~31;
-        if (chunk_hi < own_hi) n = min(__ldg(chunk_start + chunk_hi), n) & ~31; // (the last chunk of the owned range ends at the count)
+        if (part) {
+            const int t1 = min((__ldg(chunk_start + chunk_lo) + 31) & ~31, n);
+            const int t2 = max(min(__ldg(chunk_start + chunk_hi), n) & ~31, t1);
+            p_lo = part == 1 ? 0 : (part == 2 ? t1 : t2);
+            n = part == 1 ? t1 : (part == 2 ? t2 : n);
+        } else {
+            p_lo = min(__ldg(chunk_start + chunk_lo), n) & ~31;
+            if (chunk_hi < own_hi) n = min(__ldg(chunk_start + chunk_hi), n) & ~31; // (the last chunk of the owned range ends at the count)
+        }
     }
     const int first = p_lo + ((blockIdx.x * warps_per_block + warp) << 5);
     const int stride = (int)gridDim.x * (warps_per_block * 32);

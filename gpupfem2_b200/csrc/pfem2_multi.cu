@@ -58,7 +58,7 @@ extern "C" {
 
 int pfem2_advect_move(pfem2_handle *h, const double *vx, const double *vy, double dt, int substeps)
 {
-    return advect_move(h, nodal(vx, vy, nullptr), dt, substeps, 0, true);
+    return advect_move(h, nodal(vx, vy, nullptr), dt, substeps, 0, true, false);
 }
 
 int pfem2_advect_finish(pfem2_handle *h, const double *vx, const double *vy) { return advect_finish(h, nodal(vx, vy, nullptr), 1); }
@@ -313,19 +313,14 @@ int pfem2_immigrants_recv_p2p(pfem2_handle *h)
     return PFEM2_OK;
 }
 
-int pfem2_project_halo_p2p(pfem2_handle *h, double *d_acc3)
+// interface sums -> the neighbours' halo blocks + release (one launch) / wait for theirs + add (one launch)
+static int halo_send(pfem2_handle *h, double *d_acc3)
 {
-    if (!h || !d_acc3) return PFEM2_EINVAL;
-    CU(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const int cap = h->p2p.cap;
-    if (!h->p2p.peer[0] && !h->p2p.peer[1]) return PFEM2_OK;
     const unsigned seq = ++h->p2p.halo_seq;
     const int parity = (int)(seq & 1u);
-    // two launches: store my interface sums into both neighbours' halo blocks + release the flags (last block);
-    // wait for theirs + add (two contributions per shared node: a + b == b + a bit for bit)
     unsigned char *peer[2] = {(unsigned char *)h->p2p.peer[0], (unsigned char *)h->p2p.peer[1]};
-    unsigned char *inbox[2] = {(unsigned char *)h->p2p.inbox[0], (unsigned char *)h->p2p.inbox[1]};
     const int n[2] = {peer[0] ? h->p2p.n_idx[0] : 0, peer[1] ? h->p2p.n_idx[1] : 0};
     const int total = std::max(n[0] + n[1], 1);
     PFEM2_LAUNCH(k_halo_send2, grid_for(total, kThreads, 1 << 30), kThreads, 0, st, d_acc3, h->p2p.idx[0], n[0],
@@ -333,11 +328,111 @@ int pfem2_project_halo_p2p(pfem2_handle *h, double *d_acc3)
                  peer[0] ? &((P2PInboxHead *)peer[0])->flag_halo : nullptr, h->p2p.idx[1], n[1],
                  peer[1] ? (double *)(peer[1] + p2p_halo_offset(cap, h->p2p.n_idx[1], parity)) : nullptr,
                  peer[1] ? &((P2PInboxHead *)peer[1])->flag_halo : nullptr, seq, (unsigned *)(h->p2p.cursors + 3));
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+static int halo_recv(pfem2_handle *h, double *d_acc3)
+{
+    cudaStream_t st = h->stream;
+    const int cap = h->p2p.cap;
+    const unsigned seq = h->p2p.halo_seq;
+    const int parity = (int)(seq & 1u);
+    unsigned char *peer[2] = {(unsigned char *)h->p2p.peer[0], (unsigned char *)h->p2p.peer[1]};
+    unsigned char *inbox[2] = {(unsigned char *)h->p2p.inbox[0], (unsigned char *)h->p2p.inbox[1]};
+    const int n[2] = {peer[0] ? h->p2p.n_idx[0] : 0, peer[1] ? h->p2p.n_idx[1] : 0};
+    const int total = std::max(n[0] + n[1], 1);
+    // (two contributions per shared node: a + b == b + a bit for bit)
     PFEM2_LAUNCH(k_halo_recv2, grid_for(total, kThreads, 1 << 30), kThreads, 0, st, d_acc3,
                  peer[0] ? &((const P2PInboxHead *)inbox[0])->flag_halo : nullptr, peer[1] ? &((const P2PInboxHead *)inbox[1])->flag_halo : nullptr,
                  seq, h->ctr, p2p_timeout_ns(), h->p2p.idx[0], n[0],
                  peer[0] ? (const double *)(inbox[0] + p2p_halo_offset(cap, h->p2p.n_idx[0], parity)) : nullptr, h->p2p.idx[1], n[1],
                  peer[1] ? (const double *)(inbox[1] + p2p_halo_offset(cap, h->p2p.n_idx[1], parity)) : nullptr);
+    CU(cudaGetLastError());
+    return PFEM2_OK;
+}
+
+int pfem2_project_halo_p2p(pfem2_handle *h, double *d_acc3)
+{
+    if (!h || !d_acc3) return PFEM2_EINVAL;
+    CU(cudaSetDevice(h->device));
+    if (!h->p2p.peer[0] && !h->p2p.peer[1]) return PFEM2_OK;
+    const int rc = halo_send(h, d_acc3);
+    return rc ? rc : halo_recv(h, d_acc3);
+}
+
+// PFEM2_P2P_SPLIT=1 (A/B; default off): hide the exchange behind interior work -- the cells within reach of the strip boundaries
+// are moved / reduced first, their emigrants / interface sums are sent, the interior follows while the delivery travels.  Measured
+// on channel16m (profiles/r02_summary.md §7): 2.007 against 1.937 ms per step at 8 GPUs, 3.76 against 3.72 at four -- the five extra
+// launches and the tails of the small boundary kernels cost more than the exchange latency they hide (the strips run in lockstep,
+// so a delivery is rarely late), hence off.
+static bool p2p_split()
+{
+    static const bool on = [] {
+        const char *e = getenv("PFEM2_P2P_SPLIT");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+
+// advectParticles of one strip, P2P transport, in one call: move pass (lists its emigrants), send, append the immigrants, rank pass
+int pfem2_advect_p2p(pfem2_handle *h, int rank, const double *vx, const double *vy, double dt, int substeps)
+{
+    if (!h) return PFEM2_EINVAL;
+    int rc;
+    CU(cudaSetDevice(h->device));
+    if (p2p_split() && (rc = mesh_band(h))) return rc;
+    if ((rc = advect_move(h, nodal(vx, vy, nullptr), dt, substeps, 0, true, p2p_split()))) return rc;
+    if ((rc = pfem2_emigrants_send_p2p(h, rank))) return rc;
+    if ((rc = advect_move_interior(h))) return rc;
+    if ((rc = pfem2_immigrants_recv_p2p(h))) return rc;
+    return advect_finish(h, nodal(vx, vy, nullptr), 1);
+}
+
+// projectVelocityOntoGrid of one strip, P2P transport, in one call: cell pass, node sums, halo exchange, division
+int pfem2_project_p2p(pfem2_handle *h, double *d_acc3, double *d_vx, double *d_vy)
+{
+    if (!h || !d_acc3 || !d_vx || !d_vy) return PFEM2_EINVAL;
+    if (!h->seeded) return fail(h, PFEM2_ESTATE, "project before seed");
+    CU(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = flush_correct(h))) return rc;
+    const bool connected = h->p2p.peer[0] || h->p2p.peer[1];
+    if (!p2p_split()) {
+        {
+            PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
+            launch_project_cells(h);
+        }
+        PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
+        launch_project_nodes_acc_range(h, h->own_node_lo, h->own_node_hi, d_acc3);
+        if (connected && (rc = halo_send(h, d_acc3))) return rc;
+        if (connected && (rc = halo_recv(h, d_acc3))) return rc;
+        launch_project_finalize_range(h, h->own_node_lo, h->own_node_hi, d_acc3, d_vx, d_vy);
+        CU(cudaGetLastError());
+        return PFEM2_OK;
+    }
+    // split form: the cells that touch an interface node first, their sums sent, the interior while they travel
+    if ((rc = mesh_band(h))) return rc;
+    const int bl = std::min(h->own_lo + h->band + 1, h->own_hi), br = std::max(h->own_hi - h->band - 1, bl);
+    {
+        PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
+        launch_project_cells(h, h->own_lo, bl);
+        if (br < h->own_hi) launch_project_cells(h, br, h->own_hi);
+    }
+    if (connected) {
+        PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
+        for (int side = 0; side < 2; ++side)
+            if (h->p2p.peer[side]) launch_project_nodes_acc_range(h, h->p2p.idx_lo[side], h->p2p.idx_hi[side], d_acc3);
+        if ((rc = halo_send(h, d_acc3))) return rc;
+    }
+    if (br > bl) {
+        PhaseScope ps(h, PFEM2_PHASE_PROJECT_CELLS);
+        launch_project_cells(h, bl, br);
+    }
+    PhaseScope ps(h, PFEM2_PHASE_PROJECT_NODES);
+    launch_project_nodes_acc_range(h, h->own_node_lo, h->own_node_hi, d_acc3); // (interface nodes again: the same sums)
+    if (connected && (rc = halo_recv(h, d_acc3))) return rc;
+    launch_project_finalize_range(h, h->own_node_lo, h->own_node_hi, d_acc3, d_vx, d_vy);
     CU(cudaGetLastError());
     return PFEM2_OK;
 }

@@ -269,14 +269,13 @@ class DistributedParticleHandler2D:
 
     def advect_particles(self, vel, time_step, particle_substeps):
         h, L = self.h, self.L
-        h._check(L.pfem2_advect_move(h._h, vel[0].data_ptr(), vel[1].data_ptr(), time_step, particle_substeps), "advect_move")
         if self.protocol == "p2p":
-            # three library calls, all enqueued on the handle's stream: records go straight into the neighbours' HBM over NVLink
-            h._check(L.pfem2_emigrants_send_p2p(h._h, self.rank), "emigrants_send_p2p")
-            h._check(L.pfem2_immigrants_recv_p2p(h._h), "immigrants_recv_p2p")
-            h._check(L.pfem2_advect_finish(h._h, vel[0].data_ptr(), vel[1].data_ptr()), "advect_finish")
+            # one library call, everything enqueued on the handle's stream: boundary layers moved first, emigrants stored straight into
+            # the neighbours' HBM over NVLink, interior moved while the delivery travels, immigrants appended, rank pass
+            h._check(L.pfem2_advect_p2p(h._h, self.rank, vel[0].data_ptr(), vel[1].data_ptr(), time_step, particle_substeps), "advect_p2p")
             self._sent = None  # read from the device on demand
             return
+        h._check(L.pfem2_advect_move(h._h, vel[0].data_ptr(), vel[1].data_ptr(), time_step, particle_substeps), "advect_move")
         if self._nbr is not None:
             # everything below is enqueued without waiting for the device: the library works on the legacy default stream, which
             # is torch's current stream here, and torch orders the NCCL transfers against it (w.wait() is a stream-side wait)
@@ -307,13 +306,13 @@ class DistributedParticleHandler2D:
 
     def project_velocity_onto_grid(self, vel):
         h, L = self.h, self.L
+        if self.protocol == "p2p":
+            h._check(L.pfem2_project_p2p(h._h, self.acc3.data_ptr(), vel[0].data_ptr(), vel[1].data_ptr()), "project_p2p")
+            return
         # no host synchronisation: the library works on the legacy default stream, which is also torch's current stream here,
         # and torch orders the NCCL transfers against it (w.wait() makes the current stream wait for the receive)
         h._check(L.pfem2_project_accumulate(h._h, self.acc3.data_ptr()), "project_accumulate")
-        if self.protocol == "p2p":
-            h._check(L.pfem2_project_halo_p2p(h._h, self.acc3.data_ptr()), "project_halo_p2p")
-        else:
-            exchange_interface(self.acc3, self.iface, self.group)
+        exchange_interface(self.acc3, self.iface, self.group)
         h._check(L.pfem2_project_finalize(h._h, self.acc3.data_ptr(), vel[0].data_ptr(), vel[1].data_ptr()), "project_finalize")
 
     def correct_particle_velocity(self, vel, vel_old):

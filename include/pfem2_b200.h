@@ -209,6 +209,15 @@ int pfem2_emigrants_send_p2p(pfem2_handle *h, int rank);
 int pfem2_immigrants_recv_p2p(pfem2_handle *h);
 int pfem2_project_halo_p2p(pfem2_handle *h, double *d_acc3);
 int pfem2_p2p_last_sent(pfem2_handle *h, int *out); /* records handed over by the last emigrants_send_p2p (synchronises) */
+/* The two halves of a strip's step as single calls (what DistributedParticleHandler2D uses with the P2P transport; results
+ * identical to the piecewise sequence above):
+ *   pfem2_advect_p2p   advect_move ; emigrants_send_p2p ; immigrants_recv_p2p ; advect_finish
+ *   pfem2_project_p2p  cell pass ; node sums ; project_halo_p2p ; division.  d_acc3: 3 x n_nodes doubles of scratch, zero-initialised
+ *                      once by the caller (nodes no owned cell touches are never written).
+ * PFEM2_P2P_SPLIT=1 selects a form that moves / reduces the cells next to the strip boundaries first and hides the exchange behind
+ * the interior (measured slower on B200: more, smaller launches; kept for A/B). */
+int pfem2_advect_p2p(pfem2_handle *h, int rank, const double *d_vx, const double *d_vy, double dt, int substeps);
+int pfem2_project_p2p(pfem2_handle *h, double *d_acc3, double *d_vx, double *d_vy);
 /* The whole step of ONE STRIP with host nodal buffers, driven from C (the multi-GPU form of pfem2_step_host; every rank calls it in
  * the same step):  upload of the node slice the strip's advect reads (in chunks under the move pass) ; advect_move ;
  * emigrants_send_p2p ; immigrants_recv_p2p ; advect_finish ; projection in chunks of the own cell range (interior nodes are divided

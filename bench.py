@@ -303,7 +303,8 @@ def measure(args, rank, world, local, full):
         h = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world, **opts)
         inner = h.h
     else:
-        h = handler.ParticleHandler2D(dm, level, host_pipeline=int(os.environ.get("PFEM2_HOST_PIPELINE", "0")), **opts)
+        h = handler.ParticleHandler2D(dm, level, host_pipeline=int(os.environ.get("PFEM2_HOST_PIPELINE", "0")),
+                                      graph_advect=int(os.environ.get("PFEM2_GRAPH_ADVECT", "0")), **opts)
         inner = h
     h.seed_particles()
     h.init_particle_velocity(F)
@@ -321,7 +322,10 @@ def measure(args, rank, world, local, full):
         sampler.wait_first_sample()
     if multi:
         dist.barrier()
-    inner.set_profiling(True)
+    # Per-phase CUDA events ride along in the timed region of the HBM-bound workloads.  The small shipped meshes are launch-bound and
+    # run advectParticles as one CUDA-graph launch, which the phase events would switch off: they are timed plain, and the phase
+    # breakdown comes from a second, profiled pass behind the timed region.
+    inner.set_profiling(not small)
     inner.phase_times(reset=True)
     launches0 = handler.kernel_launches()
     if sampler:
@@ -347,6 +351,12 @@ def measure(args, rank, world, local, full):
     # large states: one interval over the K steps (what lies between two steps is part of the job); flushed small states: the
     # flush sits between the per-step pairs
     total_ms = ev[0][0].elapsed_time(ev[-1][1]) if flush is None else sum(ms)
+    if small:
+        inner.set_profiling(True)
+        inner.phase_times(reset=True)
+        for k in range(args.steps):
+            h.step(F, W, dt, args.substeps)
+        h.get_particle_count()
     phases = inner.phase_times(reset=True)
     inner.set_profiling(False)
     sent = h.last_sent if multi else 0
@@ -457,6 +467,8 @@ def measure(args, rank, world, local, full):
                    "timing": "CUDA events on the launching (legacy default) stream around the K steps" + (", max over ranks, barrier on both sides" if multi else ""),
                    "mesh_bytes_per_rank": mesh_bytes, "setup_s": t_setup},
         "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches_note": ("kernel launches enqueued by the library in the timed region; a replayed CUDA graph of advectParticles "
+                              "(small meshes) counts as the kernels it contains"),
         "state_checksum": {"value": [int(v) for v in checksum.tolist()],
                            "what": "order-independent wrapping int64 sums over the GLOBAL particle set after warm-up + timed steps: "
                                    "[count, bits(x), bits(y), bits(L0), bits(L1), bits(L2), cell]; identical for every N"},

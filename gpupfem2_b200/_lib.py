@@ -37,7 +37,7 @@ class MeshView(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("struct_size", C.c_int), ("subcell_mode", C.c_int), ("max_division_level", C.c_int),
-                ("capacity_factor", C.c_double), ("stream", C.c_void_p), ("device", C.c_int), ("verbose", C.c_int), ("exact_search", C.c_int), ("stable_order", C.c_int), ("reserved_scatter_tma", C.c_int), ("defer_correct", C.c_int), ("reserved_lane_per_record", C.c_int), ("host_pipeline", C.c_int), ("reserved_fuse_project", C.c_int), ("lazy_sort", C.c_int)]
+                ("capacity_factor", C.c_double), ("stream", C.c_void_p), ("device", C.c_int), ("verbose", C.c_int), ("exact_search", C.c_int), ("stable_order", C.c_int), ("reserved_scatter_tma", C.c_int), ("defer_correct", C.c_int), ("reserved_lane_per_record", C.c_int), ("host_pipeline", C.c_int), ("reserved_fuse_project", C.c_int), ("lazy_sort", C.c_int), ("graph_advect", C.c_int)]
 
 
 class Stats(C.Structure):

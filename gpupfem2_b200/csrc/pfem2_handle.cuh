@@ -142,6 +142,21 @@ struct pfem2_handle {
         unsigned mig_seq = 0, halo_seq = 0;     // deliveries made so far (block parity = seq & 1)
     } p2p;
 
+    // CUDA graphs of advectParticles for launch-bound (small) cases: pfem2_api.cu, advect_graphed.  One graph per parity of the buffer
+    // ping-pong (cur, cs, perm_buf), replayed while the arguments of the call stay what they were captured for
+    struct AdvectGraph {
+        cudaGraphExec_t exec = nullptr;
+        const void *vx = nullptr, *vy = nullptr, *table = nullptr, *buf0 = nullptr, *buf1 = nullptr;
+        double dt = 0.0;
+        int substeps = 0, capacity = 0;
+        bool dv = false;
+        long long kernels = 0; // kernel nodes of the graph (pfem2_kernel_launches counts a replay as these)
+    } graphs[8];
+    cudaStream_t graph_stream = nullptr; // private capture stream (the legacy default stream cannot be captured)
+    bool capturing = false;
+    bool graphs_broken = false;          // capture failed once in this process: do not try again
+    long long graph_replays = 0;
+
     // optional per-phase CUDA-event timing (pfem2_set_profiling)
     bool profiling = false;
     struct PhaseRec { int phase; cudaEvent_t a, b; };

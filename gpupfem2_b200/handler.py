@@ -164,7 +164,7 @@ class ParticleHandler2D:
 
     def __init__(self, mesh: DeviceMesh, cell_division_level: int, *, subcell_mode=0, max_division_level=4,
                  capacity_factor=1.5, verbose=False, exact_search=False, stable_order=False, defer_correct=True, host_pipeline=0,
-                 lazy_sort=True):
+                 lazy_sort=True, graph_advect=0):
         self._L = _lib.load()
         self.mesh = mesh  # borrowed for the handler's lifetime, like the reference's `const Mesh2D *`
         opt = _lib.Options()
@@ -179,6 +179,7 @@ class ParticleHandler2D:
         opt.defer_correct = 1 if defer_correct else 0
         opt.host_pipeline = int(host_pipeline)
         opt.lazy_sort = 1 if lazy_sort else 0
+        opt.graph_advect = int(graph_advect)
         self._h = C.c_void_p()
         view = mesh.view()
         rc = self._L.pfem2_create(C.byref(self._h), C.byref(view), cell_division_level, C.byref(opt))

@@ -77,6 +77,9 @@ typedef struct pfem2_options {
                                records, the eager correction) materialises the sorted array first.  Same results; 14.3 instead of
                                17.7 ms per step on the 16M-triangle channel.  0: physical re-sort in every advect.  Ignored (off)
                                with stable_order */
+    int graph_advect;       /* CUDA graph of advectParticles: 0 (default) = on meshes below 262144 cells (launch-bound: the shipped cases
+                               run ~10 kernels of a few microseconds per call), 1 = always, -1 = never.  The first call of a buffer
+                               parity captures the enqueue sequence, later calls with the same arguments replay it as ONE launch */
 } pfem2_options;
 
 /* counters of the last pfem2_advect call (device-resident, read back on demand) */

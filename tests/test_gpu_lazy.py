@@ -228,3 +228,43 @@ def test_capacity_overflow_is_reported_not_written_out_of_bounds(gpu, oracle):
     h.advect_particles(f, 1e-9, 3)
     assert h.get_particle_count() == cap + 15 * m.n_cells
     h.close()
+
+
+@pytest.mark.parametrize("name", ["channel_l2", "cyl3_l2"])
+def test_graphed_advect_equals_plain_launches(gpu, oracle, name):
+    """pfem2_options.graph_advect: advectParticles replayed as ONE CUDA-graph launch per call (automatic on the small shipped meshes).
+    Same particle set bit for bit, same counters and projected field as the plain enqueue sequence, across everything that
+    invalidates or bypasses a graph: the first (physical-state) call, a changed time step (re-capture), a reader of the physical
+    order in between (materialise -> plain call -> capture again), an eager correction, capacity growth, and both pointer flavours."""
+    c = cases.build_case(name)
+    oracle.complete_mesh(c.mesh)
+    dm = gpu.DeviceMesh(c.mesh)
+    hg = gpu.ParticleHandler2D(dm, c.level, graph_advect=1, capacity_factor=1.06)
+    hp = gpu.ParticleHandler2D(dm, c.level, graph_advect=-1, capacity_factor=1.06)
+    f, wg = dev_field(c)
+    wp = (torch.zeros_like(f[0]), torch.zeros_like(f[0]))
+    table = torch.tensor([f[0].data_ptr(), f[1].data_ptr()], dtype=torch.int64, device="cuda")
+    for h in (hg, hp):
+        h.seed_particles()
+        h.init_particle_velocity(f)
+    for s in range(24):
+        dt = c.dt if s < 14 else 0.5 * c.dt  # a new time step: the graphs are captured again
+        for h, w in ((hg, wg), (hp, wp)):
+            if s % 5 == 4:
+                h.advect_particles_ptrs(table, dt, c.substeps)  # deviceVector<double*>::data flavour
+            else:
+                h.advect_particles(f, dt, c.substeps)
+            h.project_velocity_onto_grid(w)
+            h.correct_particle_velocity(f, w)
+        assert hg.get_particle_count() == hp.get_particle_count(), f"step {s}"
+        sg, sp = hg.stats(), hp.stats()
+        assert (sg["lost"], sg["added"], sg["movers"]) == (sp["lost"], sp["added"], sp["movers"]), f"step {s}"
+        assert rel_inf(wg[0].cpu().numpy(), wp[0].cpu().numpy()) <= REL_TOL and rel_inf(wg[1].cpu().numpy(), wp[1].cpu().numpy()) <= REL_TOL
+        if s == 8:  # a reader of the physical order: the next advect starts from the identity permutation, without a graph
+            assert_states_equal(hg.download(), hp.download(), f"{name} step {s}")
+        if s == 11:  # getParticles applies the deferred correction eagerly: the next graph is captured without it
+            assert hg.get_particles().shape == hp.get_particles().shape
+    assert hg.stats()["capacity"] == hp.stats()["capacity"]
+    assert_states_equal(hg.download(), hp.download(), name)
+    hg.close()
+    hp.close()

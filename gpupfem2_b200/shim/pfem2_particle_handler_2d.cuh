@@ -55,6 +55,13 @@ public:
 private:
     void check(int rc, const char *what) const; // reference error behaviour: message on stderr + exit(EXIT_FAILURE)
 
+    // advectParticles' stdout line needs the new count, i.e. a wait for the whole advect.  The line is printed by the NEXT call
+    // into the handler instead (in the cases: projectVelocityOntoGrid, two statements later, with nothing printed in between:
+    // cases/Cylinder2D/main.cu:797-803), when the count has long arrived through the asynchronous read-back -- same text, same
+    // position in the output, no host stall inside advectParticles.
+    void flushCountLine() const;
+    mutable bool countLinePending = false;
+
     const Mesh2D *mesh;
     pfem2_handle *handle;
 };

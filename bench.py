@@ -426,10 +426,12 @@ def measure(args, rank, world, local, full):
         torch.cuda.synchronize()
         if multi:
             dist.barrier()
-        e2e_counts = []
+        e2e_counts, e2e_ms = [], []
         t0 = time.perf_counter()
         for k in range(args.steps):
-            e2e_counts.append(step_host())
+            t1 = time.perf_counter()
+            e2e_counts.append(step_host())  # (returns when the projected field and the count are on the host)
+            e2e_ms.append((time.perf_counter() - t1) * 1e3)
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t0
         if prev_affinity:
@@ -443,7 +445,8 @@ def measure(args, rank, world, local, full):
         else:
             e2e_ps = float(sum(e2e_counts))
         e2e = {"value": e2e_ps / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": t_e2e / args.steps * 1e3, "timing": "host clock around K calls, synchronised on both sides, max over ranks",
+               "ms_per_step": t_e2e / args.steps * 1e3, "ms_per_step_min": min(e2e_ms), "ms_per_step_median": statistics.median(e2e_ms),
+               "ms_per_step_max": max(e2e_ms), "timing": "host clock around K calls, synchronised on both sides, max over ranks",
                "host_cpus": ("bound to the GPU-local CPUs (NVML affinity)" if prev_affinity else "process default"), "api": api}
     mesh_bytes = sum(int(t_.numel()) * t_.element_size() for t_ in (dm.vertices, dm.cells, dm.inv_jacobi, dm.nbr_offsets, dm.nbr_indices))
     h.close()
@@ -456,7 +459,7 @@ def measure(args, rank, world, local, full):
     out = {
         "metric": "particle-steps/sec (advect+locate+sort+project+correct)", "value": value, "unit": "particle-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "ms_per_step_min": sm[0], "ms_per_step_median": statistics.median(sm),
+        "ms_per_step_min": sm[0], "ms_per_step_median": statistics.median(sm), "ms_per_step_list": [round(v, 3) for v in ms],
         "higher_is_better": True, "scaling": "weak" if args.workload in WEAK else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_description(args, world) + (f", strip-partitioned over {world} GPUs (quad columns)" if multi else ""),
                    "particles_mean": psteps / args.steps, "cells": dm.n_cells_global or dm.n_cells, "nodes": dm.n_nodes_global or dm.n_nodes,

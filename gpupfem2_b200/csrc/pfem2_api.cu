@@ -367,6 +367,14 @@ static void launch_move(pfem2_handle *h, bool lazy, double hsub, int substeps, i
 
 // split (strips, lazy + fused only): this call moves only the cells within reach of the strip boundaries -- every emigrant comes from
 // there --, so that the caller can send them and move the interior (advect_move_interior) while the delivery travels
+// Rows an advect may need beyond the live count: the re-seeds of the step (extrapolated from the last one), in a strip the
+// immigrants of both inboxes, and 3 % for good measure.  (The dense array of the lazy re-sort needs exactly count + immigrants +
+// re-seeds rows: the particles lost in the pass sit inside the first `count` rows.)
+static long long capacity_margin(const pfem2_handle *h)
+{
+    return std::max<long long>({(long long)h->host_count / 32, 4ll * h->host_added, 4096ll}) + 2ll * h->p2p.cap;
+}
+
 int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_count, bool mg_move, bool split)
 {
     if (!h) return PFEM2_EINVAL;
@@ -383,9 +391,8 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     // the gathered (lazy) pass needs the emigrant list in the strip-partitioned step: the unfused protocol searches the physical array
     const bool lazy = lazy_enabled(h) && (!mg_move || fused);
     if (!lazy && (rc = materialize(h))) return rc;
-    {   // capacity policy: keep room for the growth seen so far (re-seeding only ever adds).  In the lazy re-sort the dense
-        // array also holds the particles lost in the pass and the re-seeds / immigrants are appended behind it: twice the margin
-        const long long margin = (lazy ? 2 : 1) * std::max<long long>({(long long)h->host_count / 16, 4ll * h->host_added, 4096ll});
+    {   // capacity policy: keep room for the growth seen so far (re-seeding only ever adds)
+        const long long margin = capacity_margin(h);
         if ((long long)h->host_count + margin > h->capacity) {
             const long long want = std::max<long long>((long long)(1.25 * h->host_count), (long long)h->host_count + 2 * margin);
             if (want > 2147483647ll - 1024) return fail(h, PFEM2_ECAPACITY, "particle count exceeds 32-bit indexing");
@@ -626,8 +633,7 @@ static int advect_graphed(pfem2_handle *h, NodalVel vel, double dt, int substeps
     int rc;
     if ((rc = sync_counters(h))) return rc;
     {   // the capacity policy of advect_move: a call that has to grow runs the plain way
-        const long long margin = 2 * std::max<long long>({(long long)h->host_count / 16, 4ll * h->host_added, 4096ll});
-        if ((long long)h->host_count + margin > h->capacity) return PFEM2_OK;
+        if ((long long)h->host_count + capacity_margin(h) > h->capacity) return PFEM2_OK;
     }
     pfem2_handle::AdvectGraph &g = h->graphs[h->cur | (h->cs << 1) | (h->perm_buf << 2)];
     const bool match = g.exec && g.vx == vel.x && g.vy == vel.y && g.table == (const void *)vel.table && g.dt == dt && g.substeps == substeps &&

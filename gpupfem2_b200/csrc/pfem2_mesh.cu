@@ -43,14 +43,14 @@ int pfem2_sort_pairs(int n, int key_bits, unsigned *keys, unsigned *vals, unsign
     if (n < 0 || key_bits < 1 || key_bits > 32 || !keys || !vals || !keys_tmp || !vals_tmp || !result_in_tmp)
         return fail(nullptr, PFEM2_EINVAL, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    DeviceTemps tmp;
     int *n_dev = nullptr, *hist = nullptr, *scratch = nullptr;
-    CU(cudaMalloc((void **)&n_dev, 8 * sizeof(int)));
-    CU(cudaMalloc((void **)&hist, sizeof(int) * rs_hist_elems(std::max(n, 1))));
-    CU(cudaMalloc((void **)&scratch, sizeof(int) * rs_scan_scratch_elems(std::max(n, 1))));
+    CU(tmp.alloc(&n_dev, 8));
+    CU(tmp.alloc(&hist, rs_hist_elems(std::max(n, 1))));
+    CU(tmp.alloc(&scratch, rs_scan_scratch_elems(std::max(n, 1))));
     CU(cudaMemcpyAsync(n_dev, &n, sizeof(int), cudaMemcpyHostToDevice, st));
     *result_in_tmp = radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n_dev, n, key_bits, hist, scratch, n_dev + 4, st);
     CU(cudaStreamSynchronize(st));
-    cudaFree(n_dev); cudaFree(hist); cudaFree(scratch);
     CU(cudaGetLastError());
     return PFEM2_OK;
 }
@@ -61,36 +61,35 @@ int pfem2_mesh_one_ring(int n_nodes, int n_cells, const unsigned *d_cells, int *
     if (n_nodes <= 0 || n_cells <= 0 || !d_cells || !d_offsets || !nnz) return fail(nullptr, PFEM2_EINVAL, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int m = 3 * n_cells;
+    DeviceTemps tmp; // every temporary is freed on every exit path
     unsigned *k0, *k1, *v0, *v1;
-    int *count, *node_off, *n_dev, *hist, *scratch, *scratch2, *err;
-    CU(cudaMalloc((void **)&k0, sizeof(unsigned) * (size_t)m)); CU(cudaMalloc((void **)&k1, sizeof(unsigned) * (size_t)m));
-    CU(cudaMalloc((void **)&v0, sizeof(unsigned) * (size_t)m)); CU(cudaMalloc((void **)&v1, sizeof(unsigned) * (size_t)m));
-    CU(cudaMalloc((void **)&count, sizeof(int) * ((size_t)n_nodes + 1)));
-    CU(cudaMalloc((void **)&node_off, sizeof(int) * ((size_t)n_nodes + 1)));
-    CU(cudaMalloc((void **)&n_dev, sizeof(int))); CU(cudaMalloc((void **)&err, sizeof(int)));
-    CU(cudaMalloc((void **)&hist, sizeof(int) * rs_hist_elems(m)));
-    CU(cudaMalloc((void **)&scratch, sizeof(int) * rs_scan_scratch_elems(m)));
-    CU(cudaMalloc((void **)&scratch2, sizeof(int) * scan_scratch_elems<int>(std::max(n_nodes, n_cells))));
+    int *count, *node_off, *n_dev, *hist, *scratch, *scratch2, *err, *info, *len_dev;
+    CU(tmp.alloc(&k0, (size_t)m)); CU(tmp.alloc(&k1, (size_t)m));
+    CU(tmp.alloc(&v0, (size_t)m)); CU(tmp.alloc(&v1, (size_t)m));
+    CU(tmp.alloc(&count, (size_t)n_nodes + 1));
+    CU(tmp.alloc(&node_off, (size_t)n_nodes + 1));
+    CU(tmp.alloc(&n_dev, 1)); CU(tmp.alloc(&err, 1));
+    CU(tmp.alloc(&hist, rs_hist_elems(m)));
+    CU(tmp.alloc(&scratch, rs_scan_scratch_elems(m)));
+    CU(tmp.alloc(&scratch2, scan_scratch_elems<int>(std::max(n_nodes, n_cells))));
+    CU(tmp.alloc(&info, 4));
+    CU(tmp.alloc(&len_dev, 2));
     CU(cudaMemsetAsync(count, 0, sizeof(int) * ((size_t)n_nodes + 1), st));
     CU(cudaMemsetAsync(err, 0, sizeof(int), st));
     CU(cudaMemcpyAsync(n_dev, &m, sizeof(int), cudaMemcpyHostToDevice, st));
     PFEM2_LAUNCH(k_incidence_keys, grid_for(m, kThreads, 1 << 30), kThreads, 0, st, n_cells, d_cells, k0, v0, count);
     int bits = 1;
     while ((1ll << bits) < n_nodes) ++bits;
-    int *info;
-    CU(cudaMalloc((void **)&info, 4 * sizeof(int)));
     const int flip = radix_sort_pairs(k0, v0, k1, v1, n_dev, m, bits, hist, scratch, info, st);
     const unsigned *inc = flip ? v1 : v0;
-    int *len_dev;
-    CU(cudaMalloc((void **)&len_dev, 2 * sizeof(int)));
     {
         const int lens[2] = {n_nodes, n_cells};
         CU(cudaMemcpyAsync(len_dev, lens, sizeof lens, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st)); // `lens` is a stack temporary
     }
     exclusive_scan_dev<int>(count, node_off, len_dev, 1, 0, n_nodes, scratch2, st);
     if (!d_indices) {
-        int *counts = (int *)k0 == (int *)inc ? (int *)k1 : (int *)k0; // any free buffer of >= n_cells ints
-        counts = flip ? (int *)k0 : (int *)k1;
+        int *counts = flip ? (int *)k0 : (int *)k1; // the key buffer the sort did not end in: free, >= n_cells ints
         PFEM2_LAUNCH(k_one_ring, grid_for(n_cells, 128, 1 << 30), 128, 0, st, n_cells, d_cells, node_off, inc, counts, nullptr, nullptr, err);
         exclusive_scan_dev<int>(counts, d_offsets, len_dev + 1, 1, 0, n_cells, scratch2, st);
     } else {
@@ -100,8 +99,6 @@ int pfem2_mesh_one_ring(int n_nodes, int n_cells, const unsigned *d_cells, int *
     CU(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(nnz, d_offsets + n_cells, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(count); cudaFree(node_off); cudaFree(n_dev);
-    cudaFree(err); cudaFree(hist); cudaFree(scratch); cudaFree(scratch2); cudaFree(len_dev); cudaFree(info);
     CU(cudaGetLastError());
     if (herr) return fail(nullptr, PFEM2_EINVAL, "a cell has more than 96 one-ring neighbours");
     return PFEM2_OK;

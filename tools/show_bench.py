@@ -9,7 +9,7 @@ for f in sys.argv[1:]:
         continue
     j = json.loads(ls[-1])
     e = j.get("e2e") or {}
-    print(f"{f}: N={j.get('n_gpus')} ms/step {j['ms_per_step']:.3f} (min {j.get('ms_per_step_min', 0):.3f}) {j['value'] / 1e9:.2f} G  e2e {e.get('ms_per_step', 0):.3f} ms  "
+    print(f"{f}: N={j.get('n_gpus')} ms/step {j['ms_per_step']:.3f} (min {j.get('ms_per_step_min', 0):.3f}) {j['value'] / 1e9:.2f} G  e2e {e.get('ms_per_step', 0):.3f} ms (min {e.get('ms_per_step_min', 0):.2f} med {e.get('ms_per_step_median', 0):.2f} max {e.get('ms_per_step_max', 0):.2f})  "
           f"launches/step {j['gpu_launches'] / j['steps']:.1f}  parity {j.get('parity_check')}  checksum {j.get('state_checksum', {}).get('value', [None] * 2)[:2]}")
     r = j["roofline"]
     print("    phases", {k: round(v["ms_per_step"], 3) for k, v in r["phases"].items()}, "kernel frac", round(r["frac"], 3), "step frac", round(r["step"]["frac"], 3),

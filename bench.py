@@ -94,7 +94,7 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=float(os.environ.get("PFEM2_BENCH_NVML_PERIOD", "0.05"))):
         import threading
 
         self.rows, self.skip, self.p, self.f = [], 0, None, None
@@ -295,17 +295,19 @@ def measure(args, rank, world, local, full):
     W = (torch.zeros_like(F[0]), torch.zeros_like(F[0]))
     lazy = bool(int(os.environ.get("PFEM2_LAZY_SORT", "1")))  # A/B switch: 0 = physical re-sort in every advect
     opts = dict(max_division_level=8, capacity_factor=args.capacity_factor, lazy_sort=lazy)
-    if multi:
-        from gpupfem2_b200 import multi_gpu
+    def make_handler():
+        if multi:
+            from gpupfem2_b200 import multi_gpu
 
-        ny = WORKLOADS[args.workload][1]
-        bounds = multi_gpu.strip_bounds(dm.n_cells_global, world, align=2 * ny)
-        h = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world, **opts)
-        inner = h.h
-    else:
-        h = handler.ParticleHandler2D(dm, level, host_pipeline=int(os.environ.get("PFEM2_HOST_PIPELINE", "0")),
-                                      graph_advect=int(os.environ.get("PFEM2_GRAPH_ADVECT", "0")), **opts)
-        inner = h
+            ny = WORKLOADS[args.workload][1]
+            bounds = multi_gpu.strip_bounds(dm.n_cells_global, world, align=2 * ny)
+            hh = multi_gpu.DistributedParticleHandler2D(dm, level, bounds, rank, world, **opts)
+            return hh, hh.h
+        hh = handler.ParticleHandler2D(dm, level, host_pipeline=int(os.environ.get("PFEM2_HOST_PIPELINE", "0")),
+                                       graph_advect=int(os.environ.get("PFEM2_GRAPH_ADVECT", "0")), **opts)
+        return hh, hh
+
+    h, inner = make_handler()
     h.seed_particles()
     h.init_particle_velocity(F)
     torch.cuda.synchronize()
@@ -359,14 +361,13 @@ def measure(args, rank, world, local, full):
         h.get_particle_count()
     phases = inner.phase_times(reset=True)
     inner.set_profiling(False)
-    sent = h.last_sent if multi else 0
     checksum = h.state_checksum()  # order-independent, global (all-reduced over the strips): identical for every N
-    t = torch.tensor([total_ms, float(sum(counts)), float(sent)], dtype=torch.float64, device=device)
+    t = torch.tensor([total_ms, float(sum(counts)), float(h.last_sent if multi else 0)], dtype=torch.float64, device=device)
     if multi:
         tmax, tsum = t.clone(), t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, psteps, sent = float(tmax[0]), float(tsum[1]), float(tsum[2])
+        total_ms, psteps, sent_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
     else:
         psteps = float(sum(counts))
     value = psteps / (total_ms * 1e-3)
@@ -422,7 +423,17 @@ def measure(args, rank, world, local, full):
             h2d, d2h = 2 * dm.n_nodes * 8, 2 * dm.n_nodes * 8 + 32
             api = ("pfem2_step_host (C ABI), pinned host nodal buffers in, projected nodal field + count out; the call pipelines the upload "
                    "with the move pass and the projection with the download in chunks of the cell range (pfem2_options.host_pipeline)")
-        step_host()
+        # the SAME steps of the same simulation as the device-timed leg (the flow develops: particle count and cost per step grow
+        # with the step number), so that e2e and `value` differ by the host <-> device traffic only: a fresh handler, the same
+        # warm-up steps (untimed, through the same call), then the K timed steps
+        h.close()
+        del h, inner
+        torch.cuda.empty_cache()
+        h, inner = make_handler()
+        h.seed_particles()
+        h.init_particle_velocity(F)
+        for _ in range(args.warmup):
+            step_host()
         torch.cuda.synchronize()
         if multi:
             dist.barrier()
@@ -479,7 +490,7 @@ def measure(args, rank, world, local, full):
     if e2e:
         out["e2e"] = e2e
     if multi:
-        out["config"]["migrated_particles_per_step"] = sent
+        out["config"]["migrated_particles_per_step"] = sent_all
         out["config"]["migration_protocol"] = h_protocol_description(os.environ.get("PFEM2_MG_PROTOCOL", "p2p"))
     return out
 

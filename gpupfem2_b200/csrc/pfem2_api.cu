@@ -331,7 +331,8 @@ static void launch_move(pfem2_handle *h, bool lazy, double hsub, int substeps, i
     PFEM2_LAUNCH((k_move_gather<W, NSUB, SWZ>), grid, kAdvThreads, smem, st, h->gmap[src], h->omap[src ^ 1],                                \
                  (const int4 *)h->vals[h->perm_buf], h->keys[1], h->geom, h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, \
                  hsub, substeps, mode, C, h->ppc, h->level, h->sub_step, h->ctr, h->stay, h->cell_mask, dv2, h->own_lo, h->own_hi,         \
-                 h->mg_bounds, h->mg_ranks, h->mg_rank_count, emig, cstart, c_lo, c_hi, part)
+                 h->mg_bounds, h->mg_ranks, h->mg_rank_count, emig, cstart, c_lo, c_hi, part,                                              \
+                 h->tail_cursor + kTileCursor0 + 32 * (h->mv_launches++ & 31))
 #define PFEM2_MOVE_GATHER_W(W)                                                                                                            \
     do {                                                                                                                                  \
         if (!h->lazy_swizzle) PFEM2_MOVE_GATHER(W, 0, false);                                                                             \
@@ -414,11 +415,12 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
         CU(cudaMemsetAsync(h->cell_mask + lo, 0, sizeof(unsigned long long) * len, st));
     }
     h->mg_fused = fused;
+    h->mv_launches = 0; // (tile cursors of the gathered pass: zeroed by the launch that opens the advect, one per move launch)
     if (fused) do_count = 1;
     if (!h->v2) CU(cudaMalloc((void **)&h->v2, sizeof(double2) * (size_t)h->mesh.n_nodes));
     if ((rc = ensure_v2_node_range(h, substeps))) return rc;
     if (lazy) {
-        if (!h->tail_cursor) CU(cudaMalloc((void **)&h->tail_cursor, sizeof(int)));
+        if (!h->tail_cursor) CU(cudaMalloc((void **)&h->tail_cursor, sizeof(int) * (kTileCursor0 + kTileCursors)));
         if (!h->permuted) { // physically sorted (seed, upload, materialize): the identity permutation
             const int padded = (h->host_count + 31) & ~31;
             PFEM2_LAUNCH(k_iota, grid_for(padded), kThreads, 0, st, h->vals[h->perm_buf], h->ctr, padded);
@@ -1375,5 +1377,16 @@ int pfem2_set_owned_cells(pfem2_handle *h, int cell_lo, int cell_hi)
     }
     return PFEM2_OK;
 }
+
+#ifdef PFEM2_MOVE_TRACE
+// diagnosis build only (tools/trace_move.py): buffers for the per-warp / per-tile timing of the gathered move pass
+int pfem2_debug_move_trace(unsigned long long *warp_buf, uint4 *tile_buf)
+{
+    pfem2_handle *h = nullptr;
+    CU(cudaMemcpyToSymbol(g_trace_warp, &warp_buf, sizeof(warp_buf)));
+    CU(cudaMemcpyToSymbol(g_trace_tile, &tile_buf, sizeof(tile_buf)));
+    return PFEM2_OK;
+}
+#endif
 
 } // extern "C"

@@ -55,7 +55,8 @@ struct pfem2_handle {
     bool permuted = false;
     int perm_buf = 0;
     bool lazy_move = false;                  // the move pass in flight was the gathered one (advect_finish ranks instead of scattering)
-    int *tail_cursor = nullptr;              // device int: re-seeded records appended behind the dense array
+    int *tail_cursor = nullptr;              // device ints: [0] re-seeded records appended behind the dense array, then the tile cursors of the move pass
+    int mv_launches = 0;                     // launches of the gathered move pass inside the advect in flight (each has its own tile cursor)
     bool lazy_swizzle = true;                // PFEM2_LAZY_SWIZZLE=0: linear tiles (layout cross-check of the tests)
     bool lazy_nsub3 = true;                  // PFEM2_LAZY_NSUB3=0: runtime-S form of the move pass also for S = 3 (A/B)
     CUtensorMap gmap[2], omap[2];            // gather maps (box {16, 1}) and tile-store maps (box {16, 32}) of the two buffers

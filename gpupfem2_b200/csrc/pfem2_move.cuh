@@ -161,11 +161,39 @@ __device__ __forceinline__ int rank_of_cell(unsigned c, const int *__restrict__ 
 // that neither a counting nor a search pass over the whole array is needed afterwards.
 // ---------------------------------------------------------------------------------------------
 constexpr int kAdvTileBytes = 32 * (int)sizeof(ParticleRec); // one warp tile
+// device ints behind pfem2_handle::tail_cursor: [0] the cursor of the appended re-seeds, [kTileCursor0 + i] the tile cursor of the
+// i-th launch of the gathered move pass inside one advect (chunks of pfem2_step_host, parts of a split strip pass), 128 bytes apart
+constexpr int kTileCursor0 = 32, kTileCursors = 32 * 32;
+
+#ifdef PFEM2_MOVE_TRACE
+// diagnosis build (make variant NAME=trace DEFS=-DPFEM2_MOVE_TRACE, tools/trace_move.py): per-warp start / end time + SM of the gathered move
+// pass and the duration of every tile iteration, written to buffers handed in through pfem2_debug_move_trace
+static __device__ unsigned long long *g_trace_warp = nullptr; // [warps][4]: t_start, t_end (globaltimer ns), smid, tiles
+static __device__ uint4 *g_trace_tile = nullptr;              // [tiles]: ns in the four parts of the tile's iteration (top + issue, wait for the tile, move, store + statistics)
+__device__ __forceinline__ unsigned long long trace_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned trace_smid()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+#endif
 constexpr size_t advect_tma_smem_bytes(int threads) { return (size_t)(threads / 32) * (2 * kAdvTileBytes + 2 * sizeof(uint64_t)) + 1024; }
 
 // Block size / resident blocks per SM of the move pass, compile-time.  Swept on B200 (channel16m, ms per pass):
 // 256x4 8.42, 128x8 8.38, 64x16 8.45 (all 64 registers, 32 warps per SM); 192x5 8.67 (30 warps); 128x7 8.97 (72 registers, 28 warps);
 // 128x6 9.14 and 256x3 9.24 (80 registers, no spills, 24 warps): the pass is latency-bound, resident warps beat registers.
+// How the warps of the gathered move pass get their tiles: PFEM2_MOVE_GDYN = G > 0 (default 4): groups of G consecutive tiles through one
+// global cursor, every warp works at the front of the pass; 0: the fixed warp-strided share of round 2 (A/B: profiles/r03_summary.md).
+#ifndef PFEM2_MOVE_GDYN
+#define PFEM2_MOVE_GDYN 4
+#endif
+static_assert(PFEM2_MOVE_GDYN >= 0 && (PFEM2_MOVE_GDYN & (PFEM2_MOVE_GDYN - 1)) == 0, "PFEM2_MOVE_GDYN: 0 or a power of two");
 #ifndef PFEM2_ADV_THREADS
 #define PFEM2_ADV_THREADS 256
 #define PFEM2_ADV_MINB 4
@@ -387,7 +415,7 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
               int subcell_mode, int n_cells, int ppc, int level, double sub_step, Counters *ctr, int *__restrict__ stay,
               unsigned long long *__restrict__ cell_mask, const double2 *__restrict__ dV2, int own_lo, int own_hi,
               const int *__restrict__ rank_bounds, int n_ranks, int *__restrict__ rank_count, unsigned *__restrict__ emig_idx,
-              const int *__restrict__ chunk_start, int chunk_lo, int chunk_hi, int part)
+              const int *__restrict__ chunk_start, int chunk_lo, int chunk_hi, int part, int *__restrict__ tile_cursor)
 {
     // part = 1, 2, 3: split pass of a strip (multi-GPU).  With t1 = start of cell chunk_lo rounded UP to a tile and t2 = start of cell
     // chunk_hi rounded down (>= t1), part 1 moves the positions [0, t1) (every particle of the cells next to the left strip boundary),
@@ -405,6 +433,18 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
     const uint32_t smem = (smem_u32(adv_smem_raw) + 1023u) & ~1023u;
     const uint32_t tile0 = smem + (uint32_t)warp * (2 * kAdvTileBytes);
     const uint32_t bar0 = smem + (uint32_t)warps_per_block * (2 * kAdvTileBytes) + (uint32_t)warp * 16;
+#if PFEM2_MOVE_GDYN
+    // Tiles are handed out through ONE cursor in global memory (zeroed by the launch that opens the advect): every warp works at the
+    // front of the pass, where the cell records and nodal values it gathers were fetched moments ago by the warps on the neighbouring
+    // tiles.  With a fixed share per warp a warp that falls a few rounds behind that front loses those hits, gets slower (every level
+    // of its dependent gathers becomes a DRAM access: +2.2 us per tile measured), falls further behind and ends the pass up to 2.5 ms
+    // after everybody else (profiles/r03_summary.md).  Here a slow warp simply takes fewer tiles.  A claim is a group of G consecutive
+    // tiles (single tiles: 21.7 instead of 9.7 ms, the one address takes ~0.4 atomics per ns); the first group of a warp is a fixed one.
+    // A claim is made at least two iterations before its gather is issued, so the atomic's round trip is off the critical path: the
+    // raw claim waits in a register of lane 0, the two pending positions of the warp in shared memory (all lanes read them with one
+    // broadcast load each).
+    __shared__ int s_next[warps_per_block][2];
+#endif
     if (threadIdx.x == 0) s_mov = s_lost = 0;
     if (lane == 0) {
         mbar_init(bar0, 1);
@@ -426,14 +466,36 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
             if (chunk_hi < own_hi) n = min(__ldg(chunk_start + chunk_hi), n) & ~31; // (the last chunk of the owned range ends at the count)
         }
     }
-    const int first = p_lo + ((blockIdx.x * warps_per_block + warp) << 5);
     const int stride = (int)gridDim.x * (warps_per_block * 32);
+#if PFEM2_MOVE_GDYN
+    constexpr int kClaim = PFEM2_MOVE_GDYN;                 // consecutive tiles per claim (a power of two)
+    constexpr int kClaimLast = (kClaim - 1) << 5;           // (position - p_lo) & kClaimLast == kClaimLast: last tile of its group
+    const int first = p_lo + (((blockIdx.x * warps_per_block + warp) * kClaim) << 5); // group number `global warp` is the fixed one
+    const int dyn0 = p_lo + stride * kClaim;                // sorted position of claim 0
+    auto follow = [&](int pos, int claim) { return ((pos - p_lo) & kClaimLast) != kClaimLast ? pos + 32 : dyn0 + claim * (kClaim * 32); };
+#else
+    const int first = p_lo + ((blockIdx.x * warps_per_block + warp) << 5);
+#endif
     const uint32_t my0 = (uint32_t)lane * 64 + (SWZ ? ((((uint32_t)lane >> 1) & 3) << 4) : 0u);
     // Fetch of a tile = 8 gather4 operations.  The eight lanes 0..7 each hold the four row indices of "their" quarter-kilobyte and issue
     // one gather4 (the hardware instruction is warp-uniform: ptxas wraps a divergent issue in an elect / R2UR loop over the active lanes,
     // so this costs the same 8 UTMALDG as one lane issuing all eight), but the indices arrive with ONE coalesced 128-byte load per tile
     // that is issued an iteration ahead -- in the one-lane form each 16-byte index load sat right in front of the gather4 that consumed it
     // (the asm statements are memory barriers to the compiler): eight DRAM latencies in a row on the warp's critical path.
+#if PFEM2_MOVE_GDYN
+    const uint32_t slot = smem_u32(&s_next[warp][0]);
+    int pending = 0; // lane 0: the claimed group the warp turns to when it has taken the last tile of the one it is in
+    if (lane == 0) {
+        pending = atomicAdd(tile_cursor, 1);
+        const int p1 = kClaim > 1 ? first + 32 : dyn0 + pending * (kClaim * 32);
+        if (kClaim == 1) pending = atomicAdd(tile_cursor, 1);
+        const int p2 = kClaim > 2 ? first + 64 : dyn0 + pending * (kClaim * 32);
+        if (kClaim <= 2) pending = atomicAdd(tile_cursor, 1);
+        sts32(slot, (unsigned)p1);
+        sts32(slot + 4u, (unsigned)p2);
+    }
+    __syncwarp();
+#endif
     auto load_rows = [&](int base) { // indices of the tile at sorted position `base` (lanes 0..7), zeros otherwise
         int4 r = make_int4(0, 0, 0, 0);
         if (lane < 8 && base < n) r = __ldg(src + ((size_t)base >> 2) + lane);
@@ -442,24 +504,53 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
     auto issue = [&](int4 r, uint32_t buf, uint32_t bar) { // all lanes call; expect_tx was armed by lane 0 before the __syncwarp
         if (lane < 8) tma_gather4_rows(buf + (uint32_t)lane * 256u, &gmap, r, bar);
     };
+#ifdef PFEM2_MOVE_TRACE
+    const int trace_w = blockIdx.x * warps_per_block + warp;
+    if (lane == 0 && g_trace_warp) {
+        g_trace_warp[4 * trace_w + 0] = trace_now();
+        g_trace_warp[4 * trace_w + 2] = trace_smid();
+        g_trace_warp[4 * trace_w + 3] = 0;
+    }
+#endif
     int4 rows = load_rows(first);
     if (first < n) {
         if (lane == 0) mbar_arrive_expect_tx(bar0, kAdvTileBytes);
         __syncwarp();
         issue(rows, tile0, bar0);
     }
+#if PFEM2_MOVE_GDYN
+    rows = load_rows((int)lds32(slot));
+#else
     rows = load_rows(first + stride); // for the fetch at the top of the first iteration
+#endif
     uint32_t b = 0, par = 0;
+#if PFEM2_MOVE_GDYN
+    for (int base = first, nxt_base; base < n; base = nxt_base) {
+#else
     for (int base = first; base < n; base += stride) {
+#endif
+#ifdef PFEM2_MOVE_TRACE
+        const unsigned trace_t0 = (unsigned)trace_now();
+#endif
         const uint32_t buf = tile0 + b * kAdvTileBytes;
+#if PFEM2_MOVE_GDYN
+        const int nxt = (int)lds32(slot);
+#else
         const int nxt = base + stride;
+#endif
         if (lane == 0) {
             bulk_wait_group_read<0>(); // the other buffer's store (previous iteration) has finished reading shared memory
             if (nxt < n) mbar_arrive_expect_tx(bar0 + (b ^ 1) * 8, kAdvTileBytes);
         }
         __syncwarp(); // lanes 1..7 write into that buffer too: behind lane 0's wait
         if (nxt < n) issue(rows, tile0 + (b ^ 1) * kAdvTileBytes, bar0 + (b ^ 1) * 8);
+#ifdef PFEM2_MOVE_TRACE
+        const unsigned trace_t1 = (unsigned)trace_now();
+#endif
         mbar_wait(bar0 + b * 8, par);
+#ifdef PFEM2_MOVE_TRACE
+        const unsigned trace_t2 = (unsigned)trace_now();
+#endif
         par ^= b;
         b ^= 1;
         const int i = base + lane;
@@ -469,6 +560,10 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
         int moved = 0;
         bool lost = false;
         if (valid) move_record<WALK, NSUB>(buf + my0, geom, edge_nbr, nbr_off, nbr_idx, V2, dV2, h, substeps, c, L0, L1, L2, moved, lost);
+#ifdef PFEM2_MOVE_TRACE
+        __syncwarp();
+        const unsigned trace_t3 = (unsigned)trace_now();
+#endif
         bool live = valid && !lost;
         if (list_emigrant(live, c, i, own_lo, own_hi, rank_bounds, n_ranks, rank_count, emig_idx)) live = false; // row i of the dense output
         // the dense key array of the rank pass: one coalesced 128-byte store per tile (padding lanes, lost particles and emigrants: kLostCell)
@@ -479,7 +574,23 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
             tma_store_tile_2d(&tmap_out, 0, base, buf);
             bulk_commit_group();
         }
+#if PFEM2_MOVE_GDYN
+        {   // indices of the tile after the next; the pending positions move up, the claim of the previous iteration becomes a position
+            // and one more tile is claimed
+            nxt_base = (int)lds32(slot);
+            const int nn = (int)lds32(slot + 4u);
+            rows = load_rows(nn);
+            __syncwarp(); // (every lane has read the slots)
+            if (lane == 0) {
+                sts32(slot, (unsigned)nn);
+                sts32(slot + 4u, (unsigned)follow(nn, pending));
+                if (((nn - p_lo) & kClaimLast) == kClaimLast) pending = atomicAdd(tile_cursor, 1); // (used at the earliest kClaim iterations from now)
+            }
+            __syncwarp();
+        }
+#else
         rows = load_rows(nxt + stride); // indices of the tile after the next: in flight during the statistics, consumed at the next loop top
+#endif
         // the fast order only needs the number of survivors per cell (stayers + arrivals, accumulate_cell_stats with arrive == nullptr),
         // so the cell the particle started in is not carried through the substep loop
         const unsigned sb = __ballot_sync(0xffffffffu, live), mb = 0u;
@@ -491,7 +602,16 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
         }
         accumulate_cell_stats(subcell_mode, live, c, L0, L1, L2, sb, mb, lane, n_cells, ppc, level, sub_step, stay, (int *)nullptr,
                                                     cell_mask);
+#ifdef PFEM2_MOVE_TRACE
+        if (lane == 0 && g_trace_tile) {
+            g_trace_tile[base >> 5] = make_uint4(trace_t1 - trace_t0, trace_t2 - trace_t1, trace_t3 - trace_t2, (unsigned)trace_now() - trace_t3);
+            g_trace_warp[4 * trace_w + 3] += 1;
+        }
+#endif
     }
+#ifdef PFEM2_MOVE_TRACE
+    if (lane == 0 && g_trace_warp) g_trace_warp[4 * trace_w + 1] = trace_now();
+#endif
     if (lane == 0) bulk_wait_group<0>();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -522,7 +642,8 @@ k_pack_nodal(int node_lo, int node_hi, NodalVel vel, double2 *__restrict__ V2, C
         begin_ctr->n_old = begin_ctr->count;
         begin_ctr->n_warps = (begin_ctr->count + 31) >> 5;
         for (int k = 0; k < n_rank_count; ++k) rank_count[k] = 0;
-        if (tail_cursor) *tail_cursor = 0;
+        if (tail_cursor) // [0]: appended re-seeds; [kTileCursor0 ..): tile cursors of the move launches of this advect
+            for (int k = 0; k < kTileCursor0 + kTileCursors; ++k) tail_cursor[k] = 0;
     }
     const double *Vx, *Vy;
     vel.resolve(Vx, Vy);

@@ -47,7 +47,7 @@ ALG_BYTES = {  # algorithmic bytes per particle per launch (64 B fp
     "project_cells": 44,  # R(L,cell,v)
 }
 ALG_BYTES_STEP = 192  # the three calls as separate passes (88 + 44 + 60); the reference point of roofline.step
-TRAFFIC_FILE = "r02_traffic.json"  # committed ncu --set full capture of the HEAD kernels (tools/traffic_from_ncu.py)
+TRAFFIC_FILE = "r03_traffic.json"  # committed ncu --set full capture of the HEAD kernels (tools/traffic_from_ncu.py)
 
 WORKLOADS = {
     # name: (nx, ny, lx, ly, default level)

@@ -327,20 +327,31 @@ static void launch_move(pfem2_handle *h, bool lazy, double hsub, int substeps, i
     unsigned *emig = h->mg_fused ? h->keys[0] : nullptr;
     cudaStream_t st = h->stream;
     if (lazy) {
-#define PFEM2_MOVE_GATHER(W, NSUB, SWZ)                                                                                                   \
-    PFEM2_LAUNCH((k_move_gather<W, NSUB, SWZ>), grid, kAdvThreads, smem, st, h->gmap[src], h->omap[src ^ 1],                                \
+        // tiles per claim of the global tile cursor: groups when every warp of the grid gets several of them, single tiles otherwise (a
+        // small pass -- the shipped meshes, one chunk of a small strip -- would leave most warps without a group)
+        const long long tiles = ((long long)h->host_count + 31) / 32 / std::max(1, h->pipe.active ? h->pipe.K : 1);
+        constexpr int kGroup = PFEM2_MOVE_GDYN > 0 ? PFEM2_MOVE_GDYN : 1;
+        const bool groups = part != 1 && part != 3 && tiles > (long long)grid * (kAdvThreads / 32) * kGroup;
+#define PFEM2_MOVE_GATHER(W, NSUB, SWZ, CLAIM)                                                                                            \
+    PFEM2_LAUNCH((k_move_gather<W, NSUB, SWZ, CLAIM>), grid, kAdvThreads, smem, st, h->gmap[src], h->omap[src ^ 1],                         \
                  (const int4 *)h->vals[h->perm_buf], h->keys[1], h->geom, h->edge_nbr, h->mesh.d_nbr_offsets, h->mesh.d_nbr_indices, h->v2, \
                  hsub, substeps, mode, C, h->ppc, h->level, h->sub_step, h->ctr, h->stay, h->cell_mask, dv2, h->own_lo, h->own_hi,         \
                  h->mg_bounds, h->mg_ranks, h->mg_rank_count, emig, cstart, c_lo, c_hi, part,                                              \
                  h->tail_cursor + kTileCursor0 + 32 * (h->mv_launches++ & 31))
+#define PFEM2_MOVE_GATHER_C(W, CLAIM)                                                                                                     \
+    do {                                                                                                                                  \
+        if (!h->lazy_swizzle) PFEM2_MOVE_GATHER(W, 0, false, CLAIM);                                                                      \
+        else if (substeps == 3 && h->lazy_nsub3) PFEM2_MOVE_GATHER(W, 3, true, CLAIM);                                                    \
+        else PFEM2_MOVE_GATHER(W, 0, true, CLAIM);                                                                                        \
+    } while (0)
 #define PFEM2_MOVE_GATHER_W(W)                                                                                                            \
     do {                                                                                                                                  \
-        if (!h->lazy_swizzle) PFEM2_MOVE_GATHER(W, 0, false);                                                                             \
-        else if (substeps == 3 && h->lazy_nsub3) PFEM2_MOVE_GATHER(W, 3, true);                                                           \
-        else PFEM2_MOVE_GATHER(W, 0, true);                                                                                               \
+        if (groups) PFEM2_MOVE_GATHER_C(W, kGroup);                                                                                       \
+        else PFEM2_MOVE_GATHER_C(W, 1);                                                                                                   \
     } while (0)
         if (walk) PFEM2_MOVE_GATHER_W(true);
         else PFEM2_MOVE_GATHER_W(false);
+#undef PFEM2_MOVE_GATHER_C
 #undef PFEM2_MOVE_GATHER_W
 #undef PFEM2_MOVE_GATHER
         return;
@@ -552,7 +563,9 @@ static int rank_and_reseed(pfem2_handle *h, NodalVel vel)
     const int lo = h->own_lo, hi = h->own_hi, own_n = hi - lo;
     launch_plan(h, true, true);
     unsigned *src_new = h->vals[h->perm_buf ^ 1];
-    PFEM2_LAUNCH(k_rank, grid_for(h->capacity), kThreads, 0, st, (const unsigned *)h->keys[1], (const int *)&h->ctr->n_old, h->cursor, src_new,
+    // one pass per warp (1024 keys per block) in the hardware's block order, like the projection: 0.1 ms faster than 16 blocks per SM
+    // striding over the array (the blocks in flight write one window of the permutation)
+    PFEM2_LAUNCH(k_rank, grid_for(((long long)h->host_count + h->host_added + 3) / 4 + kThreads, kThreads, 1 << 30), kThreads, 0, st, (const unsigned *)h->keys[1], (const int *)&h->ctr->n_old, h->cursor, src_new,
                  h->ctr);
     PFEM2_LAUNCH(k_reseed_lazy, grid_for(own_n + 1, kThreads, 1 << 30), kThreads, 0, st, lo, hi, h->ppc, (const double2 *)h->mesh.d_vertices,
                  h->geom, h->centers, vel, h->cell_mask, h->stay, h->packed, h->soa[h->cur], (const int *)&h->ctr->n_old, h->tail_cursor,
@@ -738,13 +751,17 @@ void launch_project_cells(pfem2_handle *h, int c_lo, int c_hi)
     const long long nc = c_hi - c_lo;
     const int *cs = h->cell_start[h->cs];
     // lanes per cell: about a quarter of the nominal segment length, so each lane keeps several loads in flight
+    // One block per 256 / G cells, in the hardware's block order: the blocks in flight work on one contiguous window of the sorted
+    // order (3.0 ms on channel16m; as 16 resident-size blocks per SM striding over the cells 3.5 ms -- 3.2 waves with a 20 % tail -- and
+    // 3.3 ms with exactly 5 or 10 per SM: profiles/r03_summary.md §4)
+    const int max_blocks = 1 << 30;
 #define PFEM2_PROJECT(G)                                                                                                                   \
     do {                                                                                                                                   \
         if (h->permuted) /* lazy re-sort: the segment [cell_start[c], cell_start[c + 1]) names its records through the permutation */      \
-            PFEM2_LAUNCH(k_project_cells_lazy<G>, grid_for(nc * G), kThreads, 0, st, c_lo, c_hi, p, (const unsigned *)h->vals[h->perm_buf], cs, \
-                         h->partial);                                                                                                      \
+            PFEM2_LAUNCH(k_project_cells_lazy<G>, grid_for(nc * G, kThreads, max_blocks), kThreads, 0, st, c_lo, c_hi, p,                  \
+                         (const unsigned *)h->vals[h->perm_buf], cs, h->partial);                                                          \
         else                                                                                                                               \
-            PFEM2_LAUNCH(k_project_cells<G>, grid_for(nc * G), kThreads, 0, st, c_lo, c_hi, p, cs, h->partial);                             \
+            PFEM2_LAUNCH(k_project_cells<G>, grid_for(nc * G, kThreads, max_blocks), kThreads, 0, st, c_lo, c_hi, p, cs, h->partial);      \
     } while (0)
     if (ppc <= 4) PFEM2_PROJECT(2);
     else if (ppc <= 16) PFEM2_PROJECT(4);

@@ -407,7 +407,7 @@ k_move_tiles(const __grid_constant__ CUtensorMap tmap, const CellGeom *__restric
 // profiles/r02a_gather4_swizzle.log and the parity tests in both layouts).
 // SWZ = false (PFEM2_LAZY_SWIZZLE=0): both maps are encoded without swizzle and lane r reads its record at r * 64 (4-way bank
 // conflicts on the shared-memory side; 15.4 instead of 14.3 ms per step): kept as the layout-independent cross-check of the tests.
-template <bool WALK, int NSUB, bool SWZ>
+template <bool WALK, int NSUB, bool SWZ, int CLAIM>
 __global__ void __launch_bounds__(kAdvThreads, kAdvBlocksPerSM)
 k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap tmap_out, const int4 *__restrict__ src,
               unsigned *__restrict__ keys, const CellGeom *__restrict__ geom, const int4 *__restrict__ edge_nbr,
@@ -468,10 +468,13 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
     }
     const int stride = (int)gridDim.x * (warps_per_block * 32);
 #if PFEM2_MOVE_GDYN
-    constexpr int kClaim = PFEM2_MOVE_GDYN;                 // consecutive tiles per claim (a power of two)
-    constexpr int kClaimLast = (kClaim - 1) << 5;           // (position - p_lo) & kClaimLast == kClaimLast: last tile of its group
+    // CLAIM consecutive tiles per claim: PFEM2_MOVE_GDYN for passes of many tiles per warp, single tiles (host's choice) when the pass
+    // has so few tiles that groups would leave warps without work
+    constexpr int kClaim = CLAIM, kClaimLog2 = CLAIM == 1 ? 0 : (CLAIM == 2 ? 1 : (CLAIM == 4 ? 2 : 3));
+    static_assert((1 << kClaimLog2) == kClaim, "CLAIM: 1, 2, 4 or 8 tiles");
+    constexpr int kClaimLast = (kClaim - 1) << 5;            // (position - p_lo) & kClaimLast == kClaimLast: last tile of its group
     const int first = p_lo + (((blockIdx.x * warps_per_block + warp) * kClaim) << 5); // group number `global warp` is the fixed one
-    const int dyn0 = p_lo + stride * kClaim;                // sorted position of claim 0
+    const int dyn0 = p_lo + stride * kClaim;                 // sorted position of claim 0
     auto follow = [&](int pos, int claim) { return ((pos - p_lo) & kClaimLast) != kClaimLast ? pos + 32 : dyn0 + claim * (kClaim * 32); };
 #else
     const int first = p_lo + ((blockIdx.x * warps_per_block + warp) << 5);
@@ -486,11 +489,11 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
     const uint32_t slot = smem_u32(&s_next[warp][0]);
     int pending = 0; // lane 0: the claimed group the warp turns to when it has taken the last tile of the one it is in
     if (lane == 0) {
-        pending = atomicAdd(tile_cursor, 1);
-        const int p1 = kClaim > 1 ? first + 32 : dyn0 + pending * (kClaim * 32);
-        if (kClaim == 1) pending = atomicAdd(tile_cursor, 1);
-        const int p2 = kClaim > 2 ? first + 64 : dyn0 + pending * (kClaim * 32);
-        if (kClaim <= 2) pending = atomicAdd(tile_cursor, 1);
+        // the claims the first two pending positions use up (groups of 1 / 2 / >= 4 tiles: 2 / 1 / 0) and the one that waits, in ONE atomic
+        pending = atomicAdd(tile_cursor, kClaim == 1 ? 3 : (kClaim == 2 ? 2 : 1));
+        const int p1 = kClaim > 1 ? first + 32 : dyn0 + pending * 32;
+        const int p2 = kClaim > 2 ? first + 64 : (kClaim == 2 ? dyn0 + pending * 64 : dyn0 + (pending + 1) * 32);
+        if (kClaim <= 2) pending += kClaim == 1 ? 2 : 1;
         sts32(slot, (unsigned)p1);
         sts32(slot + 4u, (unsigned)p2);
     }
@@ -584,7 +587,7 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
             if (lane == 0) {
                 sts32(slot, (unsigned)nn);
                 sts32(slot + 4u, (unsigned)follow(nn, pending));
-                if (((nn - p_lo) & kClaimLast) == kClaimLast) pending = atomicAdd(tile_cursor, 1); // (used at the earliest kClaim iterations from now)
+                if (((nn - p_lo) & kClaimLast) == kClaimLast) pending = atomicAdd(tile_cursor, 1); // (used one group of iterations from now)
             }
             __syncwarp();
         }
@@ -642,8 +645,10 @@ k_pack_nodal(int node_lo, int node_hi, NodalVel vel, double2 *__restrict__ V2, C
         begin_ctr->n_old = begin_ctr->count;
         begin_ctr->n_warps = (begin_ctr->count + 31) >> 5;
         for (int k = 0; k < n_rank_count; ++k) rank_count[k] = 0;
-        if (tail_cursor) // [0]: appended re-seeds; [kTileCursor0 ..): tile cursors of the move launches of this advect
-            for (int k = 0; k < kTileCursor0 + kTileCursors; ++k) tail_cursor[k] = 0;
+        if (tail_cursor) { // [0]: appended re-seeds; [kTileCursor0 + 32 i]: tile cursor of the i-th move launch of this advect
+            *tail_cursor = 0;
+            for (int k = 0; k < 32; ++k) tail_cursor[kTileCursor0 + 32 * k] = 0;
+        }
     }
     const double *Vx, *Vy;
     vel.resolve(Vx, Vy);

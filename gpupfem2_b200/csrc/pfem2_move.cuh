@@ -261,6 +261,16 @@ __device__ __forceinline__ void move_record(uint32_t sa0, const CellGeom *__rest
     }
 }
 
+// One thread's atomic add whose result is NOT needed right away.  atomicAdd() inside `if (lane == 0)` is compiled as a warp-aggregated
+// atomic -- vote, leader's ATOMG, SHFL of the result -- and the shuffle waits for the round trip on the spot; the plain instruction
+// leaves the result in flight until its first use (measured neutral on channel16m: the wait overlapped the statistics of the tile).
+__device__ __forceinline__ int atom_add_in_flight(int *p, int v)
+{
+    int r;
+    asm volatile("atom.relaxed.gpu.global.add.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+    return r;
+}
+
 // multi-GPU: list an emigrant (rare: a handful per tile row at a strip interface); returns true if the particle left the owned range
 __device__ __forceinline__ bool list_emigrant(bool live, unsigned c, int row, int own_lo, int own_hi, const int *__restrict__ rank_bounds,
                                               int n_ranks, int *__restrict__ rank_count, unsigned *__restrict__ emig_idx)
@@ -490,7 +500,7 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
     int pending = 0; // lane 0: the claimed group the warp turns to when it has taken the last tile of the one it is in
     if (lane == 0) {
         // the claims the first two pending positions use up (groups of 1 / 2 / >= 4 tiles: 2 / 1 / 0) and the one that waits, in ONE atomic
-        pending = atomicAdd(tile_cursor, kClaim == 1 ? 3 : (kClaim == 2 ? 2 : 1));
+        pending = atom_add_in_flight(tile_cursor, kClaim == 1 ? 3 : (kClaim == 2 ? 2 : 1));
         const int p1 = kClaim > 1 ? first + 32 : dyn0 + pending * 32;
         const int p2 = kClaim > 2 ? first + 64 : (kClaim == 2 ? dyn0 + pending * 64 : dyn0 + (pending + 1) * 32);
         if (kClaim <= 2) pending += kClaim == 1 ? 2 : 1;
@@ -587,7 +597,7 @@ k_move_gather(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ 
             if (lane == 0) {
                 sts32(slot, (unsigned)nn);
                 sts32(slot + 4u, (unsigned)follow(nn, pending));
-                if (((nn - p_lo) & kClaimLast) == kClaimLast) pending = atomicAdd(tile_cursor, 1); // (used one group of iterations from now)
+                if (((nn - p_lo) & kClaimLast) == kClaimLast) pending = atom_add_in_flight(tile_cursor, 1); // (used one group of iterations from now)
             }
             __syncwarp();
         }

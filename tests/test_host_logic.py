@@ -165,3 +165,61 @@ def test_partitioned_mesh_slices_find_the_global_interface_nodes():
         for nb, idx in mine.items():
             assert abs(nb - r) == 1
             assert torch.equal(idx + node_base, glob[r][nb])
+
+
+def test_tile_claim_index_model():
+    """Index-level model of how the gathered move pass hands out its tiles (pfem2_move.cuh, k_move_gather with PFEM2_MOVE_GDYN): every
+    warp starts with the fixed group `global warp`, keeps two pending positions and one raw claim, and turns to a claimed group when it
+    has taken the last tile of the group it is in.  Whatever the order in which the warps advance, every tile of [p_lo, n) must be
+    taken exactly once and a claim must be at least two iterations old when its first tile becomes the current one."""
+    rng = np.random.default_rng(5)
+    for claim in (1, 2, 4, 8):
+        for warps, tiles, p_lo in ((8, 0, 0), (8, 5, 64), (8, 8 * claim, 0), (24, 1000, 32), (16, 777, 0), (4, 64 * claim + 3, 96)):
+            stride = warps * 32
+            n = p_lo + tiles * 32 - (7 if tiles else 0)  # a partial last tile
+            last = (claim - 1) << 5
+            dyn0 = p_lo + stride * claim
+            cursor = [0]
+
+            def atomic_add(v):
+                r = cursor[0]
+                cursor[0] += v
+                return r
+
+            def follow(pos, c):
+                return pos + 32 if ((pos - p_lo) & last) != last else dyn0 + c * (claim * 32)
+
+            class Warp:
+                def __init__(self, w):
+                    self.base = p_lo + ((w * claim) << 5)
+                    self.pending = atomic_add(3 if claim == 1 else (2 if claim == 2 else 1))
+                    self.claimed_at = -2  # (prologue claims are used at the earliest two iterations later by construction)
+                    self.it = 0
+                    p1 = self.base + 32 if claim > 1 else dyn0 + self.pending * 32
+                    p2 = self.base + 64 if claim > 2 else (dyn0 + self.pending * 64 if claim == 2 else dyn0 + (self.pending + 1) * 32)
+                    if claim <= 2:
+                        self.pending += 2 if claim == 1 else 1
+                    self.slot = [p1, p2]
+                    self.done = self.base >= n
+
+                def step(self, taken):
+                    taken.append(self.base)
+                    nxt, nn = self.slot
+                    self.slot = [nn, follow(nn, self.pending)]
+                    if ((nn - p_lo) & last) == last:  # the pending claim was consumed: it must not be younger than one iteration
+                        assert self.it - self.claimed_at >= 1
+                        self.pending = atomic_add(1)
+                        self.claimed_at = self.it
+                    self.it += 1
+                    self.base = nxt
+                    self.done = self.base >= n
+
+            ws = [Warp(w) for w in range(warps)]
+            taken = []
+            while True:
+                live = [w for w in ws if not w.done]
+                if not live:
+                    break
+                live[rng.integers(len(live))].step(taken)  # an arbitrary interleaving of the warps
+            want = list(range(p_lo, n, 32))
+            assert sorted(taken) == want, (claim, warps, tiles)

@@ -210,6 +210,61 @@ k_scatter_movers(ParticleSoA src, ParticleSoA dst, int n_cells, const int *__res
     }
 }
 
+// The new particles of the 32 cells of a warp (missing > 0 in the lanes whose cell needs some), one LANE PER NEW PARTICLE:
+// kAddParticlesToCell (:197-236), one particle at the centre of every empty sub-cell in ascending sub-cell order, velocity interpolated
+// from the current nodal field.  The cell of lane o gets the rows d(o) .. d(o) + missing(o) - 1 of `rec`; with src_new != nullptr
+// (lazy re-sort) their indices go to src_new[j(o) ..].  All 32 lanes must call.
+// (Forms measured before this one, stress case = 1.35 new particles per cell and step: one thread looping over its cell's sub-cells and
+// writing up to ppc 64-byte records on its own with an atomic per cell on the one cursor 0.83 ms; the needy cells of a warp served one
+// after the other by the whole warp, one atomic per warp 0.32 ms; profiles/r03_summary.md §7.)
+__device__ __forceinline__ void reseed_cells_of_warp(int c, int missing, int d, int j, unsigned long long mask, int ppc,
+                                                     const double2 *__restrict__ vertices, const CellGeom *__restrict__ geom,
+                                                     const double *__restrict__ centers, NodalVel vel, const ParticleSoA &rec,
+                                                     unsigned *__restrict__ src_new)
+{
+    const int lane = threadIdx.x & 31;
+    int incl = missing; // inclusive prefix sums of `missing` over the lanes: new particle k of the warp belongs to the lane o with excl(o) <= k < incl(o)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    const int excl = incl - missing;
+    const double *Vx, *Vy;
+    vel.resolve(Vx, Vy);
+    const unsigned long long full = ppc >= 64 ? ~0ull : ((1ull << ppc) - 1ull);
+    for (int k0 = 0; k0 < total; k0 += 32) {
+        const int k = k0 + lane;
+        int o = 0; // binary search over the lanes' inclusive sums (every lane takes part in the shuffles)
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (__shfl_sync(0xffffffffu, incl, o + step - 1) <= k) o += step;
+        o = min(o, 31);
+        const int cc = __shfl_sync(0xffffffffu, c, o), d0 = __shfl_sync(0xffffffffu, d, o), j0 = __shfl_sync(0xffffffffu, j, o);
+        const int r = k - __shfl_sync(0xffffffffu, excl, o); // rank among the cell's empty sub-cells
+        const unsigned long long m = ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(mask >> 32), o) << 32) |
+                                     __shfl_sync(0xffffffffu, (unsigned)mask, o);
+        if (k >= total) continue;
+        const unsigned long long empty = ~m & full;
+        const unsigned lo = (unsigned)empty, hi = (unsigned)(empty >> 32);
+        const int nlo = __popc(lo);
+        const int s = r < nlo ? (int)__fns(lo, 0, r + 1) : 32 + (int)__fns(hi, 0, r - nlo + 1); // the r-th empty sub-cell
+        const uint4 nn = __ldg(reinterpret_cast<const uint4 *>(&geom[cc].n0));
+        const double2 v0 = __ldg(&vertices[nn.x]), v1 = __ldg(&vertices[nn.y]), v2 = __ldg(&vertices[nn.z]);
+        const double ax0 = __ldg(Vx + nn.x), ax1 = __ldg(Vx + nn.y), ax2 = __ldg(Vx + nn.z);
+        const double ay0 = __ldg(Vy + nn.x), ay1 = __ldg(Vy + nn.y), ay2 = __ldg(Vy + nn.z);
+        const double L0 = __ldg(&centers[3 * s]), L1 = __ldg(&centers[3 * s + 1]), L2 = __ldg(&centers[3 * s + 2]);
+        const int row = d0 + r;
+        rec.pos[row] = make_double2(to_global1(L0, L1, L2, v0.x, v1.x, v2.x), to_global1(L0, L1, L2, v0.y, v1.y, v2.y));
+        rec.lab[row] = make_double2(L0, L1);
+        st_tail(rec.tail + row, L2, (unsigned)cc, (unsigned)row);
+        rec.vel[row] = make_double2(interp3(L0, L1, L2, ax0, ax1, ax2), interp3(L0, L1, L2, ay0, ay1, ay2));
+        if (src_new) src_new[j0 + r] = (unsigned)row;
+    }
+}
+
 // kAddParticlesToCell (:197-236): one new particle at the centre of every empty sub-cell, velocity
 // interpolated from the current nodal field; written right behind the cell's survivors.  Also
 // materialises the segment table cell_start[].
@@ -220,30 +275,19 @@ k_reseed(int own_lo, int own_hi, int ppc, const double2 *__restrict__ vertices, 
          ParticleSoA dst, int *__restrict__ cell_start, const Counters *ctr)
 {
     const int c = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > own_hi) return;
-    const int start = (int)(unsigned)(packed_start[c] & 0xffffffffull);
-    cell_start[c] = start;
-    if (c == own_hi || ctr->overflow) return;
-    const int live = stay[c] + arrive[c];
-    const int missing = (int)(unsigned)(packed_start[c + 1] & 0xffffffffull) - start - live;
-    if (missing <= 0) return;
-    const double *Vx, *Vy;
-    vel.resolve(Vx, Vy);
-    const uint4 nn = __ldg(reinterpret_cast<const uint4 *>(&geom[c].n0));
-    const double2 v0 = __ldg(&vertices[nn.x]), v1 = __ldg(&vertices[nn.y]), v2 = __ldg(&vertices[nn.z]);
-    const double ax0 = __ldg(Vx + nn.x), ax1 = __ldg(Vx + nn.y), ax2 = __ldg(Vx + nn.z);
-    const double ay0 = __ldg(Vy + nn.x), ay1 = __ldg(Vy + nn.y), ay2 = __ldg(Vy + nn.z);
-    const unsigned long long mask = cell_mask[c];
-    int d = start + live;
-    for (int s = 0; s < ppc; ++s) {
-        if ((mask >> s) & 1ull) continue;
-        const double L0 = __ldg(&centers[3 * s]), L1 = __ldg(&centers[3 * s + 1]), L2 = __ldg(&centers[3 * s + 2]);
-        dst.pos[d] = make_double2(to_global1(L0, L1, L2, v0.x, v1.x, v2.x), to_global1(L0, L1, L2, v0.y, v1.y, v2.y));
-        dst.lab[d] = make_double2(L0, L1);
-        st_tail(dst.tail + d, L2, (unsigned)c, (unsigned)d);
-        dst.vel[d] = make_double2(interp3(L0, L1, L2, ax0, ax1, ax2), interp3(L0, L1, L2, ay0, ay1, ay2));
-        ++d;
+    int missing = 0, d = 0;
+    unsigned long long mask = 0;
+    if (c <= own_hi) {
+        const int start = (int)(unsigned)(packed_start[c] & 0xffffffffull);
+        cell_start[c] = start;
+        if (c < own_hi && !ctr->overflow) {
+            const int live = stay[c] + arrive[c];
+            missing = max((int)(unsigned)(packed_start[c + 1] & 0xffffffffull) - start - live, 0);
+            mask = missing ? cell_mask[c] : 0ull;
+            d = start + live; // right behind the cell's survivors
+        }
     }
+    reseed_cells_of_warp(c, missing, d, 0, mask, ppc, vertices, geom, centers, vel, dst, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -296,41 +340,46 @@ k_reseed_lazy(int own_lo, int own_hi, int ppc, const double2 *__restrict__ verti
               const unsigned long long *__restrict__ packed_start, ParticleSoA rec, const int *__restrict__ n_old_ptr, int *__restrict__ tail_cursor,
               unsigned *__restrict__ src_new, int *__restrict__ cell_start, const Counters *ctr)
 {
+    // one lane per cell finds out what its cell needs, then the whole warp serves the needy cells (reseed_cells_of_warp)
     const int c = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > own_hi) return;
-    const int start = (int)(unsigned)(packed_start[c] & 0xffffffffull);
-    cell_start[c] = start;
-    if (ctr->overflow) return; // (the plan found more live particles than the capacity: `start` may lie behind src_new[])
-    if (c == own_hi) { // behind the last sorted position: pad to a whole tile with a valid row
-        for (int j = start; j < ((start + 31) & ~31); ++j) src_new[j] = 0u;
+    int missing = 0, d = 0, j = 0;
+    unsigned long long mask = 0;
+    if (c <= own_hi) {
+        const int start = (int)(unsigned)(packed_start[c] & 0xffffffffull);
+        cell_start[c] = start;
+        if (!ctr->overflow) { // (the plan found more live particles than the capacity: `start` may lie behind src_new[])
+            if (c == own_hi) { // behind the last sorted position: pad to a whole tile with a valid row
+                for (int k = start; k < ((start + 31) & ~31); ++k) src_new[k] = 0u;
+            } else {
+                const int live = stay[c]; // fast order: everybody was counted into stay[]
+                missing = max((int)(unsigned)(packed_start[c + 1] & 0xffffffffull) - start - live, 0);
+                if (missing) {
+                    mask = cell_mask[c];
+                    j = start + live;
+                }
+            }
+        }
+    }
+    // rows behind the array for the whole warp with ONE atomic (an atomic per needy cell on the one cursor was what the kernel waited
+    // for: one address takes ~0.4 atomics per ns, profiles/r03_summary.md §7)
+    const int lane = threadIdx.x & 31;
+    int incl = missing;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = *n_old_ptr + atomicAdd(tail_cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if ((long long)base + total > ctr->capacity) { // (the plan only checked the number of live particles; the dense array also holds the lost ones)
+        if (lane == 31) atomicExch(const_cast<int *>(&ctr->overflow), 1);
         return;
     }
-    const int live = stay[c]; // fast order: everybody was counted into stay[]
-    const int missing = (int)(unsigned)(packed_start[c + 1] & 0xffffffffull) - start - live;
-    if (missing <= 0) return;
-    const double *Vx, *Vy;
-    vel.resolve(Vx, Vy);
-    const uint4 nn = __ldg(reinterpret_cast<const uint4 *>(&geom[c].n0));
-    const double2 v0 = __ldg(&vertices[nn.x]), v1 = __ldg(&vertices[nn.y]), v2 = __ldg(&vertices[nn.z]);
-    const double ax0 = __ldg(Vx + nn.x), ax1 = __ldg(Vx + nn.y), ax2 = __ldg(Vx + nn.z);
-    const double ay0 = __ldg(Vy + nn.x), ay1 = __ldg(Vy + nn.y), ay2 = __ldg(Vy + nn.z);
-    const unsigned long long mask = cell_mask[c];
-    int d = *n_old_ptr + atomicAdd(tail_cursor, missing); // a block of `missing` records behind the array
-    if ((long long)d + missing > ctr->capacity) { // (the plan only checked the number of live particles; the dense array also holds the lost ones)
-        atomicExch(const_cast<int *>(&ctr->overflow), 1);
-        return;
-    }
-    int j = start + live;
-    for (int s = 0; s < ppc; ++s) {
-        if ((mask >> s) & 1ull) continue;
-        const double L0 = __ldg(&centers[3 * s]), L1 = __ldg(&centers[3 * s + 1]), L2 = __ldg(&centers[3 * s + 2]);
-        rec.pos[d] = make_double2(to_global1(L0, L1, L2, v0.x, v1.x, v2.x), to_global1(L0, L1, L2, v0.y, v1.y, v2.y));
-        rec.lab[d] = make_double2(L0, L1);
-        st_tail(rec.tail + d, L2, (unsigned)c, (unsigned)d);
-        rec.vel[d] = make_double2(interp3(L0, L1, L2, ax0, ax1, ax2), interp3(L0, L1, L2, ay0, ay1, ay2));
-        src_new[j++] = (unsigned)d;
-        ++d;
-    }
+    d = base + incl - missing;
+    reseed_cells_of_warp(c, missing, d, j, mask, ppc, vertices, geom, centers, vel, rec, src_new);
 }
 
 

@@ -169,6 +169,18 @@ def test_checksum_of_checksums_between_kernel_variants(gpu):
         # field, whose last bits depend on the summation order inside a cell in the fast order -> compared to 1e-10
         sums.append((cs[:6], h.stats()["lost"], h.stats()["added"], vsum))
         h.close()
+    # the chunked pfem2_step_host at this size: four launches of the gathered move pass per step, each with a tile cursor of its own and
+    # groups of four tiles per claim (the small cases of test_gpu_lazy.py take the single-tile form)
+    h = gpu.ParticleHandler2D(dm, 4, capacity_factor=1.2, host_pipeline=4)
+    h.seed_particles()
+    h.init_particle_velocity(F)
+    hf = [t.cpu().pin_memory() for t in F]
+    hw = [torch.zeros_like(t).pin_memory() for t in hf]
+    for _ in range(3):
+        h.step_host(hf[0], hf[1], hw[0], hw[1], dt, 3)
+    sums.append((checksums(h)[:6], h.stats()["lost"], h.stats()["added"], columns(h)["vel"].sum(dim=0).tolist()))
+    assert float((hw[0].cuda() - W[0]).abs().max()) <= 1e-10 and float((hw[1].cuda() - W[1]).abs().max()) <= 1e-10
+    h.close()
     for s in sums[1:]:
         assert s[:3] == sums[0][:3]
         assert all(abs(a - b) <= 1e-10 * max(abs(a), 1.0) for a, b in zip(s[3], sums[0][3]))

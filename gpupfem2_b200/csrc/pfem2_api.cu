@@ -463,15 +463,38 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
             // pfem2_step_host: chunk j of the cell range starts as soon as the slices of the nodal field it can touch have
             // landed (events recorded on the copy stream) and have been interleaved into v2.  The gathered pass moves whole tiles
             // of the sorted order per chunk (k_move_gather)
+            // The nodal slices are interleaved on the main stream as they land; the move chunks alternate between two helper streams
+            // (each behind the packs it needs), so that the first blocks of chunk j + 1 run on the SMs the last blocks of chunk j
+            // have left -- on one stream every chunk boundary cost the tail of one launch plus the head of the next (~30 us, 7
+            // boundaries per step).  The chunks touch disjoint tiles, their counters are atomics, each has its own tile cursor.
             pfem2_handle::HostPipe &pp = h->pipe;
             const int grid = grid_for((long long)h->capacity / pp.K + 1, kAdvThreads, g_num_sms * kAdvBlocksPerSM);
+            static const bool two_streams = !(getenv("PFEM2_PIPE_STREAMS") && atoi(getenv("PFEM2_PIPE_STREAMS")) == 1); // A/B switch
+            if (two_streams && !pp.mv[0]) {
+                for (cudaStream_t &m : pp.mv) CU(cudaStreamCreateWithFlags(&m, cudaStreamNonBlocking));
+                for (cudaEvent_t &e : pp.mv_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
             for (int j = 0; j < pp.K; ++j) {
                 for (; pp.packed_slices <= pp.up_slice[j]; ++pp.packed_slices) {
                     cudaStreamWaitEvent(st, pp.up_ev[pp.packed_slices], 0);
                     launch_pack_nodal(h, pp.ns[pp.packed_slices], pp.ns[pp.packed_slices + 1], vel, pp.packed_slices == 0);
                 }
-                launch_move(h, lazy, hsub, substeps, do_count, grid, h->cell_start[h->cs], pp.cb[j], pp.cb[j + 1]);
+                if (two_streams) {
+                    cudaStream_t m = pp.mv[j & 1];
+                    CU(cudaEventRecord(pp.mv_ev[0], st)); // everything issued on the main stream so far, the packs of this chunk included
+                    CU(cudaStreamWaitEvent(m, pp.mv_ev[0], 0));
+                    h->stream = m;
+                    launch_move(h, lazy, hsub, substeps, do_count, grid, h->cell_start[h->cs], pp.cb[j], pp.cb[j + 1]);
+                    h->stream = st;
+                } else {
+                    launch_move(h, lazy, hsub, substeps, do_count, grid, h->cell_start[h->cs], pp.cb[j], pp.cb[j + 1]);
+                }
             }
+            if (two_streams)
+                for (int k = 0; k < 2; ++k) { // join: the rest of the step follows on the main stream
+                    CU(cudaEventRecord(pp.mv_ev[1 + k], pp.mv[k]));
+                    CU(cudaStreamWaitEvent(st, pp.mv_ev[1 + k], 0));
+                }
             for (; pp.packed_slices < pp.K; ++pp.packed_slices) // (not reached: the last chunk needs every slice)
                 cudaStreamWaitEvent(st, pp.up_ev[pp.packed_slices], 0);
         }
@@ -1082,6 +1105,10 @@ int pfem2_destroy(pfem2_handle *h)
     drop_graphs(h);
     if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
     if (h->pipe.copy) cudaStreamDestroy(h->pipe.copy);
+    for (cudaStream_t m : h->pipe.mv)
+        if (m) cudaStreamDestroy(m);
+    for (cudaEvent_t e : h->pipe.mv_ev)
+        if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->pipe.up_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->pipe.dn_ev) cudaEventDestroy(e);
     for (double *p : h->nodal) cudaFree(p);

@@ -124,6 +124,8 @@ struct pfem2_handle {
         std::vector<int> up_slice;        // chunk j may start once upload slices 0..up_slice[j] have landed
         std::vector<int> dn_ready;        // after projecting chunk j the nodes [0, dn_ready[j]) are final
         cudaStream_t copy = nullptr;      // non-blocking copy stream
+        cudaStream_t mv[2] = {nullptr, nullptr}; // the chunks of the move pass alternate between two streams: the head of chunk j + 1 fills the SMs the tail of chunk j leaves idle
+        cudaEvent_t mv_ev[3] = {nullptr, nullptr, nullptr}; // "packs so far done" (main stream), "chunks done" (the two move streams)
         std::vector<cudaEvent_t> up_ev, dn_ev;
         bool active = false;              // a pipelined step is being issued
         int packed_slices = 0;            // upload slices already interleaved into v2

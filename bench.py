@@ -508,6 +508,10 @@ EXTRAS = (  # BASELINE.json's other headline sizes, nested under "extra" of the 
     ("channel16m_level6", {"workload": "channel16m", "level": 6},
      "configs[3] bracket: 36/cell = 576M particles (BASELINE quotes 32/cell = 512M, not expressible in the reference: levels are squares)"),
     ("stress2m", {"workload": "stress2m", "level": 0}, "configs[4]: high-CFL vortex lattice, 2M triangles PER GPU (weak scaling)"),
+    # north_star names NCCL send/recv for the migration and NCCL for the halo sums; the default transport is NVLink peer memory
+    # without NCCL, so the NCCL form of the same headline workload is measured next to it (multi-GPU launches only)
+    ("channel16m_nccl", {"workload": "channel16m", "level": 0, "protocol": "neighbour"},
+     "the headline workload with the NCCL transport (ncclSend / ncclRecv migration buffers, NCCL halo sums) instead of peer-memory stores"),
 )
 
 
@@ -539,16 +543,27 @@ def run_ours(args):
     extras = {}
     if args.extra and args.workload == "channel16m" and not args.level:
         for name, over, what in EXTRAS:
+            if "protocol" in over and (world == 1 or os.environ.get("PFEM2_MG_PROTOCOL", "p2p") == over["protocol"]):
+                continue
             a = copy.copy(args)
             a.workload, a.level = over["workload"], over["level"]
             a.cfl, a.capacity_factor = 0.25, 1.3  # (channel_params derives the stress case's own values from these defaults)
             a.steps, a.warmup = min(args.steps, 5), 3
+            saved = os.environ.get("PFEM2_MG_PROTOCOL")
+            if "protocol" in over:
+                os.environ["PFEM2_MG_PROTOCOL"] = over["protocol"]
             try:
                 line = measure(a, rank, world, local, full=False)
                 if line:
                     line["what"] = what
             except Exception as e:  # an extra must never take the headline down
                 line = {"error": f"{type(e).__name__}: {e}"[:300], "what": what}
+            finally:
+                if "protocol" in over:
+                    if saved is None:
+                        os.environ.pop("PFEM2_MG_PROTOCOL", None)
+                    else:
+                        os.environ["PFEM2_MG_PROTOCOL"] = saved
             if rank == 0:
                 extras[name] = line
     if rank == 0:

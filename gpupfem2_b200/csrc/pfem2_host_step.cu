@@ -13,6 +13,7 @@
 #include "pfem2_setup.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 using namespace pfem2;
 using namespace pfem2::host;
@@ -96,10 +97,12 @@ int host_pipe_chunks(const pfem2_handle *h, bool strip)
     if (h->opt.host_pipeline > 1) return std::min(h->opt.host_pipeline, 16);
     const long long own = h->own_hi - h->own_lo;
     if (own < (1 << 18)) return 1; // small meshes are launch-bound: one chunk
-    // about 1M cells per chunk, 2..8 chunks (sweep on channel16m, one GPU, uniform chunks: 1 chunk 23.5 ms, 2: 20.3, 4: 19.3, 6: 18.9,
-    // 8: 18.8, 12: 18.7 against 17.8 of device time; tapered since: 8 chunks 14.78 against 14.47): a strip of an 8-GPU run moves
-    // its 2M cells in 1.1 ms and gets two chunks
-    return (int)std::min<long long>(8, std::max<long long>(2, own >> 20));
+    // about 256K cells per chunk, 2..8 chunks.  Sweeps: channel16m on one GPU, uniform chunks: 1 chunk 23.5 ms, 2: 20.3, 4: 19.3, 6: 18.9,
+    // 8: 18.8, 12: 18.7 against 17.8 of device time (tapered since: 8 chunks 14.78 against 14.47).  A strip of an 8-GPU run (2M cells,
+    // 1.9 ms of device time): 2 chunks 3.12 ms, 4: 2.98, 8: 2.88 (the move chunks overlap on two streams, so more chunks cost little
+    // and shorten the first upload / last download slice); PFEM2_PIPE_CELLS_LOG2 overrides the chunk size for A/B runs
+    static const int shift = getenv("PFEM2_PIPE_CELLS_LOG2") ? atoi(getenv("PFEM2_PIPE_CELLS_LOG2")) : 18;
+    return (int)std::min<long long>(8, std::max<long long>(2, own >> shift));
 }
 
 // strip == true: this handle is one strip of a partitioned run with connected P2P inboxes (rank = its index)

@@ -418,7 +418,7 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
     h->last_substeps = substeps;
     const double hsub = dt / substeps; // particle_handler_2d.cu:330, host double
     {   // per-cell scratch of the owned range (+ a few cells for the tolerance-band spill of the occupancy bits).  arrive[] is only
-        // written by the stable order (it stays zero otherwise) and cursor[] is initialised by k_init_cursor
+        // written by the stable order (it stays zero otherwise) and cursor[] is initialised by the plan's scan (PlanEpilogue)
         const size_t lo = (size_t)h->own_lo, len = (size_t)std::min(C, h->own_hi + 4) - lo + 1;
         CU(cudaMemsetAsync(h->stay + lo, 0, sizeof(int) * len, st));
         if (!lazy || h->arrive_dirty) CU(cudaMemsetAsync(h->arrive + lo, 0, sizeof(int) * len, st));
@@ -527,18 +527,16 @@ int advect_move_interior(pfem2_handle *h)
 // advectParticles, second half: distribution check (plan) + re-sort by owning cell + re-seed
 // ------------------------------------------------------------------------------------------------
 // plan: packed[c] = survivors + missing of cell c; scan -> segment starts; count / overflow
-// with_cursor: the cursors of the counting sort / rank pass are initialised too (k_init_cursor, which then also closes the plan)
+// with_cursor: the cursors of the counting sort / rank pass are initialised too (by the scan's epilogue, which also closes the plan)
 static void launch_plan(pfem2_handle *h, bool reseed, bool with_cursor)
 {
     cudaStream_t st = h->stream;
     const int C = h->mesh.n_cells, lo = h->own_lo, hi = h->own_hi, own_n = hi - lo; // cell-wise work only over the owned range
     PFEM2_LAUNCH(k_plan_cells, grid_for(own_n, kThreads, 1 << 30), kThreads, 0, st, C, lo, hi, h->ppc, reseed ? 1 : 0, h->stay, h->arrive,
                  h->cell_mask, h->packed, h->ctr);
-    exclusive_scan_dev<unsigned long long>(h->packed + lo, h->packed + lo, h->own_len_dev, 1, 0, own_n, h->scan_scratch64, st);
-    if (with_cursor)
-        PFEM2_LAUNCH(k_init_cursor, grid_for(std::max(own_n, 1), kThreads, 1 << 30), kThreads, 0, st, lo, hi, h->packed, h->cursor, h->ctr);
-    else
-        PFEM2_LAUNCH(k_plan_finish, 1, 1, 0, st, hi, h->packed, h->ctr);
+    // (the scan's down-sweep also writes the cursors of the counting sort / rank pass and closes the plan: PlanEpilogue)
+    exclusive_scan_dev<unsigned long long, PlanEpilogue>(h->packed + lo, h->packed + lo, h->own_len_dev, 1, 0, own_n, h->scan_scratch64, st,
+                                                         PlanEpilogue{with_cursor ? h->cursor + lo : (int *)nullptr, h->ctr});
 }
 
 // Physical re-sort into the other buffer.  stable: stayers keep their relative order, the movers listed in keys[0]/vals[0]

@@ -397,7 +397,7 @@ k_move_tiles(const __grid_constant__ CUtensorMap tmap, const CellGeom *__restric
 //   advect   k_move_gather          tile j of the SORTED order is gathered through src[] from buffer A (8 x gather4 per 32 records),
 //                                   moved, and stored DENSE to buffer B at rows 32 j .. 32 j + 31 (B = "sorted by the cell of the
 //                                   previous step"); the new cell also goes to the dense key array.
-//            k_plan_cells, scan, k_plan_finish, k_init_cursor      new segment table from the counts (pfem2_resort.cuh)
+//            k_plan_cells, scan (+ PlanEpilogue: cursors, counts)  new segment table from the counts (pfem2_resort.cuh)
 //            k_rank                 slot = cursor[cell]++ (one atomic per (warp, cell) group) ; src_new[slot] = i    (4 + 4 bytes per
 //                                   particle instead of the 128-byte-per-particle scatter)
 //            k_reseed_lazy          new particles are appended behind the array; their rows fill the tail of their cell's src_new range

@@ -73,18 +73,28 @@ k_plan_cells(int n_cells, int own_lo, int own_hi, int ppc, int reseed, const int
     }
 }
 
-static __global__ void k_plan_finish(int own_hi, const unsigned long long *__restrict__ packed_start, Counters *ctr)
-{
-    const unsigned long long t = packed_start[own_hi];
-    const long long total = (long long)(unsigned)(t & 0xffffffffull);
-    ctr->live = (int)total - ctr->added;
-    if (total > ctr->capacity) {
-        ctr->overflow |= 1; // (other bits: migration / P2P watchdog)
-        ctr->count = 0; // nothing valid to iterate over; the host reports PFEM2_ECAPACITY
-    } else {
-        ctr->count = (int)total;
+// Epilogue of the plan's scan (exclusive_scan_dev over packed[own_lo .. own_hi)): the low half of the prefix of cell c is its new
+// segment start -- the cursor of the counting sort / rank pass when `cursor` is given --, the low half of the total closes the plan
+// (live count, new count, overflow flag).  Formerly two kernels of their own behind the scan (k_init_cursor / k_plan_finish).
+struct PlanEpilogue {
+    int *cursor; // nullptr: the stable order has no cursors
+    Counters *ctr;
+    __device__ __forceinline__ void store(int i, unsigned long long x) const
+    {
+        if (cursor) cursor[i] = (int)(unsigned)(x & 0xffffffffull);
     }
-}
+    __device__ __forceinline__ void finish(unsigned long long t) const
+    {
+        const long long total = (long long)(unsigned)(t & 0xffffffffull);
+        ctr->live = (int)total - ctr->added;
+        if (total > ctr->capacity) {
+            ctr->overflow |= 1; // (other bits: migration / P2P watchdog)
+            ctr->count = 0; // nothing valid to iterate over; the host reports PFEM2_ECAPACITY
+        } else {
+            ctr->count = (int)total;
+        }
+    }
+};
 
 __device__ __forceinline__ void copy_particle(const ParticleSoA &src, int s, const ParticleSoA &dst, int d)
 {
@@ -171,25 +181,6 @@ k_scatter_all_quads(ParticleSoA src, ParticleSoA dst, const int *__restrict__ n_
             out[d * 4 + f] = v[u];
         }
     }
-}
-
-// cursor[c] = new segment start of cell c (low half of the scanned plan word), for the fast scatter / the rank pass.
-// finish_ctr != nullptr: thread 0 also closes the plan (k_plan_finish: live count, new count, overflow flag)
-static __global__ void __launch_bounds__(kThreads)
-k_init_cursor(int own_lo, int own_hi, const unsigned long long *__restrict__ packed_start, int *__restrict__ cursor, Counters *finish_ctr)
-{
-    if (finish_ctr && blockIdx.x == 0 && threadIdx.x == 0) {
-        const long long total = (long long)(unsigned)(packed_start[own_hi] & 0xffffffffull);
-        finish_ctr->live = (int)total - finish_ctr->added;
-        if (total > finish_ctr->capacity) {
-            finish_ctr->overflow |= 1;
-            finish_ctr->count = 0; // nothing valid to iterate over; the host reports PFEM2_ECAPACITY
-        } else {
-            finish_ctr->count = (int)total;
-        }
-    }
-    const int c = own_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < own_hi) cursor[c] = (int)(unsigned)(packed_start[c] & 0xffffffffull);
 }
 
 // movers, sorted by new cell (stable: array order within a cell), go right behind the cell's stayers
@@ -293,7 +284,7 @@ k_reseed(int own_lo, int own_hi, int ppc, const double2 *__restrict__ vertices, 
 // ---------------------------------------------------------------------------------------------
 // rank pass: the counting sort's scatter, applied to 4-byte indices instead of 64-byte records.
 // keys[i] = new cell of record i of the (dense) current buffer, i < n_old; cursor[c] starts at the new segment start of cell c
-// (k_init_cursor).  One atomic per (warp, cell) group like k_scatter_all_quads; the order inside a cell is the order of atomic
+// (PlanEpilogue of the plan's scan).  One atomic per (warp, cell) group like k_scatter_all_quads; the order inside a cell is the order of atomic
 // retirement, as in the fast order today.
 // ---------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(kThreads)

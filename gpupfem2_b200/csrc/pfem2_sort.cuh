@@ -108,9 +108,16 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_spine(T *__restrict__ blo
     if (threadIdx.x == 0) block_sums[nb] = carry;
 }
 
-template <class T>
+// Epilogue of the down-sweep: store(i, x) is called with the exclusive prefix x of every element i, finish(total) once with the sum
+// of all elements -- lets a caller derive a second array / close its bookkeeping without another pass (and launch) over the result.
+struct ScanNoEpilogue {
+    template <class T> __device__ __forceinline__ void store(int, T) const {}
+    template <class T> __device__ __forceinline__ void finish(T) const {}
+};
+
+template <class T, class Epi>
 __global__ void __launch_bounds__(kScanThreads)
-k_scan_down(const T *in, const int *__restrict__ n_ptr, int n_mul, int n_add, const T *__restrict__ block_sums, T *out)
+k_scan_down(const T *in, const int *__restrict__ n_ptr, int n_mul, int n_add, const T *__restrict__ block_sums, T *out, Epi epi)
 {
     __shared__ T sm[33];
     const int n = scan_len(n_ptr, n_mul, n_add);
@@ -128,24 +135,31 @@ k_scan_down(const T *in, const int *__restrict__ n_ptr, int n_mul, int n_add, co
         T ex = block_exclusive_scan(s, &total, sm) + block_sums[b];
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
-            if (base + k < n) out[base + k] = ex;
+            if (base + k < n) {
+                out[base + k] = ex;
+                epi.store(base + k, ex);
+            }
             ex += v[k];
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = block_sums[nb]; // total (spine wrote it)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out[n] = block_sums[nb]; // total (spine wrote it)
+        epi.finish(block_sums[nb]);
+    }
 }
 
 template <class T> inline size_t scan_scratch_elems(long long max_n) { return (size_t)((max_n + kScanTile - 1) / kScanTile) + 2; }
 
 // n = *n_ptr * n_mul + n_add elements (device side), at most max_n (host side, sizes scratch and grids).
-template <class T>
-inline void exclusive_scan_dev(const T *in, T *out, const int *n_ptr, int n_mul, int n_add, long long max_n, T *scratch, cudaStream_t st)
+template <class T, class Epi = ScanNoEpilogue>
+inline void exclusive_scan_dev(const T *in, T *out, const int *n_ptr, int n_mul, int n_add, long long max_n, T *scratch, cudaStream_t st,
+                               Epi epi = Epi())
 {
     const long long nb_max = (max_n + kScanTile - 1) / kScanTile;
     const int grid = persistent_grid(nb_max, 8);
     PFEM2_LAUNCH(k_scan_reduce<T>, grid, kScanThreads, 0, st, in, n_ptr, n_mul, n_add, scratch);
     PFEM2_LAUNCH(k_scan_spine<T>, 1, kScanThreads, 0, st, scratch, n_ptr, n_mul, n_add);
-    PFEM2_LAUNCH(k_scan_down<T>, grid, kScanThreads, 0, st, in, n_ptr, n_mul, n_add, scratch, out);
+    PFEM2_LAUNCH((k_scan_down<T, Epi>), grid, kScanThreads, 0, st, in, n_ptr, n_mul, n_add, scratch, out, epi);
 }
 
 // ------------------------------------------------------------------------------------------------

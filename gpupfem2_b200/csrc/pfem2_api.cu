@@ -407,7 +407,8 @@ int advect_move(pfem2_handle *h, NodalVel vel, double dt, int substeps, int do_c
         const long long margin = capacity_margin(h);
         if ((long long)h->host_count + margin > h->capacity) {
             const long long want = std::max<long long>((long long)(1.25 * h->host_count), (long long)h->host_count + 2 * margin);
-            if (want > 2147483647ll - 1024) return fail(h, PFEM2_ECAPACITY, "particle count exceeds 32-bit indexing");
+            // (sorted positions are ints; the move pass looks up to a few tile claims of every warp beyond the count: 2^24 of headroom)
+            if (want > 2147483647ll - (1ll << 24)) return fail(h, PFEM2_ECAPACITY, "particle count exceeds 32-bit indexing");
             if ((rc = materialize(h))) return rc;
             if ((rc = grow(h, (int)want))) return rc;
         }

@@ -223,3 +223,50 @@ def test_tile_claim_index_model():
                 live[rng.integers(len(live))].step(taken)  # an arbitrary interleaving of the warps
             want = list(range(p_lo, n, 32))
             assert sorted(taken) == want, (claim, warps, tiles)
+
+
+def test_reseed_lane_per_particle_index_model():
+    """Index-level model of reseed_cells_of_warp (pfem2_resort.cuh): the new particles of the 32 cells of a warp, one lane per new
+    particle -- owner lane by the kernel's binary search over the inclusive prefix sums, r-th empty sub-cell of the owner's occupancy
+    mask.  Every empty sub-cell of every needy cell must be produced exactly once, in ascending sub-cell order per cell, into the row
+    d(owner) + r and the permutation slot j(owner) + r."""
+    rng = np.random.default_rng(11)
+
+    def nth_set_bit(word, n):  # __fns(word, 0, n + 1)
+        for b in range(32):
+            if (word >> b) & 1:
+                if n == 0:
+                    return b
+                n -= 1
+        raise AssertionError("rank beyond the set bits")
+
+    for ppc in (1, 4, 16, 36, 64):
+        full = (1 << ppc) - 1
+        for _ in range(40):
+            mask = [int(rng.integers(0, 1 << 62)) & full if rng.random() < 0.6 else full for _ in range(32)]
+            missing = [ppc - bin(m).count("1") for m in mask]
+            incl = np.cumsum(missing)
+            total = int(incl[-1])
+            d = [1000 * lane for lane in range(32)]  # first row of the lane's block (any disjoint blocks)
+            j = [64 * lane for lane in range(32)]
+            got = {}
+            for k in range(total):
+                o = 0
+                step = 16
+                while step:  # the kernel's search: smallest o with incl[o] > k
+                    if incl[o + step - 1] <= k:
+                        o += step
+                    step >>= 1
+                o = min(o, 31)
+                r = k - (int(incl[o]) - missing[o])
+                assert 0 <= r < missing[o]
+                empty = ~mask[o] & full
+                lo, hi = empty & 0xffffffff, empty >> 32
+                nlo = bin(lo).count("1")
+                s = nth_set_bit(lo, r) if r < nlo else 32 + nth_set_bit(hi, r - nlo)
+                assert (o, s) not in got
+                got[(o, s)] = (d[o] + r, j[o] + r)
+            for lane in range(32):
+                subs = [s for s in range(ppc) if not (mask[lane] >> s) & 1]
+                assert [got[(lane, s)] for s in subs] == [(d[lane] + r, j[lane] + r) for r in range(len(subs))]
+            assert len(got) == total
